@@ -1,0 +1,464 @@
+"""autograd nodes over the native kernels (everything that is not a conv/linear chain)."""
+import torch
+
+from . import _lib as L
+from . import ops
+
+# ---- random-number state for dropout ------------------------------------------------------------
+# Every dropout site of a forward pass takes a fresh `offset`; (seed, offset) are host integers baked
+# into the launch, and `counter` is an optional device int64 (e.g. the optimizer step) mixed into the
+# seed on the device so that a replayed CUDA graph still draws new masks every step.
+_rng = {"seed": 0x5EED, "offset": 0, "counter": None}
+
+
+def manual_seed(seed):
+    _rng["seed"], _rng["offset"] = int(seed) & (2 ** 63 - 1), 0
+
+
+def set_rng_counter(t):
+    _rng["counter"] = t
+
+
+def next_rng():
+    _rng["offset"] += 1
+    return _rng["seed"], _rng["offset"], _rng["counter"]
+
+
+# ---- layout -------------------------------------------------------------------------------------
+class _TransposeBC(torch.autograd.Function):
+    """[B, R, C] -> [B, C, R] contiguous."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, R, Cc = x.shape
+        return ops.transpose_bc(x.contiguous(), B, R, Cc)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, R = g.shape
+        return ops.transpose_bc(g.contiguous(), B, Cc, R)
+
+
+def to_nhwc(x):
+    """logical NCHW (any strides) -> plain contiguous [N,H,W,C] tensor."""
+    N, Cc, H, W = x.shape
+    if Cc == 1:
+        return x.contiguous().view(N, H, W, 1)
+    if H * W == 1:
+        return x.contiguous().view(N, 1, 1, Cc)
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    return _TransposeBC.apply(x.contiguous().view(N, Cc, H * W)).view(N, H, W, Cc)
+
+
+def from_nhwc(y):
+    """[N,H,W,C] -> logical NCHW (a channels_last view; C == 1 gives a contiguous tensor)."""
+    N, H, W, Cc = y.shape
+    if Cc == 1 or H * W == 1:
+        return y.reshape(N, Cc, H, W)
+    return y.permute(0, 3, 1, 2)
+
+
+def nchw_flatten(x):
+    """x.flatten(1) in NCHW element order for a logical-NCHW tensor (nn.Flatten semantics)."""
+    N, Cc, H, W = x.shape
+    if x.is_contiguous():
+        return x.view(N, -1)
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return _TransposeBC.apply(v.reshape(N, H * W, Cc)).view(N, Cc * H * W)
+    return x.contiguous().view(N, -1)
+
+
+class _CatPad(torch.autograd.Function):
+    """torch.cat(parts, dim=1) into a zero-padded [B, pad4(sum)] buffer (row width a multiple of 4
+    so the GEMM kernels can use 128-bit loads; e.g. 256+12+19 = 287 -> 288)."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        B = parts[0].shape[0]
+        widths = [p.shape[1] for p in parts]
+        total = sum(widths)
+        ld = (total + 3) // 4 * 4
+        out = ops.zeros(B, ld, like=parts[0]) if ld != total else ops.empty(B, ld, like=parts[0])
+        c0 = 0
+        for p, w in zip(parts, widths):
+            pc = p.contiguous()
+            ops.copy_cols(pc, w, 0, out, ld, c0, B, w)
+            c0 += w
+        ctx.widths, ctx.ld = widths, ld
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        B = g.shape[0]
+        outs, c0 = [], 0
+        for i, w in enumerate(ctx.widths):
+            if ctx.needs_input_grad[i]:
+                d = ops.empty(B, w, like=g)
+                ops.copy_cols(g, ctx.ld, c0, d, w, 0, B, w)
+                outs.append(d)
+            else:
+                outs.append(None)
+            c0 += w
+        return tuple(outs)
+
+
+def cat_pad(parts):
+    return _CatPad.apply(*parts)
+
+
+# ---- elementwise ---------------------------------------------------------------------------------
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act, slope):
+        xc = x.contiguous()
+        y = ops.act_fwd(xc, act, slope)
+        ctx.act, ctx.slope = act, slope
+        ctx.save_for_backward(y if act == L.ACT_SIGMOID else xc)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ref,) = ctx.saved_tensors
+        return ops.act_bwd(g.contiguous(), ref, ctx.act, ctx.slope).view(g.shape), None, None
+
+
+def _elementwise_view(x):
+    """A dense tensor in its own memory order (channels_last views stay as they are)."""
+    if x.dim() == 4 and not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1), True
+    return x.contiguous(), False
+
+
+def activation(x, act, slope=0.0):
+    v, perm = _elementwise_view(x)
+    y = _Act.apply(v, act, float(slope))
+    return y.permute(0, 3, 1, 2) if perm else y
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        ctx.p = p
+        ctx.rng = next_rng()
+        seed, off, cnt = ctx.rng
+        return ops.dropout(x.contiguous(), p, seed, off, cnt).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        seed, off, cnt = ctx.rng
+        return ops.dropout(g.contiguous(), ctx.p, seed, off, cnt).view(g.shape), None
+
+
+def dropout(x, p, training):
+    if not training or p == 0.0:
+        return x
+    v, perm = _elementwise_view(x)
+    y = _Dropout.apply(v, float(p))
+    return y.permute(0, 3, 1, 2) if perm else y
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.add(a.contiguous(), b.contiguous()).view(a.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+class _Clamp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lo, hi):
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        L.check(L.lib.cvae_clamp_fwd(L.ptr(xc), L.ptr(y), xc.numel(), lo, hi, L.stream()), "clamp_fwd")
+        ctx.save_for_backward(xc)
+        ctx.lo, ctx.hi = lo, hi
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        dx = torch.empty_like(xc)
+        L.check(L.lib.cvae_clamp_bwd(L.ptr(g.contiguous()), L.ptr(xc), L.ptr(dx), xc.numel(), ctx.lo, ctx.hi,
+                                     L.stream()), "clamp_bwd")
+        return dx, None, None
+
+
+def clamp(x, lo, hi):
+    return _Clamp.apply(x, float(lo), float(hi))
+
+
+# ---- LayerNorm ------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        D = x.shape[-1]
+        if x.dim() == 2 and x.stride(1) == 1 and not x.is_contiguous():
+            xs, rows, xr = x.stride(0), x.shape[0], x            # strided rows (e.g. the CLS slice tok[:, 0])
+        else:
+            xr = x.contiguous()
+            xs, rows = D, xr.numel() // D
+        y, mean, rstd = ops.layernorm_fwd(xr, gamma, beta, rows, D, xs, eps)
+        ctx.save_for_backward(xr, gamma, mean, rstd)
+        ctx.geom = (rows, D, xs)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        xr, gamma, mean, rstd = ctx.saved_tensors
+        rows, D, xs = ctx.geom
+        g = g.contiguous()
+        dx = ops.empty(rows, D, like=g)
+        dgamma, dbeta = ops.zeros(D, like=g), ops.zeros(D, like=g)
+        ops.layernorm_bwd(g, xr, gamma, mean, rstd, rows, D, xs, dx, D, False, dgamma, dbeta)
+        return dx.view(g.shape), dgamma, dbeta, None
+
+
+def layer_norm(x, gamma, beta, eps):
+    return _LayerNorm.apply(x, gamma, beta, float(eps))
+
+
+# ---- attention core --------------------------------------------------------------------------------
+class _AttnCore(torch.autograd.Function):
+    """qkv [B,S,3D] -> softmax(QK^T/sqrt(d)) V merged over heads [B,S,D] (vit_backbone.py:28-30,43)."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, p):
+        B, S, D3 = qkv.shape
+        d = D3 // 3 // H
+        qkv = qkv.contiguous()
+        seed, off, cnt = next_rng() if p > 0 else (0, 0, None)
+        out, probs = ops.attention_fwd(qkv, B, S, H, d, p, seed, off, cnt)
+        ctx.save_for_backward(qkv, probs)
+        ctx.cfg = (B, S, H, d, p, seed, off, cnt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, probs = ctx.saved_tensors
+        B, S, H, d, p, seed, off, cnt = ctx.cfg
+        return ops.attention_bwd(qkv, probs, g.contiguous(), B, S, H, d, p, seed, off, cnt), None, None
+
+
+def attention_core(qkv, heads, p):
+    return _AttnCore.apply(qkv, heads, float(p))
+
+
+# ---- tokens ---------------------------------------------------------------------------------------
+class _Tokens(torch.autograd.Function):
+    """feat NHWC [B,h,w,D] -> tokens [B, h*w+1, D] = cat(cls, feat) + pos[:, :n+1]
+    (vessel_analysis/00_core/models.py:267-271).  NHWC makes `b c h w -> b (h w) c` a no-op."""
+
+    @staticmethod
+    def forward(ctx, feat, cls, pos):
+        B, h, w, D = feat.shape
+        n = h * w
+        tok = ops.empty(B, n + 1, D, like=feat)
+        posc = pos.contiguous()
+        L.check(L.lib.cvae_tokens_fwd(L.ptr(feat.contiguous()), L.ptr(cls), L.ptr(posc), L.ptr(tok), B, n, D,
+                                      L.stream()), "tokens_fwd")
+        ctx.geom = (B, h, w, D, pos.shape[1])
+        return tok
+
+    @staticmethod
+    def backward(ctx, g):
+        B, h, w, D, npos = ctx.geom
+        n = h * w
+        g = g.contiguous()
+        dfeat = ops.empty(B, h, w, D, like=g) if ctx.needs_input_grad[0] else None
+        dcls = ops.empty(1, 1, D, like=g)
+        dpos = ops.zeros(1, npos, D, like=g) if npos != n + 1 else ops.empty(1, npos, D, like=g)
+        L.check(L.lib.cvae_tokens_bwd(L.ptr(g), L.ptr(dfeat), L.ptr(dcls), L.ptr(dpos), B, n, D, L.stream()),
+                "tokens_bwd")
+        return dfeat, dcls, dpos
+
+
+def tokens(feat_nhwc, cls, pos):
+    return _Tokens.apply(feat_nhwc, cls, pos)
+
+
+# ---- latent ---------------------------------------------------------------------------------------
+class _Latent(torch.autograd.Function):
+    """h [B,2Z] -> (mu, logvar, z): chunk, clamp, reparameterise with the given eps
+    (vessel_analysis/00_core/models.py:282-288)."""
+
+    @staticmethod
+    def forward(ctx, h, eps, mu_clamp, lv_clamp):
+        B, Z2 = h.shape
+        Z = Z2 // 2
+        hc, ec = h.contiguous(), eps.contiguous()
+        mu, lv, z = ops.empty(B, Z, like=h), ops.empty(B, Z, like=h), ops.empty(B, Z, like=h)
+        L.check(L.lib.cvae_latent_fwd(L.ptr(hc), L.ptr(ec), L.ptr(mu), L.ptr(lv), L.ptr(z), None, B, Z, mu_clamp,
+                                      lv_clamp, L.stream()), "latent_fwd")
+        ctx.save_for_backward(hc, ec)
+        ctx.cfg = (B, Z, mu_clamp, lv_clamp)
+        return mu, lv, z
+
+    @staticmethod
+    def backward(ctx, dmu, dlv, dz):
+        hc, ec = ctx.saved_tensors
+        B, Z, mc, lc = ctx.cfg
+        dh = torch.empty_like(hc)
+        c = lambda t: None if t is None else t.contiguous()
+        L.check(L.lib.cvae_latent_bwd(L.ptr(hc), L.ptr(ec), L.ptr(c(dz)), L.ptr(c(dmu)), L.ptr(c(dlv)), L.ptr(dh), B,
+                                      Z, mc, lc, L.stream()), "latent_bwd")
+        return dh, None, None, None
+
+
+def latent(h, eps, mu_clamp=0.0, lv_clamp=0.0):
+    return _Latent.apply(h, eps, float(mu_clamp), float(lv_clamp))
+
+
+class _Reparam(torch.autograd.Function):
+    """z = mu + eps * exp(0.5*logvar) for separate mu / logvar tensors (reparameterize())."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        B, Z = mu.shape
+        h = ops.empty(B, 2 * Z, like=mu)
+        ops.copy_cols(mu.contiguous(), Z, 0, h, 2 * Z, 0, B, Z)
+        ops.copy_cols(logvar.contiguous(), Z, 0, h, 2 * Z, Z, B, Z)
+        m2, l2, z = ops.empty(B, Z, like=mu), ops.empty(B, Z, like=mu), ops.empty(B, Z, like=mu)
+        ec = eps.contiguous()
+        L.check(L.lib.cvae_latent_fwd(L.ptr(h), L.ptr(ec), L.ptr(m2), L.ptr(l2), L.ptr(z), None, B, Z, 0.0, 0.0,
+                                      L.stream()), "latent_fwd")
+        ctx.save_for_backward(h, ec)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        h, ec = ctx.saved_tensors
+        B, Z2 = h.shape
+        Z = Z2 // 2
+        dh = torch.empty_like(h)
+        L.check(L.lib.cvae_latent_bwd(L.ptr(h), L.ptr(ec), L.ptr(dz.contiguous()), None, None, L.ptr(dh), B, Z, 0.0,
+                                      0.0, L.stream()), "latent_bwd")
+        dmu, dlv = ops.empty(B, Z, like=h), ops.empty(B, Z, like=h)
+        ops.copy_cols(dh, Z2, 0, dmu, Z, 0, B, Z)
+        ops.copy_cols(dh, Z2, Z, dlv, Z, 0, B, Z)
+        return dmu, dlv, None
+
+
+def reparameterize(mu, logvar, eps=None):
+    if eps is None:
+        eps = torch.randn_like(mu)
+    return _Reparam.apply(mu, logvar, eps)
+
+
+# ---- losses ---------------------------------------------------------------------------------------
+class _VesselRecon(torch.autograd.Function):
+    """(recon_loss, sparsity_loss) of vessel_analysis/01_train/train.py:27-46."""
+
+    @staticmethod
+    def forward(ctx, recon, x):
+        rc, xc = recon.contiguous(), x.contiguous()
+        n = rc.numel()
+        sums = ops.zeros(3, dtype=torch.float64, like=rc)
+        L.check(L.lib.cvae_vessel_xsum(L.ptr(xc), n, L.ptr(sums), L.stream()), "vessel_xsum")
+        L.check(L.lib.cvae_vessel_recon_fwd(L.ptr(rc), L.ptr(xc), n, L.ptr(sums), L.stream()), "vessel_recon_fwd")
+        ctx.save_for_backward(rc, xc, sums)
+        return ops.finish_scalar(sums[1:2]), ops.finish_scalar(sums[2:3])
+
+    @staticmethod
+    def backward(ctx, g_rec, g_sp):
+        rc, xc, sums = ctx.saved_tensors
+        d = torch.empty_like(rc)
+        L.check(L.lib.cvae_vessel_recon_bwd(L.ptr(rc), L.ptr(xc), rc.numel(), L.ptr(sums), L.ptr(g_rec.contiguous()),
+                                            L.ptr(g_sp.contiguous()), L.ptr(d), L.stream()), "vessel_recon_bwd")
+        return d, None
+
+
+def vessel_recon_loss(recon, x):
+    return _VesselRecon.apply(recon, x)
+
+
+class _Kld(torch.autograd.Function):
+    """-0.5 * sum(1 + logvar - mu^2 - exp(logvar))  (train.py:49), scaled by `mul`."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, mul):
+        mc, lc = mu.contiguous(), logvar.contiguous()
+        acc = ops.zeros(1, dtype=torch.float64, like=mc)
+        L.check(L.lib.cvae_kld_fwd(L.ptr(mc), L.ptr(lc), mc.numel(), L.ptr(acc), L.stream()), "kld_fwd")
+        ctx.save_for_backward(mc, lc)
+        ctx.mul = mul
+        return ops.finish_scalar(acc, mul)
+
+    @staticmethod
+    def backward(ctx, g):
+        mc, lc = ctx.saved_tensors
+        dmu, dlv = torch.empty_like(mc), torch.empty_like(lc)
+        L.check(L.lib.cvae_kld_bwd(L.ptr(mc), L.ptr(lc), L.ptr(g.contiguous()), ctx.mul, L.ptr(dmu), L.ptr(dlv),
+                                   mc.numel(), 0, L.stream()), "kld_bwd")
+        return dmu, dlv, None
+
+
+def kld_loss(mu, logvar, mul=1.0):
+    return _Kld.apply(mu, logvar, float(mul))
+
+
+class _GaussNLL(torch.autograd.Function):
+    """0.5 * sum(logvar + (m - mu)^2 / exp(logvar))  (train.py:55-58)."""
+
+    @staticmethod
+    def forward(ctx, m, m_mu, m_logvar):
+        mc, uc, lc = m.contiguous(), m_mu.contiguous(), m_logvar.contiguous()
+        acc = ops.zeros(1, dtype=torch.float64, like=mc)
+        L.check(L.lib.cvae_gauss_nll_fwd(L.ptr(mc), L.ptr(uc), L.ptr(lc), None, L.ptr(acc), mc.numel(), 0.0,
+                                         L.stream()), "gauss_nll_fwd")
+        ctx.save_for_backward(mc, uc, lc)
+        return ops.finish_scalar(acc)
+
+    @staticmethod
+    def backward(ctx, g):
+        mc, uc, lc = ctx.saved_tensors
+        dmu, dlv = torch.empty_like(uc), torch.empty_like(lc)
+        L.check(L.lib.cvae_gauss_nll_bwd(L.ptr(mc), L.ptr(uc), L.ptr(lc), L.ptr(g.contiguous()), 1.0, L.ptr(dmu),
+                                         L.ptr(dlv), mc.numel(), 0.0, L.stream()), "gauss_nll_bwd")
+        return None, dmu, dlv
+
+
+def gauss_nll_loss(m, m_mu, m_logvar):
+    return _GaussNLL.apply(m, m_mu, m_logvar)
+
+
+class _PairLoss(torch.autograd.Function):
+    """sum-reduced squared error (kind 0) or BCE with log clamp -100 (kind 1), times `mul`;
+    gradient w.r.t. the first argument only."""
+
+    @staticmethod
+    def forward(ctx, a, b, kind, mul):
+        ac, bc = a.contiguous(), b.contiguous()
+        acc = ops.zeros(1, dtype=torch.float64, like=ac)
+        fn = L.lib.cvae_mse_fwd if kind == 0 else L.lib.cvae_bce_fwd
+        L.check(fn(L.ptr(ac), L.ptr(bc), ac.numel(), L.ptr(acc), L.stream()), "pair_loss_fwd")
+        ctx.save_for_backward(ac, bc)
+        ctx.kind, ctx.mul = kind, mul
+        return ops.finish_scalar(acc, mul)
+
+    @staticmethod
+    def backward(ctx, g):
+        ac, bc = ctx.saved_tensors
+        da = torch.empty_like(ac)
+        fn = L.lib.cvae_mse_bwd if ctx.kind == 0 else L.lib.cvae_bce_bwd
+        L.check(fn(L.ptr(ac), L.ptr(bc), ac.numel(), L.ptr(g.contiguous()), ctx.mul, L.ptr(da), L.stream()),
+                "pair_loss_bwd")
+        return da, None, None, None
+
+
+def mse_sum(a, b, mul=1.0):
+    return _PairLoss.apply(a, b, 0, float(mul))
+
+
+def bce_sum(p, y, mul=1.0):
+    return _PairLoss.apply(p, y, 1, float(mul))

@@ -1,0 +1,216 @@
+"""Thin Python wrappers over the C ABI (one call = one enqueue on the current CUDA stream).
+
+No autograd here: these functions take and return raw CUDA tensors.  Image activations are plain
+contiguous [N, H, W, C] tensors (NHWC); matrices are [rows, cols].
+"""
+import torch
+
+from . import _lib as L
+
+f32 = torch.float32
+
+
+def empty(*shape, dtype=f32, like=None):
+    dev = like.device if like is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def zeros(*shape, dtype=f32, like=None):
+    dev = like.device if like is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.zeros(shape, dtype=dtype, device=dev)
+
+
+class XF:
+    """Deferred per-channel transform: v*scale[c]+shift[c] then leaky-relu(slope)."""
+    __slots__ = ("scale", "shift", "slope")
+
+    def __init__(self, scale=None, shift=None, slope=1.0):
+        self.scale, self.shift, self.slope = scale, shift, float(slope)
+
+    @property
+    def identity(self):
+        return self.scale is None and self.slope == 1.0
+
+    def c(self):
+        return L.xform(self.scale, self.shift, self.slope)
+
+
+IDENT = XF()
+
+
+def pack_weight(w, A, A_pad, B, taps, src_bat, src_ld):
+    out = empty(taps, A_pad, B, like=w)
+    L.check(L.lib.cvae_pack_weight(L.ptr(w), L.ptr(out), A, A_pad, B, taps, int(src_bat), src_ld, L.stream()),
+            "pack_weight")
+    return out
+
+
+def conv_gather(src, wt, bias, out_hw_c, k, stride, pad, mode, in_x=IDENT, epi=L.EPI_PLAIN, epi_ref=None,
+                epi_add=None, epi_x=IDENT, stats=None, out=None):
+    N, Hs, Ws, Cs = src.shape
+    Hd, Wd, Cd = out_hw_c
+    dst = out if out is not None else empty(N, Hd, Wd, Cd, like=src)
+    p = L.ConvParams(L.ptr(src), L.ptr(wt), L.ptr(bias), L.ptr(dst), in_x.c(), epi, L.ptr(epi_ref),
+                     L.ptr(epi_add), epi_x.c(), L.ptr(stats), N, Hs, Ws, Cs, Hd, Wd, Cd, k, k, stride, pad, mode)
+    L.check(L.lib.cvae_conv_gather(p, L.stream()), f"conv_gather N={N} {Hs}x{Ws}x{Cs}->{Hd}x{Wd}x{Cd} k{k}s{stride} mode{mode}")
+    return dst
+
+
+def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulate=False):
+    """grad_out (torch layout [Cb][Ca_real][k*k]) = sum_pix xa(ga[gather]) (x) xb(db)."""
+    N, Ha, Wa, Ca = ga.shape
+    _, Hq, Wq, Cb = db.shape
+    taps = k * k
+    rows = taps * Ca
+    splits = L.lib.cvae_wgrad_splits(N * Hq * Wq, rows, Cb)
+    partial = empty(splits, rows, Cb, like=ga)
+    p = L.WgradParams(L.ptr(ga), L.ptr(db), xa.c(), xb.c(), L.ptr(partial), splits, N, Ha, Wa, Ca, Hq, Wq, Cb,
+                      k, k, stride, pad)
+    L.check(L.lib.cvae_conv_wgrad(p, L.stream()), f"conv_wgrad {Ha}x{Wa}x{Ca} / {Hq}x{Wq}x{Cb} k{k}s{stride}")
+    L.check(L.lib.cvae_wgrad_reduce(L.ptr(partial), splits, taps, Ca, Ca if ca_real is None else ca_real, Cb,
+                                    L.ptr(grad_out), int(accumulate), L.stream()), "wgrad_reduce")
+    return grad_out
+
+
+def bn_finalize(stats, C, count, bn, train_buffers=True):
+    scale, shift, mean, rstd = (empty(C, like=stats) for _ in range(4))
+    rm = bn.running_mean if (train_buffers and bn.track_running_stats) else None
+    rv = bn.running_var if (train_buffers and bn.track_running_stats) else None
+    nbt = bn.num_batches_tracked if (train_buffers and bn.track_running_stats) else None
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    L.check(L.lib.cvae_bn_finalize(L.ptr(stats), C, float(count), L.ptr(bn.weight), L.ptr(bn.bias), bn.eps, mom,
+                                   L.ptr(rm), L.ptr(rv), L.ptr(nbt), L.ptr(scale), L.ptr(shift), L.ptr(mean),
+                                   L.ptr(rstd), L.stream()), "bn_finalize")
+    return scale, shift, mean, rstd
+
+
+def bn_eval_coeffs(bn):
+    C = bn.num_features
+    scale, shift = empty(C, like=bn.running_mean), empty(C, like=bn.running_mean)
+    L.check(L.lib.cvae_bn_eval_coeffs(L.ptr(bn.running_mean), L.ptr(bn.running_var), L.ptr(bn.weight),
+                                      L.ptr(bn.bias), bn.eps, C, L.ptr(scale), L.ptr(shift), L.stream()),
+            "bn_eval_coeffs")
+    return scale, shift
+
+
+def col_stats(y2d_rows, C, y, stats):
+    L.check(L.lib.cvae_col_stats(L.ptr(y), y2d_rows, C, L.ptr(stats), L.stream()), "col_stats")
+
+
+def bn_bwd_finalize(stats, C, count, gamma, mean, rstd, want_dbias):
+    ca, cb, cc, dg, db = (empty(C, like=mean) for _ in range(5))
+    dbias = empty(C, like=mean) if want_dbias else None
+    L.check(L.lib.cvae_bn_bwd_finalize(L.ptr(stats), C, float(count), L.ptr(gamma), L.ptr(mean), L.ptr(rstd),
+                                       L.ptr(ca), L.ptr(cb), L.ptr(cc), L.ptr(dg), L.ptr(db), L.ptr(dbias),
+                                       L.stream()), "bn_bwd_finalize")
+    return ca, cb, cc, dg, db, dbias
+
+
+def affine_act(a, xa, b=None, xb=IDENT, out=None):
+    C = a.shape[-1]
+    rows = a.numel() // C
+    out = out if out is not None else torch.empty_like(a)
+    L.check(L.lib.cvae_affine_act(L.ptr(a), xa.c(), L.ptr(b), xb.c(), L.ptr(out), rows, C, L.stream()), "affine_act")
+    return out
+
+
+def bn_bwd_apply(dz, y, ca, cb, cc, out=None):
+    C = y.shape[-1]
+    rows = y.numel() // C
+    out = out if out is not None else torch.empty_like(y)
+    L.check(L.lib.cvae_bn_bwd_apply(L.ptr(dz), L.ptr(y), L.ptr(ca), L.ptr(cb), L.ptr(cc), L.ptr(out), rows, C,
+                                    L.stream()), "bn_bwd_apply")
+    return out
+
+
+def dact_stats(g, ref, x, stats):
+    C = ref.shape[-1]
+    rows = ref.numel() // C
+    dz = torch.empty_like(ref)
+    L.check(L.lib.cvae_dact_stats(L.ptr(g), L.ptr(ref), x.c(), L.ptr(dz), L.ptr(stats), rows, C, L.stream()),
+            "dact_stats")
+    return dz
+
+
+def col_sum(x, C, out=None, accumulate=False):
+    rows = x.numel() // C
+    out = out if out is not None else empty(C, like=x)
+    L.check(L.lib.cvae_col_sum(L.ptr(x), rows, C, L.ptr(out), int(accumulate), L.stream()), "col_sum")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, rows, D, row_stride, eps):
+    y = empty(rows, D, like=x)
+    mean, rstd = empty(rows, like=x), empty(rows, like=x)
+    L.check(L.lib.cvae_layernorm_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(mean), L.ptr(rstd), rows,
+                                     D, row_stride, eps, L.stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, rows, D, x_row_stride, dx, dx_row_stride, accumulate_dx, dgamma, dbeta):
+    L.check(L.lib.cvae_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
+                                     L.ptr(dgamma), L.ptr(dbeta), rows, D, x_row_stride, dx_row_stride,
+                                     int(accumulate_dx), L.stream()), "layernorm_bwd")
+
+
+def attention_fwd(qkv, B, S, H, d, p, seed, offset, counter=None):
+    out = empty(B, S, H * d, like=qkv)
+    probs = empty(B, H, S, S, like=qkv)
+    L.check(L.lib.cvae_attention_fwd(L.ptr(qkv), L.ptr(out), L.ptr(probs), B, S, H, d, p, seed, offset, L.ptr(counter),
+                                     L.stream()),
+            f"attention_fwd S={S} d={d}")
+    return out, probs
+
+
+def attention_bwd(qkv, probs, dout, B, S, H, d, p, seed, offset, counter=None):
+    dqkv = torch.empty_like(qkv)
+    L.check(L.lib.cvae_attention_bwd(L.ptr(qkv), L.ptr(probs), L.ptr(dout), L.ptr(dqkv), B, S, H, d, p, seed, offset,
+                                     L.ptr(counter), L.stream()), "attention_bwd")
+    return dqkv
+
+
+def act_fwd(x, act, slope=0.0):
+    y = torch.empty_like(x)
+    L.check(L.lib.cvae_act_fwd(L.ptr(x), L.ptr(y), x.numel(), act, slope, L.stream()), "act_fwd")
+    return y
+
+
+def act_bwd(dy, x, act, slope=0.0):
+    dx = torch.empty_like(x)
+    L.check(L.lib.cvae_act_bwd(L.ptr(dy), L.ptr(x), L.ptr(dx), x.numel(), act, slope, L.stream()), "act_bwd")
+    return dx
+
+
+def add(a, b, out=None):
+    out = out if out is not None else torch.empty_like(a)
+    L.check(L.lib.cvae_add(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), L.stream()), "add")
+    return out
+
+
+def dropout(x, p, seed, offset, counter=None):
+    y = torch.empty_like(x)
+    L.check(L.lib.cvae_dropout(L.ptr(x), L.ptr(y), x.numel(), p, seed, offset, L.ptr(counter), L.stream()), "dropout")
+    return y
+
+
+def transpose_bc(src, B, rows, cols):
+    """[B, rows, cols] -> [B, cols, rows]"""
+    dst = empty(B, cols, rows, like=src)
+    L.check(L.lib.cvae_transpose_bc(L.ptr(src), L.ptr(dst), B, rows, cols, L.stream()), "transpose_bc")
+    return dst
+
+
+def copy_cols(src, src_ld, src_col0, dst, dst_ld, dst_col0, rows, w, accumulate=False):
+    L.check(L.lib.cvae_copy_cols(L.ptr(src), src_ld, src_col0, L.ptr(dst), dst_ld, dst_col0, rows, w,
+                                 int(accumulate), L.stream()), "copy_cols")
+
+
+def fill(t, v):
+    L.check(L.lib.cvae_fill(L.ptr(t), t.numel(), float(v), L.stream()), "fill")
+    return t
+
+
+def finish_scalar(acc, mul=1.0):
+    out = torch.empty((), dtype=f32, device=acc.device)
+    L.check(L.lib.cvae_finish_scalar(L.ptr(acc), float(mul), L.ptr(out), L.stream()), "finish_scalar")
+    return out

@@ -1,0 +1,111 @@
+"""Vessel training step — mirrors vessel_analysis/01_train/train.py:18-98 (loss_function,
+train_one_epoch's inner step) on the native kernels, plus a CUDA-graph-captured whole step."""
+import torch
+
+from .. import functional as F
+from ..optim import FlatParams, FusedClipAdam
+from .models import CONFIG
+
+
+def loss_function(recon_x, x, m_hat, m, mu, logvar, m_mu, m_logvar):
+    """(recon_loss, kld_loss, morph_loss, sparsity_loss) — train.py:18-60.  One fused pass computes
+    the weighted-MSE and sparsity sums (pos_weight from x.sum() on device), one each the KL and the
+    Gaussian NLL; all accumulate in fp64."""
+    recon_loss, sparsity_loss = F.vessel_recon_loss(recon_x, x)
+    kld_loss = F.kld_loss(mu, logvar)
+    morph_loss = F.gauss_nll_loss(m, m_mu, m_logvar)
+    return recon_loss, kld_loss, morph_loss, sparsity_loss
+
+
+def total_loss(recon, kld, morph, sparsity, beta=None, lambda_morph=1.0):
+    """train.py:82 (lambda_morph = 1) / train_kfold.py:71 (lambda_morph = CONFIG['LAMBDA_MORPH'])."""
+    beta = CONFIG["BETA"] if beta is None else beta
+    return recon + beta * kld + lambda_morph * morph + 0.3 * sparsity
+
+
+class VesselTrainer:
+    """fwd + loss + bwd + clip_grad_norm_(5.0) + Adam(lr) for CausalViTVAE (train.py:77-86).
+
+    `step(x, m, t)` runs eagerly; `capture(B)` records the whole step into a CUDA graph over static
+    input buffers so a replay costs one launch (the eager step is ~10^3 small enqueues).  With
+    `world_size > 1` the flat gradient is all-reduced (SUM: every reference loss is sum-reduced, so
+    the sum of shard gradients is the single-device gradient — SURVEY §8(e)) before the clip."""
+
+    def __init__(self, model, lr=None, max_norm=5.0, beta=None, lambda_morph=1.0, process_group=None,
+                 distributed=False):
+        self.model = model
+        self.flat = FlatParams(model)
+        self.opt = FusedClipAdam(self.flat, CONFIG["LEARNING_RATE"] if lr is None else lr, max_norm)
+        self.beta, self.lambda_morph = beta, lambda_morph
+        self.distributed, self.pg = distributed, process_group
+        self.graph = None
+        self.static = None
+        F.set_rng_counter(self.opt.step_count)
+
+    def _fwd_bwd(self, x, m, t, eps):
+        self.opt.zero_grad()
+        out = self.model(x, m, t, eps)
+        recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
+        loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
+        loss.backward()
+        return loss, recon, kld, morph, sp
+
+    def _allreduce(self):
+        if self.distributed:
+            torch.distributed.all_reduce(self.flat.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def step(self, x, m, t, eps=None):
+        self.model.train()
+        losses = self._fwd_bwd(x, m, t, eps)
+        self._allreduce()
+        self.opt.step()
+        return losses
+
+    # ---- CUDA graph ------------------------------------------------------------------------------
+    def capture(self, B, H=None, W=None, warmup=3):
+        H = CONFIG["IMG_HEIGHT"] if H is None else H
+        W = CONFIG["IMG_WIDTH"] if W is None else W
+        dev = self.flat.data.device
+        self.static = dict(
+            x=torch.zeros(B, 1, H, W, device=dev), m=torch.zeros(B, CONFIG["M_DIM"], device=dev),
+            t=torch.zeros(B, CONFIG["T_DIM"], device=dev), eps=torch.zeros(B, CONFIG["Z_DIM"], device=dev))
+        self.static["t"][:, 0] = 1.0
+        self.model.train()
+        snap = (self.flat.data.clone(), {k: v.clone() for k, v in self.model.state_dict().items()})
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._fwd_bwd(**self.static)
+                self._allreduce()
+                self.opt.step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        # undo the warm-up updates (parameters, BN running stats, Adam state)
+        with torch.no_grad():
+            self.flat.data.copy_(snap[0])
+            for k, v in self.model.state_dict().items():
+                if not v.is_floating_point() or k.endswith(("running_mean", "running_var")):
+                    v.copy_(snap[1][k])
+            self.opt.exp_avg.zero_(); self.opt.exp_avg_sq.zero_(); self.opt.step_count.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_losses = self._fwd_bwd(**self.static)
+            self._allreduce()
+            self.opt.step()
+        # the capture pass itself does not execute; nothing to undo
+        return self
+
+    def load_batch(self, x, m, t, eps=None):
+        """host (pinned) or device tensors -> static graph inputs (async H2D on the current stream)."""
+        self.static["x"].copy_(x, non_blocking=True)
+        self.static["m"].copy_(m, non_blocking=True)
+        self.static["t"].copy_(t, non_blocking=True)
+        if eps is not None:
+            self.static["eps"].copy_(eps, non_blocking=True)
+        else:
+            self.static["eps"].normal_()
+
+    def replay(self):
+        self.graph.replay()
+        return self.static_losses

@@ -1,0 +1,86 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/cvae_b200.h declares,
+the drop-in modules expose the reference's state_dict keys (golden tables recorded from the live
+reference), there is no CPU fallback, and the product never imports the oracle."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_header_symbols_exported():
+    from causal_vae_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "cvae_b200.h")).read()
+    declared = set(re.findall(r"^\s*int\s+(cvae_\w+)\s*\(", hdr, flags=re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert _lib.lib.cvae_version() >= 100 and _lib.lib.cvae_built_arch() == 100
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (cvae_\w+)", out))
+    assert declared <= exported
+
+
+def test_sass_is_sm100a():
+    from causal_vae_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_state_dict_keys_match_reference():
+    from causal_vae_b200.vessel import models
+    for tag in ("vessel_64x64_b4", "vessel_256x256_b8"):
+        g = json.load(open(os.path.join(G, tag + ".json")))
+        models.CONFIG["IMG_HEIGHT"], models.CONFIG["IMG_WIDTH"] = g["config"]["H"], g["config"]["W"]
+        sd = models.CausalViTVAE().state_dict()
+        assert {k: list(v.shape) for k, v in sd.items()} == g["state_dict_shapes"]
+        assert list(sd.keys()) == list(g["state_dict_shapes"].keys()), "key order"
+        assert sd["backbone.stem.1.num_batches_tracked"].dtype == torch.int64
+
+
+def test_no_cpu_fallback():
+    from causal_vae_b200 import nn
+    with pytest.raises(RuntimeError, match="CUDA"):
+        nn.Conv2d(1, 8, 3, 2, 1)(torch.zeros(1, 1, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        nn.Sequential(nn.Linear(8, 8), nn.LeakyReLU(0.2))(torch.zeros(2, 8))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "causal_vae_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("oracle/", "").lower() or f == "__init__.py" and False, \
+                    f"{f} mentions the oracle"
+
+
+def test_sequential_fusion_plan():
+    from causal_vae_b200 import nn
+    from causal_vae_b200.chain import ResUnit, Unit
+    seq = nn.Sequential(nn.ConvTranspose2d(8, 8, 3, 2, 1, 1), nn.BatchNorm2d(8), nn.LeakyReLU(), nn.ResBlock(8),
+                        nn.Conv2d(8, 1, 3, padding=1))
+    plan = seq._plan()
+    assert len(plan) == 1 and plan[0][0] == "chain"
+    u = plan[0][1]
+    assert isinstance(u[0], Unit) and u[0].bn is seq[1] and u[0].act == pytest.approx(0.01)
+    assert isinstance(u[1], ResUnit) and u[1].u1.act == pytest.approx(0.2) and u[1].u2.act is None
+    assert isinstance(u[2], Unit) and u[2].bn is None
+    mlp = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Dropout(0.1), nn.Linear(16, 8), nn.Dropout(0.1))
+    kinds = [k for k, _ in mlp._plan()]
+    assert kinds == ["chain", "mod", "mod", "chain", "mod"]

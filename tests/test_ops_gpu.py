@@ -1,0 +1,324 @@
+"""Per-op parity: native sm_100a kernels (through the C ABI / drop-in modules) vs the oracle's
+building blocks evaluated in fp64 on the CPU.  Tolerances: 1e-5 relative on forward values,
+1e-4 on gradients (relative to each tensor's max |value|), as stated by BASELINE north_star."""
+import math
+
+import pytest
+import torch
+
+from oracle import cvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL, GRAD_TOL = 1e-5, 1e-4
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def assert_close(a, b, tol, what):
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    e = rel(a, b)
+    assert e <= tol, f"{what}: rel err {e:.3e} > {tol}"
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def run_pair(mod_gpu, sd, ref_fn, x, train=True, tol_f=FWD_TOL, tol_g=GRAD_TOL, need_dx=True):
+    """Load `sd` into the native module, run fwd/bwd on GPU and `ref_fn(P64, x64)` on CPU fp64."""
+    mod_gpu.load_state_dict(sd)
+    mod_gpu = mod_gpu.cuda()
+    mod_gpu.train(train)
+    xg = x.cuda().requires_grad_(need_dx)
+    y = mod_gpu(xg)
+    P = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    W = O.trainable(P)
+    for v in W.values():
+        v.requires_grad_(True)
+    xr = x.double().requires_grad_(need_dx)
+    yr = ref_fn(P, xr)
+    assert_close(y, yr, tol_f, "forward")
+    gy = gen(*yr.shape, seed=99)
+    y.backward(gy.cuda())
+    yr.backward(gy.double())
+    if need_dx:
+        assert_close(xg.grad, xr.grad, tol_g, "grad input")
+    for k, p in mod_gpu.named_parameters():
+        assert p.grad is not None, f"no grad for {k}"
+        assert_close(p.grad, W[k].grad, tol_g, f"grad {k}")
+    if train:
+        for k, v in mod_gpu.state_dict().items():
+            if k.endswith(("running_mean", "running_var")):
+                assert_close(v, P[k], 1e-5, k)
+            if k.endswith("num_batches_tracked"):
+                assert int(v) == int(P[k]), k
+    return y, yr
+
+
+CONV_CASES = [
+    # Cin, Cout, k, s, p, H, W, B
+    (1, 32, 3, 2, 1, 32, 32, 3),      # stem.0 (thread-per-pixel kernel, Cin = 1)
+    (32, 64, 3, 2, 1, 16, 16, 3),
+    (64, 128, 3, 2, 1, 10, 14, 2),    # ragged tile sizes
+    (16, 1, 3, 1, 1, 20, 24, 2),      # image head (Cout = 1)
+    (16, 16, 3, 1, 1, 12, 12, 2),
+    (32, 64, 4, 2, 1, 14, 14, 3),     # mnist / cascade 4x4 s2
+    (1, 32, 4, 2, 1, 28, 28, 2),
+    (128, 256, 3, 2, 1, 8, 8, 5),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d(case):
+    from causal_vae_b200 import nn
+    Cin, Cout, k, s, p, H, W, B = case
+    sd = O.fill_state_dict({"weight": (Cout, Cin, k, k), "bias": (Cout,)}, seed=1)
+    x = gen(B, Cin, H, W, seed=2)
+    run_pair(nn.Conv2d(Cin, Cout, k, s, p), sd, lambda P, xx: O._conv({"c.weight": P["weight"], "c.bias": P["bias"]}, "c", xx, s, p), x)
+
+
+CONVT_CASES = [
+    # Cin, Cout, k, s, p, op, H, W, B
+    (256, 128, 3, 2, 1, 1, 4, 4, 3),
+    (32, 16, 3, 2, 1, 1, 16, 12, 2),
+    (16, 16, 3, 2, 1, 1, 16, 16, 2),
+    (64, 32, 4, 2, 1, 0, 7, 7, 3),    # mnist dec_conv.0
+    (32, 1, 4, 2, 1, 0, 14, 14, 3),   # mnist dec_conv.2 (Cout = 1)
+]
+
+
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transpose2d(case):
+    from causal_vae_b200 import nn
+    Cin, Cout, k, s, p, op, H, W, B = case
+    sd = O.fill_state_dict({"weight": (Cin, Cout, k, k), "bias": (Cout,)}, seed=3)
+    x = gen(B, Cin, H, W, seed=4)
+    run_pair(nn.ConvTranspose2d(Cin, Cout, k, s, p, op), sd,
+             lambda P, xx: O._convT({"c.weight": P["weight"], "c.bias": P["bias"]}, "c", xx, s, p, op), x)
+
+
+@pytest.mark.parametrize("shape", [(64, 287, 512), (7, 19, 64), (130, 256, 768), (5, 512, 1024), (64, 64, 12)])
+def test_linear(shape):
+    from causal_vae_b200 import nn
+    B, K, N = shape
+    sd = O.fill_state_dict({"weight": (N, K), "bias": (N,)}, seed=5)
+    x = gen(B, K, seed=6)
+    run_pair(nn.Linear(K, N), sd, lambda P, xx: O._lin({"l.weight": P["weight"], "l.bias": P["bias"]}, "l", xx), x)
+
+
+def test_stem_like_chain_train():
+    """Conv-BN-LReLU x3 in training mode: fused statistics epilogue + deferred normalise."""
+    from causal_vae_b200 import nn
+    seq = nn.Sequential(nn.Conv2d(1, 32, 3, 2, 1), nn.BatchNorm2d(32), nn.LeakyReLU(),
+                        nn.Conv2d(32, 64, 3, 2, 1), nn.BatchNorm2d(64), nn.LeakyReLU(),
+                        nn.Conv2d(64, 128, 3, 2, 1), nn.BatchNorm2d(128), nn.LeakyReLU())
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in seq.state_dict().items()}, seed=7)
+    x = (gen(4, 1, 32, 32, seed=8) > 0.8).float()
+
+    def ref(P, xx):
+        h = xx
+        for i in range(3):
+            h = torch.nn.functional.leaky_relu(O._bn(P, f"{3 * i + 1}", O._conv(P, f"{3 * i}", h, 2, 1), True), 0.01)
+        return h
+    run_pair(seq, sd, ref, x, need_dx=False)
+
+
+def test_decoder_like_chain_train():
+    """ConvT-BN-LReLU + ResBlock + ConvT-BN-LReLU + Conv head."""
+    from causal_vae_b200 import nn
+    seq = nn.Sequential(nn.ConvTranspose2d(64, 32, 3, 2, 1, 1), nn.BatchNorm2d(32), nn.LeakyReLU(), nn.ResBlock(32),
+                        nn.ConvTranspose2d(32, 16, 3, 2, 1, 1), nn.BatchNorm2d(16), nn.LeakyReLU(),
+                        nn.Conv2d(16, 1, 3, padding=1))
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in seq.state_dict().items()}, seed=9)
+    x = gen(3, 64, 6, 6, seed=10)
+
+    def ref(P, xx):
+        lr = torch.nn.functional.leaky_relu
+        h = lr(O._bn(P, "1", O._convT(P, "0", xx, 2, 1, 1), True), 0.01)
+        h = O._resblock(P, "3", h, True)
+        h = lr(O._bn(P, "5", O._convT(P, "4", h, 2, 1, 1), True), 0.01)
+        return O._conv(P, "7", h, 1, 1)
+    run_pair(seq, sd, ref, x)
+
+
+def test_chain_eval_mode_forward():
+    from causal_vae_b200 import nn
+    seq = nn.Sequential(nn.ConvTranspose2d(32, 16, 3, 2, 1, 1), nn.BatchNorm2d(16), nn.LeakyReLU(), nn.ResBlock(16),
+                        nn.Conv2d(16, 1, 3, padding=1))
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in seq.state_dict().items()}, seed=11)
+    seq.load_state_dict(sd)
+    seq = seq.cuda().eval()
+    x = gen(2, 32, 5, 7, seed=12)
+    with torch.no_grad():
+        y = seq(x.cuda())
+    P = {k: v.double() if v.is_floating_point() else v for k, v in sd.items()}
+    lr = torch.nn.functional.leaky_relu
+    h = lr(O._bn(P, "1", O._convT(P, "0", x.double(), 2, 1, 1), False), 0.01)
+    h = O._resblock(P, "3", h, False)
+    assert_close(y, O._conv(P, "4", h, 1, 1), FWD_TOL, "eval chain")
+
+
+def test_adapter_chain_train():
+    """Linear -> BatchNorm1d -> LeakyReLU(0.2) -> Linear on an unaligned (287-wide) input."""
+    from causal_vae_b200 import nn
+    seq = nn.Sequential(nn.Linear(287, 512), nn.BatchNorm1d(512), nn.LeakyReLU(0.2), nn.Linear(512, 256))
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in seq.state_dict().items()}, seed=13)
+    x = gen(16, 287, seed=14)
+
+    def ref(P, xx):
+        h = torch.nn.functional.leaky_relu(O._bn(P, "1", O._lin(P, "0", xx), True), 0.2)
+        return O._lin(P, "3", h)
+    run_pair(seq, sd, ref, x)
+
+
+def test_mlp_relu_sigmoid_chains():
+    from causal_vae_b200 import nn
+    seq = nn.Sequential(nn.ConvTranspose2d(64, 32, 4, 2, 1), nn.ReLU(), nn.ConvTranspose2d(32, 1, 4, 2, 1), nn.Sigmoid())
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in seq.state_dict().items()}, seed=15)
+    x = gen(3, 64, 7, 7, seed=16)
+
+    def ref(P, xx):
+        h = torch.relu(O._convT(P, "0", xx, 2, 1, 0))
+        return torch.sigmoid(O._convT(P, "2", h, 2, 1, 0))
+    run_pair(seq, sd, ref, x)
+
+
+def test_layernorm_and_strided_rows():
+    from causal_vae_b200 import nn
+    ln = nn.LayerNorm(256)
+    sd = O.fill_state_dict({"weight": (256,), "bias": (256,)}, seed=17)
+    x = gen(6, 9, 256, seed=18)
+    run_pair(ln, sd, lambda P, xx: O._ln({"n.weight": P["weight"], "n.bias": P["bias"]}, "n", xx), x)
+    # CLS-row slice (row stride S*D)
+    ln.load_state_dict(sd)
+    ln = ln.cuda()
+    tok = x.cuda()
+    y = ln(tok[:, 0])
+    yr = O._ln({"n.weight": sd["weight"].double(), "n.bias": sd["bias"].double()}, "n", x.double()[:, 0])
+    assert_close(y, yr, FWD_TOL, "cls layernorm")
+
+
+@pytest.mark.parametrize("S", [5, 17, 65])
+def test_vit_block(S):
+    from causal_vae_b200.vessel.vit_backbone import ViTBlock
+    blk = ViTBlock(256, 8, 512)
+    for mod in blk.modules():
+        if hasattr(mod, "p") and isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    blk.attn.dropout = 0.0
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=19)
+    x = gen(3, S, 256, seed=20)
+    run_pair(blk, sd, lambda P, xx: O.vit_block({"b." + k: v for k, v in P.items()}, "b", xx), x, tol_g=2e-4)
+
+
+def test_tokens_latent_losses():
+    from causal_vae_b200 import functional as F
+    B, h, w, D, Z = 3, 2, 3, 256, 128
+    feat = gen(B, h, w, D, seed=21)
+    cls, pos = gen(1, 1, D, seed=22), gen(1, h * w + 1, D, seed=23)
+    fg, cg, pg = (t.cuda().requires_grad_(True) for t in (feat, cls, pos))
+    tok = F.tokens(fg, cg, pg)
+    fr, cr, pr = (t.double().requires_grad_(True) for t in (feat, cls, pos))
+    tr = O.vit_tokens({"b.cls_token": cr, "b.pos_embedding": pr}, "b", fr.permute(0, 3, 1, 2))
+    assert_close(tok, tr, FWD_TOL, "tokens")
+    g = gen(*tr.shape, seed=24)
+    tok.backward(g.cuda()); tr.backward(g.double())
+    assert_close(fg.grad, fr.grad, GRAD_TOL, "dfeat"); assert_close(cg.grad, cr.grad, GRAD_TOL, "dcls")
+    assert_close(pg.grad, pr.grad, GRAD_TOL, "dpos")
+
+    hh = gen(B, 2 * Z, seed=25, scale=4.0)
+    hh[0, 3] = 150.0; hh[1, Z + 5] = 12.0; hh[2, Z + 7] = -11.0     # hit every clamp
+    eps = gen(B, Z, seed=26)
+    hg = hh.cuda().requires_grad_(True)
+    mu, lv, z = F.latent(hg, eps.cuda(), 100.0, 10.0)
+    hr = hh.double().requires_grad_(True)
+    mur, lvr = hr.chunk(2, dim=1)
+    mur, lvr = torch.clamp(mur, -100, 100), torch.clamp(lvr, -10, 10)
+    zr = O.reparameterize(mur, lvr, eps.double())
+    for a, b, n in ((mu, mur, "mu"), (lv, lvr, "logvar"), (z, zr, "z")):
+        assert_close(a, b, FWD_TOL, n)
+    kl = F.kld_loss(mu, lv)
+    klr = -0.5 * torch.sum(1 + lvr - mur.pow(2) - lvr.exp())
+    assert_close(kl, klr, FWD_TOL, "kld")
+    gz = gen(B, Z, seed=27)
+    (kl * 0.5 + (z * gz.cuda()).sum()).backward()
+    (klr * 0.5 + (zr * gz.double()).sum()).backward()
+    assert_close(hg.grad, hr.grad, GRAD_TOL, "dh latent")
+
+    # vessel reconstruction / sparsity / gaussian nll
+    x = (gen(2, 1, 32, 48, seed=28) > 0.8).float()
+    r = gen(2, 1, 32, 48, seed=29)
+    r[0, 0, 0, :5] = 0.0
+    m, mm, ml = gen(2, 12, seed=30), gen(2, 12, seed=31), gen(2, 12, seed=32)
+    rg, mmg, mlg = (t.cuda().requires_grad_(True) for t in (r, mm, ml))
+    rec, sp = F.vessel_recon_loss(rg, x.cuda())
+    nll = F.gauss_nll_loss(m.cuda(), mmg, mlg)
+    rr, mmr, mlr = (t.double().requires_grad_(True) for t in (r, mm, ml))
+    recr, _, nllr, spr = O.vessel_loss(rr, x.double(), None, m.double(), torch.zeros(1), torch.zeros(1), mmr, mlr)
+    assert_close(rec, recr, FWD_TOL, "recon"); assert_close(sp, spr, FWD_TOL, "sparsity")
+    assert_close(nll, nllr, FWD_TOL, "nll")
+    (rec + 0.3 * sp + nll).backward(); (recr + 0.3 * spr + nllr).backward()
+    assert_close(rg.grad, rr.grad, GRAD_TOL, "d recon"); assert_close(mmg.grad, mmr.grad, GRAD_TOL, "d m_mu")
+    assert_close(mlg.grad, mlr.grad, GRAD_TOL, "d m_logvar")
+
+    p = torch.sigmoid(gen(4, 784, seed=33)); y = torch.rand(4, 784, generator=torch.Generator().manual_seed(34))
+    p[0, 0] = 0.0; p[0, 1] = 1.0
+    pg2 = p.cuda().requires_grad_(True)
+    b = F.bce_sum(pg2, y.cuda())
+    pr2 = p.double().requires_grad_(True)
+    br = O.bce_sum(pr2, y.double())
+    assert_close(b, br, FWD_TOL, "bce")
+    ms = F.mse_sum(pg2, y.cuda(), 2000.0)
+    assert_close(ms, 2000.0 * ((p.double() - y.double()) ** 2).sum(), FWD_TOL, "mse")
+
+
+def test_fused_clip_adam_matches_oracle():
+    from causal_vae_b200.optim import FlatParams, FusedClipAdam
+    mod = torch.nn.ModuleDict({"a": torch.nn.Linear(37, 19), "b": torch.nn.Linear(19, 5)}).cuda()
+    flat = FlatParams(mod)
+    opt = FusedClipAdam(flat, lr=1e-3, max_norm=5.0)
+    P = {k: v.detach().cpu().clone() for k, v in mod.named_parameters()}
+    state = {}
+    for step in range(1, 4):
+        grads = {k: gen(*v.shape, seed=40 + step, scale=3.0) for k, v in P.items()}
+        opt.zero_grad()
+        for k, p in mod.named_parameters():
+            p.grad.copy_(grads[k].cuda())
+        opt.step()
+        clipped, total = O.clip_grad_norm({k: g.clone() for k, g in grads.items()}, 5.0)
+        O.adam_step(P, clipped, state, step, 1e-3)
+        assert abs(opt.grad_norm().item() - total.item()) <= 1e-5 * total.item()
+        for k, p in mod.named_parameters():
+            assert_close(p, P[k], 1e-5, f"step{step} {k}")
+
+
+def test_dropout_statistics():
+    from causal_vae_b200 import functional as F
+    x = torch.ones(1 << 20, device="cuda", requires_grad=True)
+    F.manual_seed(1234)
+    y = F.dropout(x, 0.1, True)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - 0.9) < 3e-3
+    assert abs(y.max().item() - 1.0 / 0.9) < 1e-6
+    y.sum().backward()
+    assert torch.equal((x.grad != 0), (y != 0)), "backward must regenerate the same mask"
+
+
+def test_counterfactual_helpers():
+    from causal_vae_b200.counterfactual import do_expand, rowdiff_l2
+    S, K, Z = 5, 12, 128
+    m, z = gen(S, K, seed=50), gen(S, Z, seed=51)
+    out = do_expand(m.cuda(), z.cuda(), delta=5.0).cpu()
+    for s in range(S):
+        for k in range(K):
+            ref = torch.cat([O.counterfactual_do(m[s:s + 1], k, delta=5.0), z[s:s + 1]], dim=1)[0]
+            assert torch.equal(out[s * K + k], ref)          # index / scatter work is bit-exact
+    a, b = gen(S * K, 1, 16, 16, seed=52), gen(S, 1, 16, 16, seed=53)
+    d = rowdiff_l2(a.cuda(), b.cuda(), K).cpu()
+    ref = (a.view(S, K, -1) - b.view(S, 1, -1)).double().norm(dim=2).view(-1)
+    assert_close(d, ref, 1e-5, "rowdiff")

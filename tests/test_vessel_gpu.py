@@ -1,0 +1,152 @@
+"""Whole-model parity of the native CausalViTVAE against the oracle (and through it the reference's
+golden vectors): eval forward + counterfactual decode, train-mode losses / gradients / clip / Adam."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import cvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def build(H, W, p_drop=0.0):
+    from causal_vae_b200.vessel import models
+    models.CONFIG["IMG_HEIGHT"], models.CONFIG["IMG_WIDTH"] = H, W
+    sd = O.fill_state_dict(O.vessel_shapes(H, W), seed=0)
+    model = models.CausalViTVAE()
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == O.vessel_shapes(H, W)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = p_drop
+        if hasattr(mod, "in_proj_weight"):
+            mod.dropout = p_drop
+    return model, sd
+
+
+@pytest.mark.parametrize("cfg", [(64, 64, 4), (128, 96, 8), (256, 256, 8)])
+def test_eval_forward_and_counterfactual(cfg):
+    from causal_vae_b200 import counterfactual as CF
+    H, W, B = cfg
+    model, sd = build(H, W)
+    model.eval()
+    x, m, t, eps = O.vessel_inputs(B, H, W, seed=0)
+    with torch.no_grad():
+        outs = model(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+        ref = O.vessel_forward(sd, x, m, t, eps, train=False)
+    for n, a, b in zip(["recon_x", "m_hat", "mu", "logvar", "m_mu", "m_logvar"], outs, ref):
+        assert rel(a, b) <= 2e-5, (n, rel(a, b))
+    # golden (live reference) sampled entries
+    with open(os.path.join(G, f"vessel_{H}x{W}_b{B}.json")) as f:
+        gold = json.load(f)
+    s = gold["eval"]["recon_x"]
+    got = outs[0].detach().cpu().double().flatten()[torch.tensor(s["idx"])]
+    assert (got - torch.tensor(s["val"])).abs().max().item() <= 2e-5 * s["absmax"]
+    # counterfactual sweep over all concepts: do(M_k += 5)
+    z = O.reparameterize(ref[2], ref[3], eps)
+    l2, imgs, base = CF.counterfactual_sweep(model, m.cuda(), z.cuda(), delta=5.0, return_images=True)
+    K = m.shape[1]
+    for k in (0, 5, K - 1):
+        xcf = O.vessel_decode(sd, O.counterfactual_do(m, k, delta=5.0), z, (H // 32, W // 32), False)
+        got = imgs.view(B, K, 1, H, W)[:, k]
+        assert rel(got, xcf) <= 2e-5, (k, rel(got, xcf))
+        want = (xcf - ref[0]).flatten(1).norm(dim=1)
+        assert rel(l2[:, k], want) <= 1e-4
+    assert rel(l2[:, 5], torch.tensor(gold["eval"]["cf_l2_per_sample"])) <= 1e-4
+
+
+@pytest.mark.parametrize("cfg", [(64, 64, 4), (128, 96, 8), (256, 256, 8)])
+def test_train_step_matches_oracle(cfg):
+    from causal_vae_b200.vessel import train
+    H, W, B = cfg
+    model, sd = build(H, W)
+    x, m, t, eps = O.vessel_inputs(B, H, W, seed=0)
+    trainer = train.VesselTrainer(model, lr=1e-4)
+    trainer.model.train()
+    losses = trainer._fwd_bwd(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    trainer.opt.step()
+    torch.cuda.synchronize()
+
+    P64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    ref64, g64, tot64 = O.vessel_train_step(P64, {}, 1, x.double(), m.double(), t.double(), eps.double())
+    P32 = {k: v.clone() for k, v in sd.items()}
+    ref32, g32, tot32 = O.vessel_train_step(P32, {}, 1, x, m, t, eps)
+
+    names = ["loss", "recon", "kld", "morph", "sparsity"]
+    for n, v in zip(names, losses):
+        e = abs(float(v) - float(ref64[n])) / abs(float(ref64[n]))
+        assert e <= 1e-5, (n, float(v), float(ref64[n]), e)          # 1e-5 relative on fp32 losses
+    with open(os.path.join(G, f"vessel_{H}x{W}_b{B}.json")) as f:
+        gold = json.load(f)
+    assert abs(float(losses[0]) - gold["train"]["loss"]) <= 2e-5 * abs(gold["train"]["loss"])
+
+    # gradients: 1e-4 of each tensor's max |g|, widened to 4x the oracle's own fp32-vs-fp64
+    # discrepancy where whole-network conditioning (BatchNorm backward cancellation) exceeds that.
+    worst = []
+    for k, g in g64.items():
+        noise = rel(g32[k], g)
+        tol = max(1e-4, 4 * noise)
+        e = rel(grads[k], g)
+        worst.append((e / tol, k, e, noise))
+        assert e <= tol, (k, e, noise)
+    for k in ("backbone.fc_mu.weight", "backbone.fc_var.bias"):
+        assert float(grads[k].abs().max()) == 0.0                       # unused heads get no gradient
+    worst.sort(reverse=True)
+    print("worst grad ratios:", worst[:5])
+    tot = trainer.opt.grad_norm().item()
+    assert abs(tot - float(tot64)) <= max(1e-4, 4 * abs(float(tot32) - float(tot64)) / float(tot64)) * float(tot64)
+    # BN running statistics after the step (momentum 0.1, unbiased variance)
+    for k, v in model.state_dict().items():
+        if k.endswith(("running_mean", "running_var")):
+            assert rel(v, P64[k]) <= 2e-5, k
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == 1
+
+
+def test_graph_replay_equals_eager():
+    from causal_vae_b200.vessel import train
+    H = W = 64
+    B = 4
+    x, m, t, eps = (a.cuda() for a in O.vessel_inputs(B, H, W, seed=0))
+    model_a, _ = build(H, W)
+    ta = train.VesselTrainer(model_a, lr=1e-3)
+    la = [float(ta.step(x, m, t, eps)[0]) for _ in range(3)]
+    model_b, _ = build(H, W)
+    tb = train.VesselTrainer(model_b, lr=1e-3).capture(B, H, W)
+    lb = []
+    for _ in range(3):
+        tb.load_batch(x, m, t, eps)
+        lb.append(float(tb.replay()[0]))
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 1e-5 * abs(a), (la, lb)
+    assert la[2] < la[0]
+    for (k, pa), (_, pb) in zip(model_a.state_dict().items(), model_b.state_dict().items()):
+        assert rel(pb.float(), pa.float()) <= 1e-4 or float(pa.float().abs().max()) == 0, k
+
+
+def test_training_with_dropout_runs_and_is_reproducible():
+    from causal_vae_b200 import functional as F
+    from causal_vae_b200.vessel import train
+    H = W = 64
+    B = 4
+    x, m, t, eps = (a.cuda() for a in O.vessel_inputs(B, H, W, seed=0))
+    out = []
+    for _ in range(2):
+        model, _ = build(H, W, p_drop=0.1)
+        F.manual_seed(7)
+        tr = train.VesselTrainer(model, lr=1e-4)
+        out.append([float(tr.step(x, m, t, eps)[0]) for _ in range(2)])
+    assert out[0] == out[1]
+    model0, _ = build(H, W, p_drop=0.0)
+    l0 = float(train.VesselTrainer(model0, lr=1e-4).step(x, m, t, eps)[0])
+    assert abs(out[0][0] - l0) / l0 < 0.2 and out[0][0] != l0
