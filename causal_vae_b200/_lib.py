@@ -22,7 +22,7 @@ vp, f32, i32, i64, u64, f64 = C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_uin
 
 
 class Xform(C.Structure):
-    _fields_ = [("scale", vp), ("shift", vp), ("slope", f32)]
+    _fields_ = [("scale", vp), ("shift", vp), ("center", vp), ("slope", f32)]
 
 
 class ConvParams(C.Structure):
@@ -55,7 +55,7 @@ _SIGS = {
     "cvae_col_stats": [vp, i64, i32, vp, vp],
     "cvae_bn_bwd_finalize": [vp, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "cvae_affine_act": [vp, Xform, vp, Xform, vp, i64, i32, vp],
-    "cvae_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, i64, i32, vp],
+    "cvae_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "cvae_dact_stats": [vp, vp, Xform, vp, vp, i64, i32, vp],
     "cvae_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, f32, vp],
     "cvae_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i32, vp],
@@ -125,5 +125,5 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def xform(scale=None, shift=None, slope=1.0):
-    return Xform(ptr(scale), ptr(shift), float(slope))
+def xform(scale=None, shift=None, slope=1.0, center=None):
+    return Xform(ptr(scale), ptr(shift), ptr(center), float(slope))

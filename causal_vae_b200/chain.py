@@ -110,7 +110,7 @@ def _unit_fwd(u, S, train, keep):
                                                                train_buffers=u.bn.training)
         else:
             scale, shift = ops.bn_eval_coeffs(u.bn)
-        out = State(y, XF(scale, shift, slope))
+        out = State(y, XF(scale, shift, slope, rec.mean if bn_train else u.bn.running_mean))
     elif isinstance(u.act, float):
         out = State(y, XF(None, None, slope))
     elif u.act == "sigmoid":
@@ -158,7 +158,7 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
             raise NotImplementedError("backward through eval-mode BatchNorm is not supported")
         ca, cb, cc, dgamma, dbeta, dbias = ops.bn_bwd_finalize(stats, Cd, N * Hd * Wd, u.bn.weight, rec.mean,
                                                                rec.rstd, has_bias)
-        dy = ops.bn_bwd_apply(dz, y, ca, cb, cc)
+        dy = ops.bn_bwd_apply(dz, y, ca, cb, cc, rec.mean)
     else:
         dy = dz
         dgamma = dbeta = None
@@ -191,7 +191,7 @@ def _entry(chain, recs, i):
         return r.S_out, e
     # ResUnit: r = T2(y2) + skip; d r / d T2 = 1 -> slope-1 entry on y2 so the consumer gathers BN2's sums
     r2 = r[1]
-    return State(r2.y, XF(r2.S_out.x.scale, r2.S_out.x.shift, 1.0)), e.u2
+    return State(r2.y, XF(r2.S_out.x.scale, r2.S_out.x.shift, 1.0, r2.S_out.x.center)), e.u2
 
 
 def chain_backward(chain, recs, final, gout, need_dx, grad_cols=None):

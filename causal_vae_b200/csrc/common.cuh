@@ -23,6 +23,7 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 struct XformDev {
   const float* scale;
   const float* shift;
+  const float* center;
   float slope;
   bool affine;
   bool act;

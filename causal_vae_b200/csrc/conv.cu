@@ -18,9 +18,9 @@ struct PhaseGeom { int ph, pw, Hq, Wq, ntaps; TapEntry taps[16]; };
 
 struct GatherArgs {
   const float* src; const float* wt; const float* bias; float* dst;
-  const float* in_scale; const float* in_shift; float in_slope; int in_affine; int in_act;
+  const float* in_scale; const float* in_shift; const float* in_center; float in_slope; int in_affine; int in_act;
   int epi; const float* epi_ref; const float* epi_add;
-  const float* e_scale; const float* e_shift; float e_slope; int e_affine;
+  const float* e_scale; const float* e_shift; const float* e_center; float e_slope; int e_affine;
   double* stats;
   int N, Hs, Ws, Cs, Hd, Wd, Cd;
   int os, is, wtaps, nphase;
@@ -79,6 +79,10 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
         if (a.in_affine) {
           const float4 sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c));
           const float4 sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c));
+          if (a.in_center != nullptr) {
+            const float4 ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c));
+            v.x -= ce.x; v.y -= ce.y; v.z -= ce.z; v.w -= ce.w;
+          }
           v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
           v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         }
@@ -145,16 +149,19 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
   // ---------------- epilogue ----------------
   const int cbase = n0 + tx * TN;
   const bool col_ok = cbase < a.Cd;
-  float bias[TN], esc[TN], esh[TN];
+  float bias[TN], esc[TN], esh[TN], ece[TN];
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     bias[j] = (a.bias != nullptr && col_ok) ? __ldg(a.bias + cbase + j) : 0.f;
     esc[j] = (a.e_affine && col_ok) ? __ldg(a.e_scale + cbase + j) : 1.f;
     esh[j] = (a.e_affine && col_ok) ? __ldg(a.e_shift + cbase + j) : 0.f;
+    ece[j] = (a.e_affine && a.e_center != nullptr && col_ok) ? __ldg(a.e_center + cbase + j) : 0.f;
   }
-  float s1[TN], s2[TN];
+  // per-thread statistics in double: fp32 products are exact in double, so E[y^2] - mean^2 keeps
+  // two-pass accuracy even for channels with |mean| >> std
+  double s1[TN], s2[TN];
 #pragma unroll
-  for (int j = 0; j < TN; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int j = 0; j < TN; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
 
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -168,15 +175,15 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
     for (int j = 0; j < TN; ++j) v[j] = acc[i][j] + bias[j];
     if (a.epi == CVAE_EPI_STATS) {
 #pragma unroll
-      for (int j = 0; j < TN; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+      for (int j = 0; j < TN; ++j) { s1[j] += (double)v[j]; s2[j] += (double)v[j] * (double)v[j]; }
     } else if (a.epi == CVAE_EPI_DACT) {
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
-        const float ref = __ldg(a.epi_ref + off + j);
+        const float refc = __ldg(a.epi_ref + off + j) - ece[j];
         if (a.epi_add != nullptr) v[j] += __ldg(a.epi_add + off + j);
-        const float z = fmaf(ref, esc[j], esh[j]);
+        const float z = fmaf(refc, esc[j], esh[j]);
         v[j] = z > 0.f ? v[j] : v[j] * a.e_slope;
-        s1[j] += v[j]; s2[j] = fmaf(v[j], ref, s2[j]);
+        s1[j] += (double)v[j]; s2[j] += (double)v[j] * (double)refc;
       }
     }
     if constexpr (TN == 4) {
@@ -189,18 +196,19 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
   }
 
   if (a.epi != CVAE_EPI_PLAIN && a.stats != nullptr) {
-    float* red1 = &As[0][0][0];            // [16][BN]
-    float* red2 = red1 + 16 * BN;          // [16][BN]
+    static_assert(sizeof(As) >= 2 * 16 * BN * sizeof(double), "reduction scratch does not fit");
+    double* red1 = reinterpret_cast<double*>(&As[0][0][0]);   // [16][BN]
+    double* red2 = red1 + 16 * BN;                            // [16][BN]
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < TN; ++j) { red1[ty * BN + tx * TN + j] = s1[j]; red2[ty * BN + tx * TN + j] = s2[j]; }
     __syncthreads();
     if (tid < BN && n0 + tid < a.Cd) {
-      float t1 = 0.f, t2 = 0.f;
+      double t1 = 0.0, t2 = 0.0;
 #pragma unroll
       for (int y = 0; y < 16; ++y) { t1 += red1[y * BN + tid]; t2 += red2[y * BN + tid]; }
-      atomicAdd(a.stats + n0 + tid, (double)t1);
-      atomicAdd(a.stats + a.Cd + n0 + tid, (double)t2);
+      atomicAdd(a.stats + n0 + tid, t1);
+      atomicAdd(a.stats + a.Cd + n0 + tid, t2);
     }
   }
 }
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
 template <int CD>
 __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ GatherArgs a) {
   extern __shared__ float s_w[];  // [wtaps][Cs][CD]
-  __shared__ float s_red[4][2 * CD];
+  __shared__ double s_red[4][2 * CD];
   const int tid = threadIdx.x;
   const int wcount = a.wtaps * a.Cs * CD;
   for (int i = tid; i < wcount; i += blockDim.x) s_w[i] = __ldg(a.wt + i);
@@ -221,9 +229,11 @@ __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ G
   const PhaseGeom& P = a.phase[blockIdx.z];
   const int M = a.N * P.Hq * P.Wq;
   const bool vec = (a.Cs & 3) == 0;
-  float s1[CD], s2[CD];
+  float s1[CD], s2[CD];          // fp32 partials over <= 8 pixels, flushed into the doubles below
+  double d1[CD], d2[CD];
 #pragma unroll
-  for (int j = 0; j < CD; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int j = 0; j < CD; ++j) { s1[j] = 0.f; s2[j] = 0.f; d1[j] = 0.0; d2[j] = 0.0; }
+  int since_flush = 0;
 
   for (int m = blockIdx.x * blockDim.x + tid; m < M; m += gridDim.x * blockDim.x) {
     const int qw = m % P.Wq, t = m / P.Wq, qh = t % P.Hq, n = t / P.Hq;
@@ -242,7 +252,10 @@ __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ G
           float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (a.in_affine) v[u] = fmaf(v[u], __ldg(a.in_scale + c + u), __ldg(a.in_shift + c + u));
+            if (a.in_affine) {
+              if (a.in_center != nullptr) v[u] -= __ldg(a.in_center + c + u);
+              v[u] = fmaf(v[u], __ldg(a.in_scale + c + u), __ldg(a.in_shift + c + u));
+            }
             if (a.in_act) v[u] = lrelu(v[u], a.in_slope);
 #pragma unroll
             for (int j = 0; j < CD; ++j) acc[j] = fmaf(v[u], wp[(c + u) * CD + j], acc[j]);
@@ -251,7 +264,10 @@ __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ G
       } else {
         for (int c = 0; c < a.Cs; ++c) {
           float v = __ldg(sp + c);
-          if (a.in_affine) v = fmaf(v, __ldg(a.in_scale + c), __ldg(a.in_shift + c));
+          if (a.in_affine) {
+            if (a.in_center != nullptr) v -= __ldg(a.in_center + c);
+            v = fmaf(v, __ldg(a.in_scale + c), __ldg(a.in_shift + c));
+          }
           if (a.in_act) v = lrelu(v, a.in_slope);
 #pragma unroll
           for (int j = 0; j < CD; ++j) acc[j] = fmaf(v, wp[c * CD + j], acc[j]);
@@ -266,12 +282,18 @@ __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ G
     } else if (a.epi == CVAE_EPI_DACT) {
 #pragma unroll
       for (int j = 0; j < CD; ++j) {
-        const float ref = __ldg(a.epi_ref + off + j);
+        float ref = __ldg(a.epi_ref + off + j);
+        if (a.e_affine && a.e_center != nullptr) ref -= __ldg(a.e_center + j);
         if (a.epi_add != nullptr) acc[j] += __ldg(a.epi_add + off + j);
         const float z = a.e_affine ? fmaf(ref, __ldg(a.e_scale + j), __ldg(a.e_shift + j)) : ref;
         acc[j] = z > 0.f ? acc[j] : acc[j] * a.e_slope;
         s1[j] += acc[j]; s2[j] = fmaf(acc[j], ref, s2[j]);
       }
+    }
+    if (a.epi != CVAE_EPI_PLAIN && ++since_flush == 4) {
+#pragma unroll
+      for (int j = 0; j < CD; ++j) { d1[j] += (double)s1[j]; d2[j] += (double)s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+      since_flush = 0;
     }
     if constexpr (CD % 4 == 0) {
 #pragma unroll
@@ -287,13 +309,13 @@ __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ G
     const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
     for (int j = 0; j < CD; ++j) {
-      const float t1 = warp_sum(s1[j]), t2 = warp_sum(s2[j]);
+      const double t1 = warp_sum_d(d1[j] + (double)s1[j]), t2 = warp_sum_d(d2[j] + (double)s2[j]);
       if (lane == 0) { s_red[w][j] = t1; s_red[w][CD + j] = t2; }
     }
     __syncthreads();
     if (tid < 2 * CD) {
-      const float t = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
-      atomicAdd(a.stats + tid, (double)t);
+      const double t = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+      atomicAdd(a.stats + tid, t);
     }
   }
 }
@@ -303,8 +325,8 @@ __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ G
 // ------------------------------------------------------------------------------------------------
 struct WgradArgs {
   const float* ga; const float* db;
-  const float* a_scale; const float* a_shift; float a_slope; int a_affine; int a_act;
-  const float* b_scale; const float* b_shift; float b_slope; int b_affine; int b_act;
+  const float* a_scale; const float* a_shift; const float* a_center; float a_slope; int a_affine; int a_act;
+  const float* b_scale; const float* b_shift; const float* b_center; float b_slope; int b_affine; int b_act;
   float* partial;
   int N, Ha, Wa, Ca, Hq, Wq, Cb;
   int kw, stride, pad, rows, kchunk, K;
@@ -361,7 +383,10 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ Wgra
     }
 #pragma unroll
     for (int u = 0; u < VA; ++u) {
-      if (a.a_affine) out[u] = fmaf(out[u], __ldg(a.a_scale + a_ca + u), __ldg(a.a_shift + a_ca + u));
+      if (a.a_affine) {
+        if (a.a_center != nullptr) out[u] -= __ldg(a.a_center + a_ca + u);
+        out[u] = fmaf(out[u], __ldg(a.a_scale + a_ca + u), __ldg(a.a_shift + a_ca + u));
+      }
       if (a.a_act) out[u] = lrelu(out[u], a.a_slope);
     }
   };
@@ -387,7 +412,10 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ Wgra
         }
 #pragma unroll
         for (int u = 0; u < VB; ++u) {
-          if (a.b_affine) rb[u] = fmaf(rb[u], __ldg(a.b_scale + col + u), __ldg(a.b_shift + col + u));
+          if (a.b_affine) {
+            if (a.b_center != nullptr) rb[u] -= __ldg(a.b_center + col + u);
+            rb[u] = fmaf(rb[u], __ldg(a.b_scale + col + u), __ldg(a.b_shift + col + u));
+          }
           if (a.b_act) rb[u] = lrelu(rb[u], a.b_slope);
         }
       }
@@ -531,10 +559,10 @@ extern "C" int cvae_conv_gather(const cvae_conv_params_t* p, cvae_stream_t s) {
   if (p->epi == CVAE_EPI_DACT && !p->epi_ref) return CVAE_ERR_BAD_ARG;
   GatherArgs g;
   g.src = p->src; g.wt = p->wt; g.bias = p->bias; g.dst = p->dst;
-  g.in_scale = p->in.scale; g.in_shift = p->in.shift; g.in_slope = p->in.slope;
+  g.in_scale = p->in.scale; g.in_shift = p->in.shift; g.in_center = p->in.center; g.in_slope = p->in.slope;
   g.in_affine = p->in.scale != nullptr; g.in_act = p->in.slope != 1.0f;
   g.epi = p->epi; g.epi_ref = p->epi_ref; g.epi_add = p->epi_add;
-  g.e_scale = p->epi_x.scale; g.e_shift = p->epi_x.shift; g.e_slope = p->epi_x.slope;
+  g.e_scale = p->epi_x.scale; g.e_shift = p->epi_x.shift; g.e_center = p->epi_x.center; g.e_slope = p->epi_x.slope;
   g.e_affine = p->epi_x.scale != nullptr;
   g.stats = p->stats;
   g.N = p->N; g.Hs = p->Hs; g.Ws = p->Ws; g.Cs = p->Cs; g.Hd = p->Hd; g.Wd = p->Wd; g.Cd = p->Cd;
@@ -590,9 +618,9 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_params_t* p, cvae_stream_t s) {
     return CVAE_ERR_BAD_ARG;
   WgradArgs a;
   a.ga = p->ga; a.db = p->db;
-  a.a_scale = p->xa.scale; a.a_shift = p->xa.shift; a.a_slope = p->xa.slope;
+  a.a_scale = p->xa.scale; a.a_shift = p->xa.shift; a.a_center = p->xa.center; a.a_slope = p->xa.slope;
   a.a_affine = p->xa.scale != nullptr; a.a_act = p->xa.slope != 1.0f;
-  a.b_scale = p->xb.scale; a.b_shift = p->xb.shift; a.b_slope = p->xb.slope;
+  a.b_scale = p->xb.scale; a.b_shift = p->xb.shift; a.b_center = p->xb.center; a.b_slope = p->xb.slope;
   a.b_affine = p->xb.scale != nullptr; a.b_act = p->xb.slope != 1.0f;
   a.partial = p->partial;
   a.N = p->N; a.Ha = p->Ha; a.Wa = p->Wa; a.Ca = p->Ca; a.Hq = p->Hq; a.Wq = p->Wq; a.Cb = p->Cb;

@@ -17,9 +17,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, doub
   if (var < 0.0) var = 0.0;
   const double rstd = 1.0 / sqrt(var + (double)eps);
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-  const float sc = (float)(g * rstd);
-  scale[c] = sc;
-  shift[c] = (float)((double)b - mean * (double)g * rstd);
+  scale[c] = (float)(g * rstd);   // consumer applies (v - mean) * scale + shift
+  shift[c] = b;
   if (mean_out) mean_out[c] = (float)mean;
   if (rstd_out) rstd_out[c] = (float)rstd;
   if (running_mean) {
@@ -35,28 +34,26 @@ __global__ void bn_eval_coeffs_kernel(const float* rm, const float* rv, const fl
   if (c >= C) return;
   const float rstd = 1.0f / sqrtf(rv[c] + eps);
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-  scale[c] = g * rstd;
-  shift[c] = b - rm[c] * g * rstd;
+  scale[c] = g * rstd;            // used with center = running_mean
+  shift[c] = b;
 }
 
-// stats = (sum dz, sum dz*y) ->  dy = ca*dz + cb*y + cc
+// stats = (sum dz, sum dz*(y-mean)) ->  dy = ca*dz + cb*(y-mean) + cc
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int C, double count,
                                        const float* gamma, const float* mean, const float* rstd, float* ca,
                                        float* cb, float* cc, float* dgamma, float* dbeta, float* dbias_pre) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double sdz = stats[c], sdzy = stats[C + c];
-  const double mu = mean[c], rs = rstd[c], g = gamma ? (double)gamma[c] : 1.0;
-  const double sdzxh = rs * (sdzy - mu * sdz);  // sum dz * xhat
+  const double sdz = stats[c], sdzc = stats[C + c];
+  const double rs = rstd[c], g = gamma ? (double)gamma[c] : 1.0;
+  const double sdzxh = rs * sdzc;  // sum dz * xhat
   if (dgamma) dgamma[c] = (float)sdzxh;
   if (dbeta) dbeta[c] = (float)sdz;
   const double k1 = sdz / count, k2 = sdzxh / count;
-  const double a_ = g * rs;
-  const double b_ = -g * rs * rs * k2;
-  const double c_ = -g * rs * k1 + g * rs * rs * mu * k2;
-  ca[c] = (float)a_; cb[c] = (float)b_; cc[c] = (float)c_;
-  // sum over the batch of dy = a*sum(dz) + b*sum(y) + count*c ; sum(y) = count*mean -> analytically 0
-  if (dbias_pre) dbias_pre[c] = (float)(a_ * sdz + b_ * (mu * count) + count * c_);
+  ca[c] = (float)(g * rs); cb[c] = (float)(-g * rs * rs * k2); cc[c] = (float)(-g * rs * k1);
+  // sum over the batch of dy = ca*sum(dz) + cb*sum(y-mean) + count*cc = 0: a bias feeding a
+  // training-mode BatchNorm has an exactly zero gradient (the reference produces rounding noise)
+  if (dbias_pre) dbias_pre[c] = 0.f;
 }
 
 // generic [rows, C] streaming kernels; C % 4 == 0 -> float4 path, else scalar
@@ -72,7 +69,7 @@ __global__ void affine_act_kernel(const float* __restrict__ a, XformDev xa, cons
       float r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (xa.affine) r[u] = fmaf(r[u], __ldg(xa.scale + c + u), __ldg(xa.shift + c + u));
+        if (xa.affine) r[u] = fmaf(r[u] - (xa.center ? __ldg(xa.center + c + u) : 0.f), __ldg(xa.scale + c + u), __ldg(xa.shift + c + u));
         if (xa.act) r[u] = lrelu(r[u], xa.slope);
       }
       if (HAS_B) {
@@ -80,7 +77,7 @@ __global__ void affine_act_kernel(const float* __restrict__ a, XformDev xa, cons
         float q[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (xb.affine) q[u] = fmaf(q[u], __ldg(xb.scale + c + u), __ldg(xb.shift + c + u));
+          if (xb.affine) q[u] = fmaf(q[u] - (xb.center ? __ldg(xb.center + c + u) : 0.f), __ldg(xb.scale + c + u), __ldg(xb.shift + c + u));
           if (xb.act) q[u] = lrelu(q[u], xb.slope);
           r[u] += q[u];
         }
@@ -91,11 +88,11 @@ __global__ void affine_act_kernel(const float* __restrict__ a, XformDev xa, cons
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
       const int c = (int)(i % C);
       float r = a[i];
-      if (xa.affine) r = fmaf(r, xa.scale[c], xa.shift[c]);
+      if (xa.affine) r = fmaf(r - (xa.center ? xa.center[c] : 0.f), xa.scale[c], xa.shift[c]);
       if (xa.act) r = lrelu(r, xa.slope);
       if (HAS_B) {
         float q = b[i];
-        if (xb.affine) q = fmaf(q, xb.scale[c], xb.shift[c]);
+        if (xb.affine) q = fmaf(q - (xb.center ? xb.center[c] : 0.f), xb.scale[c], xb.shift[c]);
         if (xb.act) q = lrelu(q, xb.slope);
         r += q;
       }
@@ -106,7 +103,8 @@ __global__ void affine_act_kernel(const float* __restrict__ a, XformDev xa, cons
 
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                     const float* __restrict__ ca, const float* __restrict__ cb,
-                                    const float* __restrict__ cc, float* __restrict__ out, int64_t total, int C) {
+                                    const float* __restrict__ cc, const float* __restrict__ mean,
+                                    float* __restrict__ out, int64_t total, int C) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if ((C & 3) == 0) {
     const int64_t n4 = total >> 2;
@@ -117,15 +115,16 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
       const float4 A = __ldg(reinterpret_cast<const float4*>(ca + c));
       const float4 B = __ldg(reinterpret_cast<const float4*>(cb + c));
       const float4 Cc = __ldg(reinterpret_cast<const float4*>(cc + c));
+      const float4 Mu = __ldg(reinterpret_cast<const float4*>(mean + c));
       float4 o;
-      o.x = fmaf(A.x, d.x, fmaf(B.x, v.x, Cc.x)); o.y = fmaf(A.y, d.y, fmaf(B.y, v.y, Cc.y));
-      o.z = fmaf(A.z, d.z, fmaf(B.z, v.z, Cc.z)); o.w = fmaf(A.w, d.w, fmaf(B.w, v.w, Cc.w));
+      o.x = fmaf(A.x, d.x, fmaf(B.x, v.x - Mu.x, Cc.x)); o.y = fmaf(A.y, d.y, fmaf(B.y, v.y - Mu.y, Cc.y));
+      o.z = fmaf(A.z, d.z, fmaf(B.z, v.z - Mu.z, Cc.z)); o.w = fmaf(A.w, d.w, fmaf(B.w, v.w - Mu.w, Cc.w));
       reinterpret_cast<float4*>(out)[i] = o;
     }
   } else {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
       const int c = (int)(i % C);
-      out[i] = fmaf(ca[c], dz[i], fmaf(cb[c], y[i], cc[c]));
+      out[i] = fmaf(ca[c], dz[i], fmaf(cb[c], y[i] - mean[c], cc[c]));
     }
   }
 }
@@ -137,39 +136,40 @@ template <int MODE>
 __global__ void col_reduce_kernel(const float* __restrict__ p0, const float* __restrict__ p1, XformDev x,
                                   float* __restrict__ out, double* __restrict__ stats, float* __restrict__ fsum,
                                   int64_t rows, int C, int accumulate) {
-  __shared__ float r1[8][33], r2[8][33];
+  __shared__ double r1[8][33], r2[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  float s1 = 0.f, s2 = 0.f;
+  double s1 = 0.0, s2 = 0.0;
   if (c < C) {
     const float sc = (MODE == 1 && x.affine) ? x.scale[c] : 1.f, sh = (MODE == 1 && x.affine) ? x.shift[c] : 0.f;
+    const float ce = (MODE == 1 && x.affine && x.center) ? x.center[c] : 0.f;
     for (int64_t r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
       const int64_t i = r * C + c;
       if (MODE == 0) {
-        const float v = p0[i];
-        s1 += v; s2 = fmaf(v, v, s2);
+        const double v = (double)p0[i];
+        s1 += v; s2 += v * v;
       } else if (MODE == 1) {
-        const float ref = p1[i];
+        const float ref = p1[i] - ce;
         const float z = fmaf(ref, sc, sh);
         float g = p0[i];
         g = z > 0.f ? g : g * x.slope;
         out[i] = g;
-        s1 += g; s2 = fmaf(g, ref, s2);
+        s1 += (double)g; s2 += (double)g * (double)ref;
       } else {
-        s1 += p0[i];
+        s1 += (double)p0[i];
       }
     }
   }
   r1[threadIdx.y][threadIdx.x] = s1; r2[threadIdx.y][threadIdx.x] = s2;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    float t1 = 0.f, t2 = 0.f;
+    double t1 = 0.0, t2 = 0.0;
 #pragma unroll
     for (int y = 0; y < 8; ++y) { t1 += r1[y][threadIdx.x]; t2 += r2[y][threadIdx.x]; }
     if (MODE == 2) {
-      atomicAdd(fsum + c, t1);
+      atomicAdd(fsum + c, (float)t1);
     } else {
-      atomicAdd(stats + c, (double)t1);
-      atomicAdd(stats + C + c, (double)t2);
+      atomicAdd(stats + c, t1);
+      atomicAdd(stats + C + c, t2);
     }
   }
 }
@@ -232,7 +232,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
 
 static inline XformDev make_x(cvae_xform_t x) {
   XformDev d;
-  d.scale = x.scale; d.shift = x.shift; d.slope = x.slope;
+  d.scale = x.scale; d.shift = x.shift; d.center = x.center; d.slope = x.slope;
   d.affine = x.scale != nullptr; d.act = x.slope != 1.0f;
   return d;
 }
@@ -288,11 +288,12 @@ extern "C" int cvae_affine_act(const float* a, cvae_xform_t xa, const float* b, 
 }
 
 extern "C" int cvae_bn_bwd_apply(const float* dz, const float* y, const float* ca, const float* cb,
-                                 const float* cc, float* out, int64_t rows, int C, cvae_stream_t s) {
-  if (!dz || !y || !out || rows <= 0 || C <= 0) return CVAE_ERR_BAD_ARG;
+                                 const float* cc, const float* mean, float* out, int64_t rows, int C,
+                                 cvae_stream_t s) {
+  if (!dz || !y || !out || !mean || rows <= 0 || C <= 0) return CVAE_ERR_BAD_ARG;
   const int64_t total = rows * C;
   bn_bwd_apply_kernel<<<stream_blocks((C & 3) == 0 ? total / 4 : total), 256, 0, as_stream(s)>>>(dz, y, ca, cb, cc,
-                                                                                                 out, total, C);
+                                                                                                 mean, out, total, C);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

@@ -133,9 +133,10 @@ class _BNStandalone(torch.autograd.Function):
             ctx.save_for_backward(x2d, gamma, mean, rstd)
         else:
             scale, shift = ops.bn_eval_coeffs(bn)
+            mean = bn.running_mean
             ctx.train = False
             ctx.save_for_backward(x2d, scale)
-        return ops.affine_act(x2d, ops.XF(scale, shift, 1.0))
+        return ops.affine_act(x2d, ops.XF(scale, shift, 1.0, mean))
 
     @staticmethod
     def backward(ctx, g):
@@ -144,13 +145,14 @@ class _BNStandalone(torch.autograd.Function):
         if not ctx.train:
             x2d, scale = ctx.saved_tensors
             zero = torch.zeros_like(scale)
-            return ops.bn_bwd_apply(g, x2d, scale, zero, zero), None, None, None
+            return ops.bn_bwd_apply(g, x2d, scale, zero, zero, zero), None, None, None
         x2d, gamma, mean, rstd = ctx.saved_tensors
         rows, C = x2d.shape
         stats = ops.zeros(2 * C, dtype=torch.float64, like=g)
-        dz = ops.dact_stats(g, x2d, ops.IDENT, stats)
+        one = torch.ones_like(mean)
+        dz = ops.dact_stats(g, x2d, ops.XF(one, torch.zeros_like(mean), 1.0, mean), stats)
         ca, cb, cc, dg, db, _ = ops.bn_bwd_finalize(stats, C, rows, gamma, mean, rstd, False)
-        return ops.bn_bwd_apply(dz, x2d, ca, cb, cc), None, dg, db
+        return ops.bn_bwd_apply(dz, x2d, ca, cb, cc, mean), None, dg, db
 
 
 class _BNMixin:

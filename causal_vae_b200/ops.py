@@ -21,18 +21,18 @@ def zeros(*shape, dtype=f32, like=None):
 
 
 class XF:
-    """Deferred per-channel transform: v*scale[c]+shift[c] then leaky-relu(slope)."""
-    __slots__ = ("scale", "shift", "slope")
+    """Deferred per-channel transform: (v-center[c])*scale[c]+shift[c] then leaky-relu(slope)."""
+    __slots__ = ("scale", "shift", "slope", "center")
 
-    def __init__(self, scale=None, shift=None, slope=1.0):
-        self.scale, self.shift, self.slope = scale, shift, float(slope)
+    def __init__(self, scale=None, shift=None, slope=1.0, center=None):
+        self.scale, self.shift, self.slope, self.center = scale, shift, float(slope), center
 
     @property
     def identity(self):
         return self.scale is None and self.slope == 1.0
 
     def c(self):
-        return L.xform(self.scale, self.shift, self.slope)
+        return L.xform(self.scale, self.shift, self.slope, self.center)
 
 
 IDENT = XF()
@@ -114,11 +114,11 @@ def affine_act(a, xa, b=None, xb=IDENT, out=None):
     return out
 
 
-def bn_bwd_apply(dz, y, ca, cb, cc, out=None):
+def bn_bwd_apply(dz, y, ca, cb, cc, mean, out=None):
     C = y.shape[-1]
     rows = y.numel() // C
     out = out if out is not None else torch.empty_like(y)
-    L.check(L.lib.cvae_bn_bwd_apply(L.ptr(dz), L.ptr(y), L.ptr(ca), L.ptr(cb), L.ptr(cc), L.ptr(out), rows, C,
+    L.check(L.lib.cvae_bn_bwd_apply(L.ptr(dz), L.ptr(y), L.ptr(ca), L.ptr(cb), L.ptr(cc), L.ptr(mean), L.ptr(out), rows, C,
                                     L.stream()), "bn_bwd_apply")
     return out
 

@@ -41,13 +41,16 @@ int cvae_version(void);
 int cvae_built_arch(void);
 
 /* ---- per-channel input transform applied while an operand is loaded ----------------------
- * v' = v * scale[c] + shift[c]  (skipped when scale == NULL), then leaky-relu with `slope`
- * (slope == 1 -> identity, 0 -> ReLU).  This is how training-mode BatchNorm + activation of the
+ * v' = (v - center[c]) * scale[c] + shift[c]  (skipped when scale == NULL; center == NULL means 0),
+ * then leaky-relu with `slope` (slope == 1 -> identity, 0 -> ReLU).  The centred form is the
+ * reference's BatchNorm arithmetic ((x - mean) * rstd * gamma + beta): it does not cancel for
+ * channels whose |mean| >> std.  This is how training-mode BatchNorm + activation of the
  * PRODUCER layer is applied on the CONSUMER's operand load instead of in a separate pass
  * (vit_backbone.py:74-90,124-156: Conv -> BatchNorm2d -> LeakyReLU chains). */
 typedef struct {
   const float* scale; /* [C] or NULL */
   const float* shift; /* [C] or NULL (must be non-NULL when scale is) */
+  const float* center; /* [C] or NULL */
   float slope;
 } cvae_xform_t;
 
@@ -56,7 +59,7 @@ enum {
   CVAE_EPI_PLAIN = 0,  /* dst = acc + bias */
   CVAE_EPI_STATS = 1,  /* dst = acc + bias; stats[c] += sum(dst), stats[C+c] += sum(dst^2)  (BN fwd) */
   CVAE_EPI_DACT = 2    /* g = acc (+ add); z = xform(ref) pre-activation; dst = g * act'(z);
-                          stats[c] += sum(dst), stats[C+c] += sum(dst*ref)   (act + BN backward) */
+                          stats[c] += sum(dst), stats[C+c] += sum(dst*(ref - center))   (act + BN backward) */
 };
 
 enum { CVAE_CONV_GATHER = 0, /* Conv2d forward; ConvTranspose2d input-gradient */
@@ -129,8 +132,8 @@ int cvae_bn_eval_coeffs(const float* running_mean, const float* running_var, con
 /* sum / sum-of-squares of a [rows, C] matrix into double stats[2C] (for producers without a fused
  * statistics epilogue). */
 int cvae_col_stats(const float* y, int64_t rows, int C, double* stats, cvae_stream_t s);
-/* backward coefficients from stats = (sum dz, sum dz*y):  dy = ca*dz + cb*y + cc;  dgamma, dbeta,
- * and the analytic gradient of a conv bias feeding the BN (sum dy). */
+/* backward coefficients from stats = (sum dz, sum dz*(y-mean)):  dy = ca*dz + cb*(y-mean) + cc;
+ * dgamma, dbeta, and the gradient of a conv bias feeding the BN (sum dy, analytically zero). */
 int cvae_bn_bwd_finalize(const double* stats, int C, double count, const float* gamma,
                          const float* mean, const float* rstd, float* ca, float* cb, float* cc,
                          float* dgamma, float* dbeta, float* dbias_pre, cvae_stream_t s);
@@ -138,9 +141,10 @@ int cvae_bn_bwd_finalize(const double* stats, int C, double count, const float* 
  * residual sum (vit_backbone.py:18-19 ResBlock `x + conv(x)`). */
 int cvae_affine_act(const float* a, cvae_xform_t xa, const float* b, cvae_xform_t xb, float* out,
                     int64_t rows, int C, cvae_stream_t s);
-/* out = ca[c]*dz + cb[c]*y + cc[c]  (BN input gradient) */
+/* out = ca[c]*dz + cb[c]*(y - mean[c]) + cc[c]  (BN input gradient) */
 int cvae_bn_bwd_apply(const float* dz, const float* y, const float* ca, const float* cb,
-                      const float* cc, float* out, int64_t rows, int C, cvae_stream_t s);
+                      const float* cc, const float* mean, float* out, int64_t rows, int C,
+                      cvae_stream_t s);
 /* dz = g * act'(xform(ref)); stats += (sum dz, sum dz*ref)  — the CVAE_EPI_DACT epilogue as a
  * standalone pass. */
 int cvae_dact_stats(const float* g, const float* ref, cvae_xform_t x, float* dz, double* stats,

@@ -30,33 +30,53 @@ def gen(*shape, seed=0, scale=1.0):
 
 
 def run_pair(mod_gpu, sd, ref_fn, x, train=True, tol_f=FWD_TOL, tol_g=GRAD_TOL, need_dx=True):
-    """Load `sd` into the native module, run fwd/bwd on GPU and `ref_fn(P64, x64)` on CPU fp64."""
+    """Load `sd` into the native module, run fwd/bwd on GPU and `ref_fn(P, x)` on the CPU in fp64
+    (ground truth) and fp32 (the reference's own precision).  A gradient passes when its error
+    against fp64 is within tol_g of the tensor's max |g|, or within 4x the fp32 reference's own
+    error (zero-true-gradient tensors such as a conv bias feeding BatchNorm are pure rounding noise
+    in the reference)."""
     mod_gpu.load_state_dict(sd)
     mod_gpu = mod_gpu.cuda()
     mod_gpu.train(train)
     xg = x.cuda().requires_grad_(need_dx)
     y = mod_gpu(xg)
-    P = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
-    W = O.trainable(P)
-    for v in W.values():
-        v.requires_grad_(True)
-    xr = x.double().requires_grad_(need_dx)
-    yr = ref_fn(P, xr)
-    assert_close(y, yr, tol_f, "forward")
-    gy = gen(*yr.shape, seed=99)
+    gy = gen(*y.shape, seed=99)
     y.backward(gy.cuda())
-    yr.backward(gy.double())
+
+    def ref(dt):
+        P = {k: (v.to(dt).clone() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        W = O.trainable(P)
+        for v in W.values():
+            v.requires_grad_(True)
+        xr = x.to(dt).requires_grad_(need_dx)
+        yr = ref_fn(P, xr)
+        yr.backward(gy.to(dt))
+        return P, W, xr, yr
+    P, W, xr, yr = ref(torch.float64)
+    _, W32, xr32, _ = ref(torch.float32)
+    bad = []
+    if rel(y, yr) > tol_f:
+        bad.append(("forward", rel(y, yr), 0.0))
+
+    def check(name, got, want, want32):
+        want = want.detach().double().cpu()
+        err = (got.detach().double().cpu() - want).abs().max().item()
+        noise = (want32.detach().double() - want).abs().max().item()
+        if err > max(tol_g * want.abs().max().item(), 4 * noise):
+            bad.append((name, err / max(want.abs().max().item(), 1e-30), noise / max(want.abs().max().item(), 1e-30)))
     if need_dx:
-        assert_close(xg.grad, xr.grad, tol_g, "grad input")
+        check("grad input", xg.grad, xr.grad, xr32.grad)
     for k, p in mod_gpu.named_parameters():
         assert p.grad is not None, f"no grad for {k}"
-        assert_close(p.grad, W[k].grad, tol_g, f"grad {k}")
+        check(f"grad {k}", p.grad, W[k].grad, W32[k].grad)
     if train:
         for k, v in mod_gpu.state_dict().items():
-            if k.endswith(("running_mean", "running_var")):
-                assert_close(v, P[k], 1e-5, k)
+            if k.endswith(("running_mean", "running_var")) and rel(v, P[k]) > 1e-5:
+                bad.append((k, rel(v, P[k]), 0.0))
             if k.endswith("num_batches_tracked"):
                 assert int(v) == int(P[k]), k
+    assert not bad, "mismatches (name, rel err, fp32-reference rel noise): " + "; ".join(
+        f"{n}: {e:.2e} (noise {z:.1e})" for n, e, z in bad)
     return y, yr
 
 
