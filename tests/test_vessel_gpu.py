@@ -90,12 +90,27 @@ def test_train_step_matches_oracle(cfg):
         gold = json.load(f)
     assert abs(float(losses[0]) - gold["train"]["loss"]) <= 2e-5 * abs(gold["train"]["loss"])
 
-    # gradients: 1e-4 of each tensor's max |g|, widened to 4x the oracle's own fp32-vs-fp64
-    # discrepancy where whole-network conditioning (BatchNorm backward cancellation) exceeds that.
+    # gradients: 1e-4 of each tensor's max |g| -- widened where the reference's own arithmetic is
+    # not reproducible to that level.  End-to-end gradients of this network are discontinuous at fp32
+    # rounding scale: a LeakyReLU(0.01) / |recon| / clamp kink flipping for ONE element changes
+    # whole-network gradients by 1e-2..1e-1 (measured: the reference's gradients move that much under a
+    # 3e-7 relative weight perturbation).  The floor is therefore max(4 x fp32-vs-fp64 discrepancy of
+    # the oracle, 2 x its response to 3e-7 weight perturbations); tight (1e-4) gradient parity is
+    # established per layer chain in test_ops_gpu.py and per segment in test_vessel_segments_gpu.py.
+    pert = {k: 0.0 for k in g64}
+    for seed in (1, 2, 3):
+        Pp = {k: v.clone() for k, v in sd.items()}
+        gen = torch.Generator().manual_seed(seed)
+        for k, v in Pp.items():
+            if v.is_floating_point() and "running" not in k:
+                v.mul_(1 + 3e-7 * torch.randn(v.shape, generator=gen))
+        _, gp, _ = O.vessel_train_step(Pp, {}, 1, x, m, t, eps)
+        for k in pert:
+            pert[k] = max(pert[k], rel(gp[k], g32[k]))
     worst = []
     for k, g in g64.items():
         noise = rel(g32[k], g)
-        tol = max(1e-4, 4 * noise)
+        tol = max(1e-4, 4 * noise, 2 * pert[k])
         e = rel(grads[k], g)
         worst.append((e / tol, k, e, noise))
     worst.sort(reverse=True)
