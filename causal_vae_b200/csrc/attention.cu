@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const float* __restr
   }
 }
 
-__global__ void __launch_bounds__(128) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                                                             const float* __restrict__ dout, float* __restrict__ dqkv,
                                                             int S, int H, int d, float p_drop, uint64_t seed,
                                                             uint64_t offset, const int64_t* __restrict__ counter) {
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const float* __restr
   if (counter) seed += (uint64_t)(*counter) * 0x9E3779B97F4A7C15ull;
   const int ld = d + 1, lp = S + 1;
   float* Q = sm; float* K = Q + S * ld; float* V = K + S * ld; float* dO = V + S * ld;
-  float* P = dO + S * ld; float* dS = P + S * lp;
+  float* P = dO + S * ld; float* dS = P + S * lp; float* PD = dS + S * lp;
   const int b = blockIdx.x / H, h = blockIdx.x % H, D = H * d, tid = threadIdx.x;
   const float* base = qkv + (size_t)b * S * 3 * D + h * d;
   const float* dob = dout + (size_t)b * S * D + h * d;
@@ -82,31 +82,26 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const float* __restr
   for (int i = tid; i < S * S; i += blockDim.x) P[(i / S) * lp + (i % S)] = pg[i];
   __syncthreads();
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  // dP (through dropout) -> dS buffer
+  // dP_raw = dO V^T, then (one Philox draw per probability) dP = mask*dP_raw and PD = mask*P
   for (int i = tid; i < S * S; i += blockDim.x) {
     const int qi = i / S, kj = i % S;
     float acc = 0.f;
     for (int c = 0; c < d; ++c) acc = fmaf(dO[qi * ld + c], V[kj * ld + c], acc);
+    float mk = 1.f;
     if (p_drop > 0.f) {
       const uint64_t idx = ((uint64_t)blockIdx.x * S + qi) * S + kj;
-      acc = dropout_keep(seed, offset, idx, p_drop) ? acc * keep_scale : 0.f;
+      mk = dropout_keep(seed, offset, idx, p_drop) ? keep_scale : 0.f;
     }
-    dS[qi * lp + kj] = acc;
+    dS[qi * lp + kj] = acc * mk;
+    PD[qi * lp + kj] = P[qi * lp + kj] * mk;
   }
   __syncthreads();
   float* gb = dqkv + (size_t)b * S * 3 * D + h * d;
-  // dV[j][c] = sum_i Pd[i][j] * dO[i][c]
+  // dV[j][c] = sum_i PD[i][j] * dO[i][c]
   for (int i = tid; i < S * d; i += blockDim.x) {
     const int j = i / d, c = i % d;
     float acc = 0.f;
-    for (int q = 0; q < S; ++q) {
-      float pv = P[q * lp + j];
-      if (p_drop > 0.f) {
-        const uint64_t idx = ((uint64_t)blockIdx.x * S + q) * S + j;
-        pv = dropout_keep(seed, offset, idx, p_drop) ? pv * keep_scale : 0.f;
-      }
-      acc = fmaf(pv, dO[q * ld + c], acc);
-    }
+    for (int q = 0; q < S; ++q) acc = fmaf(PD[q * lp + j], dO[q * ld + c], acc);
     gb[(size_t)j * 3 * D + 2 * D + c] = acc;
   }
   __syncthreads();
@@ -155,12 +150,12 @@ extern "C" int cvae_attention_bwd(const float* qkv, const float* probs, const fl
                                   const int64_t* counter, cvae_stream_t s) {
   if (!qkv || !probs || !dout || !dqkv || B <= 0 || S <= 0) return CVAE_ERR_BAD_ARG;
   if (S > 128 || d > 64) return CVAE_ERR_UNSUPPORTED_SHAPE;
-  const size_t smem = (size_t)(4 * S * (d + 1) + 2 * S * (S + 1)) * sizeof(float);
+  const size_t smem = (size_t)(4 * S * (d + 1) + 3 * S * (S + 1)) * sizeof(float);
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return CVAE_ERR_LAUNCH;
   }
-  attention_bwd_kernel<<<B * H, 128, smem, as_stream(s)>>>(qkv, probs, dout, dqkv, S, H, d, dropout_p, seed, offset, counter);
+  attention_bwd_kernel<<<B * H, 256, smem, as_stream(s)>>>(qkv, probs, dout, dqkv, S, H, d, dropout_p, seed, offset, counter);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

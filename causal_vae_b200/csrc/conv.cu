@@ -10,22 +10,9 @@
 // (Cin = 1 stem head, Cout = 1 image head) that are pure HBM streams.  The weight gradient is a
 // pixels-contracted GEMM with deterministic split-K partials.
 #include "common.cuh"
+#include "conv_args.cuh"
 
 namespace cvae {
-
-struct TapEntry { int dh, dw, widx; };
-struct PhaseGeom { int ph, pw, Hq, Wq, ntaps; TapEntry taps[16]; };
-
-struct GatherArgs {
-  const float* src; const float* wt; const float* bias; float* dst;
-  const float* in_scale; const float* in_shift; const float* in_center; float in_slope; int in_affine; int in_act;
-  int epi; const float* epi_ref; const float* epi_add;
-  const float* e_scale; const float* e_shift; const float* e_center; float e_slope; int e_affine;
-  double* stats;
-  int N, Hs, Ws, Cs, Hd, Wd, Cd;
-  int os, is, wtaps, nphase;
-  PhaseGeom phase[4];
-};
 
 // ------------------------------------------------------------------------------------------------
 // tiled gather kernel: BM=128 output pixels x BN channels, BK=16 input channels of one tap per step
@@ -37,7 +24,10 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
   __shared__ __align__(16) float Bs[2][BK][BN];
   __shared__ int s_n[BM], s_qh[BM], s_qw[BM];
 
-  const PhaseGeom& P = a.phase[blockIdx.z];
+  // grid.z = phase (conv-transpose / dgrad) or, for single-phase problems with a long K and few
+  // output tiles, the K-split index (partial sums are combined with atomics on a zeroed dst)
+  const int kz = a.ksplit > 1 ? blockIdx.z : 0;
+  const PhaseGeom& P = a.phase[a.ksplit > 1 ? 0 : blockIdx.z];
   const int tid = threadIdx.x;
   const int M = a.N * P.Hq * P.Wq;
   const int m0 = blockIdx.x * BM;
@@ -63,7 +53,10 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
   const bool b_active = bk < BK;
 
   const int kc = (a.Cs + BK - 1) / BK;
-  const int T = P.ntaps * kc;
+  const int Tall = P.ntaps * kc;
+  const int Tper = (Tall + max(a.ksplit, 1) - 1) / max(a.ksplit, 1);
+  const int t_beg = kz * Tper;
+  const int T = min(Tall, t_beg + Tper);
 
   float4 ra[2], rb;
   auto load_tile = [&](int t) {
@@ -116,10 +109,12 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  load_tile(0);
-  store_tile(0);
+  if (t_beg < T) {
+    load_tile(t_beg);
+    store_tile(t_beg & 1);
+  }
   __syncthreads();
-  for (int t = 0; t < T; ++t) {
+  for (int t = t_beg; t < T; ++t) {
     const int buf = t & 1;
     if (t + 1 < T) load_tile(t + 1);
 #pragma unroll
@@ -152,7 +147,7 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
   float bias[TN], esc[TN], esh[TN], ece[TN];
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
-    bias[j] = (a.bias != nullptr && col_ok) ? __ldg(a.bias + cbase + j) : 0.f;
+    bias[j] = (a.bias != nullptr && col_ok && kz == 0) ? __ldg(a.bias + cbase + j) : 0.f;
     esc[j] = (a.e_affine && col_ok) ? __ldg(a.e_scale + cbase + j) : 1.f;
     esh[j] = (a.e_affine && col_ok) ? __ldg(a.e_shift + cbase + j) : 0.f;
     ece[j] = (a.e_affine && a.e_center != nullptr && col_ok) ? __ldg(a.e_center + cbase + j) : 0.f;
@@ -186,7 +181,10 @@ __global__ void __launch_bounds__(256) igemm_gather_kernel(const __grid_constant
         s1[j] += (double)v[j]; s2[j] += (double)v[j] * (double)refc;
       }
     }
-    if constexpr (TN == 4) {
+    if (a.ksplit > 1) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) atomicAdd(a.dst + off + j, v[j]);
+    } else if constexpr (TN == 4) {
       *reinterpret_cast<float4*>(a.dst + off) = make_float4(v[0], v[1], v[2], v[3]);
     } else if constexpr (TN == 2) {
       *reinterpret_cast<float2*>(a.dst + off) = make_float2(v[0], v[1]);
@@ -323,15 +321,6 @@ __global__ void __launch_bounds__(128) conv_pix_kernel(const __grid_constant__ G
 // ------------------------------------------------------------------------------------------------
 // weight gradient:  P[split][tap*Ca + ca][cb] = sum_{pix in split} xa(ga[g(pix,tap)][ca]) * xb(db[pix][cb])
 // ------------------------------------------------------------------------------------------------
-struct WgradArgs {
-  const float* ga; const float* db;
-  const float* a_scale; const float* a_shift; const float* a_center; float a_slope; int a_affine; int a_act;
-  const float* b_scale; const float* b_shift; const float* b_center; float b_slope; int b_affine; int b_act;
-  float* partial;
-  int N, Ha, Wa, Ca, Hq, Wq, Cb;
-  int kw, stride, pad, rows, kchunk, K;
-};
-
 template <int BN, int VA, int VB>
 __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ WgradArgs a) {
   constexpr int BM = 64, BK = 16, TM = 4, TN = BN / 16, BV = BN / 4;
@@ -573,15 +562,31 @@ extern "C" int cvae_conv_gather(const cvae_conv_params_t* p, cvae_stream_t s) {
   cudaStream_t st = as_stream(s);
 
   const bool tiled_ok = (p->Cs % 4 == 0) && (p->Cd % 4 == 0) && p->Cs >= 8 && p->Cd >= 8;
+  g.ksplit = 1;
   if (tiled_ok) {
     const int gx = (maxM + 127) / 128;
-    if (p->Cd >= 64) {
-      igemm_gather_kernel<64><<<dim3(gx, (p->Cd + 63) / 64, g.nphase), 256, 0, st>>>(g);
-    } else if (p->Cd >= 32) {
-      igemm_gather_kernel<32><<<dim3(gx, (p->Cd + 31) / 32, g.nphase), 256, 0, st>>>(g);
-    } else {
-      igemm_gather_kernel<16><<<dim3(gx, (p->Cd + 15) / 16, g.nphase), 256, 0, st>>>(g);
+    const int bn = p->Cd >= 64 ? 64 : p->Cd >= 32 ? 32 : 16;
+    const int gy = (p->Cd + bn - 1) / bn;
+    int gz = g.nphase;
+    const int ksteps = g.wtaps * ((p->Cs + 15) / 16);
+    if (g.nphase == 1 && p->epi == CVAE_EPI_PLAIN && gx * gy <= kNumSMs / 2 && ksteps >= 64) {
+      int ks = (2 * kNumSMs + gx * gy - 1) / (gx * gy);
+      ks = min(ks, ksteps / 16);
+      if (ks > 1) {
+        g.ksplit = ks; gz = ks;
+        const size_t bytes = (size_t)p->N * p->Hd * p->Wd * p->Cd * sizeof(float);
+        if (cudaMemsetAsync(p->dst, 0, bytes, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
+      }
     }
+    if (bn == 64) {
+      igemm_gather_kernel<64><<<dim3(gx, gy, gz), 256, 0, st>>>(g);
+    } else if (bn == 32) {
+      igemm_gather_kernel<32><<<dim3(gx, gy, gz), 256, 0, st>>>(g);
+    } else {
+      igemm_gather_kernel<16><<<dim3(gx, gy, gz), 256, 0, st>>>(g);
+    }
+  } else if (launch_conv_cs1(g, maxM, st) || launch_conv_cd1(g, maxM, st)) {
+    // 1-channel layers: coalesced stream kernels (skinny.cu)
   } else {
     const size_t smem = (size_t)g.wtaps * p->Cs * p->Cd * sizeof(float);
     if (smem > 40 * 1024) return CVAE_ERR_UNSUPPORTED_SHAPE;
@@ -602,6 +607,7 @@ extern "C" int cvae_conv_gather(const cvae_conv_params_t* p, cvae_stream_t s) {
 }
 
 extern "C" int cvae_wgrad_splits(int pixels, int rows, int cols) {
+  if (cols == 1 || rows <= 16) return 1;   // 1-channel operands: single-pass stream kernels (skinny.cu)
   const int bn = cols >= 64 ? 64 : cols >= 32 ? 32 : 16;
   const int tiles = ((rows + 63) / 64) * ((cols + bn - 1) / bn);
   int splits = (2 * kNumSMs + tiles - 1) / tiles;
@@ -631,6 +637,10 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_params_t* p, cvae_stream_t s) {
   chunk = ((chunk + 15) / 16) * 16;
   a.kchunk = chunk;
   cudaStream_t st = as_stream(s);
+  if (p->splits == 1 && (launch_wgrad_cb1(a, p->kh * p->kw, st) || launch_wgrad_ca1(a, p->kh * p->kw, st))) {
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+  }
   const bool va4 = (p->Ca % 4) == 0, vb4 = (p->Cb % 4) == 0;
   const int gx = (a.rows + 63) / 64;
   if (vb4 && p->Cb >= 64) {

@@ -1,0 +1,269 @@
+// One-channel layers of the conv stacks as coalesced HBM streams (sm_100a).
+//
+// The image head (16 -> 1 at 256x256), the stem head (1 -> 32), their input/weight gradients and the
+// MNIST / cascade 1-channel layers have GEMM K or N of 1: a tensor-core (or even a tiled SIMT) GEMM
+// wastes > 90 % of its lanes on them, while their traffic is large (4 MB/sample for the 16-channel
+// 256x256 activation).  Here a group of TP = C/4 threads owns one pixel, every thread moves one
+// 128-bit vector per tap, weights live in shared memory as float4 rows, and all per-channel sums stay
+// in registers across the grid-stride loop.
+#include "conv_args.cuh"
+
+namespace cvae {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 xform4(float4 v, const float4& sc, const float4& sh, const float4& ce, bool affine,
+                                         bool act, float slope) {
+  if (affine) {
+    v.x = fmaf(v.x - ce.x, sc.x, sh.x); v.y = fmaf(v.y - ce.y, sc.y, sh.y);
+    v.z = fmaf(v.z - ce.z, sc.z, sh.z); v.w = fmaf(v.w - ce.w, sc.w, sh.w);
+  }
+  if (act) { v.x = lrelu(v.x, slope); v.y = lrelu(v.y, slope); v.z = lrelu(v.z, slope); v.w = lrelu(v.w, slope); }
+  return v;
+}
+
+// ---- Cs == 1 -> Cd (multiple of 4, <= 64): stem head forward, image-head input gradient ---------------
+__global__ void __launch_bounds__(kThreads) conv_cs1_kernel(const __grid_constant__ GatherArgs a) {
+  __shared__ __align__(16) float s_w[16 * 64];         // [widx][Cd]
+  __shared__ double s_red[kThreads][8];
+  const int tid = threadIdx.x, Cd = a.Cd, TP = Cd >> 2;
+  for (int i = tid; i < a.wtaps * Cd; i += kThreads) s_w[i] = __ldg(a.wt + i);
+  __syncthreads();
+  const PhaseGeom& P = a.phase[blockIdx.z];
+  const int M = a.N * P.Hq * P.Wq;
+  const int cg = tid % TP, c0 = cg * 4;
+  const float in_sc = a.in_affine ? __ldg(a.in_scale) : 1.f, in_sh = a.in_affine ? __ldg(a.in_shift) : 0.f;
+  const float in_ce = (a.in_affine && a.in_center) ? __ldg(a.in_center) : 0.f;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), esc = make_float4(1.f, 1.f, 1.f, 1.f), esh = bias, ece = bias;
+  if (a.bias) bias = __ldg(reinterpret_cast<const float4*>(a.bias + c0));
+  if (a.e_affine) {
+    esc = __ldg(reinterpret_cast<const float4*>(a.e_scale + c0));
+    esh = __ldg(reinterpret_cast<const float4*>(a.e_shift + c0));
+    if (a.e_center) ece = __ldg(reinterpret_cast<const float4*>(a.e_center + c0));
+  }
+  float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+  double d1[4] = {0.0, 0.0, 0.0, 0.0}, d2[4] = {0.0, 0.0, 0.0, 0.0};
+  int since = 0;
+  const int ppb = kThreads / TP;                        // pixels per block per iteration
+  for (int m = blockIdx.x * ppb + tid / TP; m < M; m += gridDim.x * ppb) {
+    const int qw = m % P.Wq;
+    const int t = m / P.Wq;
+    const int qh = t % P.Hq, n = t / P.Hq;
+    float4 acc = bias;
+    for (int tp = 0; tp < P.ntaps; ++tp) {
+      const TapEntry tap = P.taps[tp];
+      const int ih = qh * a.is + tap.dh, iw = qw * a.is + tap.dw;
+      if (ih < 0 || ih >= a.Hs || iw < 0 || iw >= a.Ws) continue;
+      float v = __ldg(a.src + ((size_t)n * a.Hs + ih) * a.Ws + iw);
+      if (a.in_affine) v = fmaf(v - in_ce, in_sc, in_sh);
+      if (a.in_act) v = lrelu(v, a.in_slope);
+      const float4 w = *reinterpret_cast<const float4*>(&s_w[tap.widx * Cd + c0]);
+      acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y); acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+    }
+    const int oh = qh * a.os + P.ph, ow = qw * a.os + P.pw;
+    const size_t off = (((size_t)n * a.Hd + oh) * a.Wd + ow) * Cd + c0;
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (a.epi == CVAE_EPI_STATS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { f1[j] += o[j]; f2[j] = fmaf(o[j], o[j], f2[j]); }
+    } else if (a.epi == CVAE_EPI_DACT) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.epi_ref + off));
+      float rf[4] = {r4.x - ece.x, r4.y - ece.y, r4.z - ece.z, r4.w - ece.w};
+      const float sc[4] = {esc.x, esc.y, esc.z, esc.w}, sh[4] = {esh.x, esh.y, esh.z, esh.w};
+      if (a.epi_add) {
+        const float4 ad = __ldg(reinterpret_cast<const float4*>(a.epi_add + off));
+        o[0] += ad.x; o[1] += ad.y; o[2] += ad.z; o[3] += ad.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = fmaf(rf[j], sc[j], sh[j]);
+        o[j] = z > 0.f ? o[j] : o[j] * a.e_slope;
+        f1[j] += o[j]; f2[j] = fmaf(o[j], rf[j], f2[j]);
+      }
+    }
+    *reinterpret_cast<float4*>(a.dst + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.epi != CVAE_EPI_PLAIN && ++since == 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { d1[j] += (double)f1[j]; d2[j] += (double)f2[j]; f1[j] = 0.f; f2[j] = 0.f; }
+      since = 0;
+    }
+  }
+  if (a.epi != CVAE_EPI_PLAIN && a.stats != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_red[tid][j] = d1[j] + (double)f1[j]; s_red[tid][4 + j] = d2[j] + (double)f2[j]; }
+    __syncthreads();
+    if (tid < TP * 8) {
+      const int g = tid / 8, k = tid % 8;              // channel group, which of the 8 sums
+      double t = 0.0;
+      for (int r = g; r < kThreads; r += TP) t += s_red[r][k];
+      atomicAdd(a.stats + (k < 4 ? 0 : Cd) + g * 4 + (k & 3), t);
+    }
+  }
+}
+
+// ---- Cs (multiple of 4, <= 64) -> Cd == 1, plain epilogue: image head forward ---------------------------
+__global__ void __launch_bounds__(kThreads) conv_cd1_kernel(const __grid_constant__ GatherArgs a) {
+  __shared__ __align__(16) float s_w[16 * 64];         // [widx][Cs]
+  const int tid = threadIdx.x, Cs = a.Cs, TP = Cs >> 2;
+  for (int i = tid; i < a.wtaps * Cs; i += kThreads) s_w[i] = __ldg(a.wt + i);
+  __syncthreads();
+  const PhaseGeom& P = a.phase[blockIdx.z];
+  const int M = a.N * P.Hq * P.Wq;
+  const int cg = tid % TP, c0 = cg * 4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = zero, ce = zero;
+  if (a.in_affine) {
+    sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c0));
+    sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c0));
+    if (a.in_center) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c0));
+  }
+  const float bias = a.bias ? __ldg(a.bias) : 0.f;
+  const int ppb = kThreads / TP;
+  const int Mpad = (M + ppb - 1) / ppb * ppb;           // keep whole pixel groups converged for the shuffles
+  for (int m = blockIdx.x * ppb + tid / TP; m < Mpad; m += gridDim.x * ppb) {
+    const bool live = m < M;
+    const int mm = live ? m : 0;
+    const int qw = mm % P.Wq;
+    const int t = mm / P.Wq;
+    const int qh = t % P.Hq, n = t / P.Hq;
+    float acc = 0.f;
+    for (int tp = 0; tp < P.ntaps; ++tp) {
+      const TapEntry tap = P.taps[tp];
+      const int ih = qh * a.is + tap.dh, iw = qw * a.is + tap.dw;
+      if (ih < 0 || ih >= a.Hs || iw < 0 || iw >= a.Ws) continue;
+      float4 v = __ldg(reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * Cs + c0));
+      v = xform4(v, sc, sh, ce, a.in_affine, a.in_act, a.in_slope);
+      const float4 w = *reinterpret_cast<const float4*>(&s_w[tap.widx * Cs + c0]);
+      acc = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc))));
+    }
+    for (int o = TP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && cg == 0) {
+      const int oh = qh * a.os + P.ph, ow = qw * a.os + P.pw;
+      a.dst[((size_t)n * a.Hd + oh) * a.Wd + ow] = acc + bias;
+    }
+  }
+}
+
+// ---- weight gradients with a 1-channel operand ----------------------------------------------------------
+// Cb == 1:  P[tap*Ca + ca] = sum_pix xa(ga[g(pix,tap)][ca]) * xb(db[pix])            (image head)
+// Ca == 1:  P[tap][cb]     = sum_pix xa(ga[g(pix,tap)])     * xb(db[pix][cb])        (stem head)
+template <int TAPS, bool CB1>
+__global__ void __launch_bounds__(kThreads) wgrad_c1_kernel(const __grid_constant__ WgradArgs a) {
+  __shared__ float s_red[kThreads][4];
+  const int tid = threadIdx.x;
+  const int C = CB1 ? a.Ca : a.Cb, TP = C >> 2;
+  const int cg = tid % TP, c0 = cg * 4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 vsc = make_float4(1.f, 1.f, 1.f, 1.f), vsh = zero, vce = zero;   // transform of the vector operand
+  float ssc = 1.f, ssh = 0.f, sce = 0.f;                                  // transform of the scalar operand
+  const bool v_aff = CB1 ? a.a_affine : a.b_affine, v_act = CB1 ? a.a_act : a.b_act;
+  const bool s_aff = CB1 ? a.b_affine : a.a_affine, s_act = CB1 ? a.b_act : a.a_act;
+  const float v_slope = CB1 ? a.a_slope : a.b_slope, s_slope = CB1 ? a.b_slope : a.a_slope;
+  if (v_aff) {
+    vsc = __ldg(reinterpret_cast<const float4*>((CB1 ? a.a_scale : a.b_scale) + c0));
+    vsh = __ldg(reinterpret_cast<const float4*>((CB1 ? a.a_shift : a.b_shift) + c0));
+    const float* cp = CB1 ? a.a_center : a.b_center;
+    if (cp) vce = __ldg(reinterpret_cast<const float4*>(cp + c0));
+  }
+  if (s_aff) {
+    ssc = __ldg(CB1 ? a.b_scale : a.a_scale); ssh = __ldg(CB1 ? a.b_shift : a.a_shift);
+    const float* cp = CB1 ? a.b_center : a.a_center;
+    if (cp) sce = __ldg(cp);
+  }
+  float acc[TAPS][4];
+  int tdh[TAPS], tdw[TAPS];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) {
+    acc[t][0] = 0.f; acc[t][1] = 0.f; acc[t][2] = 0.f; acc[t][3] = 0.f;
+    tdh[t] = t / a.kw - a.pad; tdw[t] = t % a.kw - a.pad;
+  }
+  const int ppb = kThreads / TP;
+  for (int pix = blockIdx.x * ppb + tid / TP; pix < a.K; pix += gridDim.x * ppb) {
+    const int qw = pix % a.Wq;
+    const int t = pix / a.Wq;
+    const int qh = t % a.Hq, n = t / a.Hq;
+    float4 dv = zero;
+    float ds = 0.f;
+    if (CB1) {
+      ds = __ldg(a.db + pix);
+      if (s_aff) ds = fmaf(ds - sce, ssc, ssh);
+      if (s_act) ds = lrelu(ds, s_slope);
+    } else {
+      dv = __ldg(reinterpret_cast<const float4*>(a.db + (size_t)pix * a.Cb + c0));
+      dv = xform4(dv, vsc, vsh, vce, v_aff, v_act, v_slope);
+    }
+#pragma unroll
+    for (int tp = 0; tp < TAPS; ++tp) {
+      const int ih = qh * a.stride + tdh[tp], iw = qw * a.stride + tdw[tp];
+      if (ih < 0 || ih >= a.Ha || iw < 0 || iw >= a.Wa) continue;
+      const size_t gp = ((size_t)n * a.Ha + ih) * a.Wa + iw;
+      if (CB1) {
+        float4 g = __ldg(reinterpret_cast<const float4*>(a.ga + gp * a.Ca + c0));
+        g = xform4(g, vsc, vsh, vce, v_aff, v_act, v_slope);
+        acc[tp][0] = fmaf(g.x, ds, acc[tp][0]); acc[tp][1] = fmaf(g.y, ds, acc[tp][1]);
+        acc[tp][2] = fmaf(g.z, ds, acc[tp][2]); acc[tp][3] = fmaf(g.w, ds, acc[tp][3]);
+      } else {
+        float g = __ldg(a.ga + gp);
+        if (s_aff) g = fmaf(g - sce, ssc, ssh);
+        if (s_act) g = lrelu(g, s_slope);
+        acc[tp][0] = fmaf(g, dv.x, acc[tp][0]); acc[tp][1] = fmaf(g, dv.y, acc[tp][1]);
+        acc[tp][2] = fmaf(g, dv.z, acc[tp][2]); acc[tp][3] = fmaf(g, dv.w, acc[tp][3]);
+      }
+    }
+  }
+  // block reduction, one tap at a time; threads [0, 4*TP) own (channel group, lane-in-vector)
+#pragma unroll
+  for (int tp = 0; tp < TAPS; ++tp) {
+    __syncthreads();
+    s_red[tid][0] = acc[tp][0]; s_red[tid][1] = acc[tp][1]; s_red[tid][2] = acc[tp][2]; s_red[tid][3] = acc[tp][3];
+    __syncthreads();
+    if (tid < TP * 4) {
+      const int g = tid >> 2, u = tid & 3;
+      float t = 0.f;
+      for (int r = g; r < kThreads; r += TP) t += s_red[r][u];
+      // CB1: row = tap*Ca + ca, col 0 ;  CA1: row = tap, col = cb
+      atomicAdd(a.partial + (size_t)tp * C + g * 4 + u, t);
+    }
+  }
+}
+
+static inline int stream_grid(int64_t pixels, int tp) {
+  const int64_t ppb = kThreads / tp;
+  int64_t b = (pixels + ppb - 1) / ppb;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+bool launch_conv_cs1(const GatherArgs& g, int maxM, cudaStream_t st) {
+  if (g.Cs != 1 || (g.Cd & 3) || g.Cd > 64 || g.Cd < 4 || g.wtaps > 16) return false;
+  const int tp = g.Cd / 4;
+  if (kThreads % tp) return false;
+  conv_cs1_kernel<<<dim3(stream_grid(maxM, tp), 1, g.nphase), kThreads, 0, st>>>(g);
+  return true;
+}
+
+bool launch_conv_cd1(const GatherArgs& g, int maxM, cudaStream_t st) {
+  if (g.Cd != 1 || (g.Cs & 3) || g.Cs > 64 || g.Cs < 4 || g.wtaps > 16 || g.epi != CVAE_EPI_PLAIN) return false;
+  const int tp = g.Cs / 4;
+  if (tp & (tp - 1)) return false;                      // power of two: shuffle reduction inside a warp
+  conv_cd1_kernel<<<dim3(stream_grid(maxM, tp), 1, g.nphase), kThreads, 0, st>>>(g);
+  return true;
+}
+
+template <bool CB1>
+static bool launch_wgrad_c1(const WgradArgs& a, int taps, cudaStream_t st) {
+  const int C = CB1 ? a.Ca : a.Cb;
+  if ((C & 3) || C > 64 || C < 4 || kThreads % (C / 4)) return false;
+  if (cudaMemsetAsync(a.partial, 0, sizeof(float) * (size_t)taps * C, st) != cudaSuccess) return false;
+  const int grid = stream_grid(a.K, C / 4);
+  if (taps == 9) wgrad_c1_kernel<9, CB1><<<grid, kThreads, 0, st>>>(a);
+  else if (taps == 16) wgrad_c1_kernel<16, CB1><<<grid, kThreads, 0, st>>>(a);
+  else return false;
+  return true;
+}
+bool launch_wgrad_cb1(const WgradArgs& a, int taps, cudaStream_t st) { return a.Cb == 1 && launch_wgrad_c1<true>(a, taps, st); }
+bool launch_wgrad_ca1(const WgradArgs& a, int taps, cudaStream_t st) { return a.Ca == 1 && launch_wgrad_c1<false>(a, taps, st); }
+
+}  // namespace cvae

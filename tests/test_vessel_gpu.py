@@ -95,22 +95,24 @@ def test_train_step_matches_oracle(cfg):
     # rounding scale: a LeakyReLU(0.01) / |recon| / clamp kink flipping for ONE element changes
     # whole-network gradients by 1e-2..1e-1 (measured: the reference's gradients move that much under a
     # 3e-7 relative weight perturbation).  The floor is therefore max(4 x fp32-vs-fp64 discrepancy of
-    # the oracle, 2 x its response to 3e-7 weight perturbations); tight (1e-4) gradient parity is
+    # the oracle, 4 x its response to 3e-7 weight perturbations); tight (1e-4) gradient parity is
     # established per layer chain in test_ops_gpu.py and per segment in test_vessel_segments_gpu.py.
     pert = {k: 0.0 for k in g64}
+    pert_tot = 0.0
     for seed in (1, 2, 3):
         Pp = {k: v.clone() for k, v in sd.items()}
         gen = torch.Generator().manual_seed(seed)
         for k, v in Pp.items():
             if v.is_floating_point() and "running" not in k:
                 v.mul_(1 + 3e-7 * torch.randn(v.shape, generator=gen))
-        _, gp, _ = O.vessel_train_step(Pp, {}, 1, x, m, t, eps)
+        _, gp, totp = O.vessel_train_step(Pp, {}, 1, x, m, t, eps)
+        pert_tot = max(pert_tot, abs(float(totp) - float(tot32)) / float(tot32))
         for k in pert:
             pert[k] = max(pert[k], rel(gp[k], g32[k]))
     worst = []
     for k, g in g64.items():
         noise = rel(g32[k], g)
-        tol = max(1e-4, 4 * noise, 2 * pert[k])
+        tol = max(1e-4, 4 * noise, 4 * pert[k])
         e = rel(grads[k], g)
         worst.append((e / tol, k, e, noise))
     worst.sort(reverse=True)
@@ -119,7 +121,7 @@ def test_train_step_matches_oracle(cfg):
     for k in ("backbone.fc_mu.weight", "backbone.fc_var.bias"):
         assert float(grads[k].abs().max()) == 0.0                       # unused heads get no gradient
     tot = trainer.opt.grad_norm().item()
-    assert abs(tot - float(tot64)) <= max(1e-4, 4 * abs(float(tot32) - float(tot64)) / float(tot64)) * float(tot64)
+    assert abs(tot - float(tot64)) <= max(1e-4, 4 * abs(float(tot32) - float(tot64)) / float(tot64), 4 * pert_tot) * float(tot64)
     # BN running statistics after the step (momentum 0.1, unbiased variance)
     for k, v in model.state_dict().items():
         if k.endswith(("running_mean", "running_var")):
