@@ -50,6 +50,13 @@ _SIGS = {
     "cvae_conv_wgrad": [C.POINTER(WgradParams), vp],
     "cvae_wgrad_reduce": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "cvae_pack_weight": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "cvae_tc_eligible": [i32, i32, i64],
+    "cvae_tc_pack_floats": [i32, i32, i32],
+    "cvae_tc_pack_weight": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "cvae_conv_gather_tc": [C.POINTER(ConvParams), vp],
+    "cvae_wgrad_tc_eligible": [i32, i32, i32],
+    "cvae_wgrad_tc_splits": [i32, i32, i32],
+    "cvae_conv_wgrad_tc": [C.POINTER(WgradParams), vp],
     "cvae_bn_finalize": [vp, i32, f64, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp],
     "cvae_bn_eval_coeffs": [vp, vp, vp, vp, f32, i32, vp, vp, vp],
     "cvae_col_stats": [vp, i64, i32, vp, vp],
@@ -97,7 +104,7 @@ EXPORTS = tuple(_SIGS)
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here = header / library drift: fail loudly
     _fn.argtypes = _args
-    _fn.restype = C.c_int
+    _fn.restype = C.c_int64 if _name == "cvae_tc_pack_floats" else C.c_int
 
 _ERR = {-1: "bad argument", -2: "unsupported shape", -3: "alignment", -4: "CUDA launch error"}
 

@@ -69,38 +69,44 @@ class _Rec:
     pass
 
 
-def _pack_fwd(u, Cs_phys):
+def _pack_fwd(u, Cs_phys, tc=False):
     w = u.mod.weight
     taps = u.k * u.k
     if u.kind == "conv":      # [Cout][Cin][tap] -> [tap][Cin][Cout]
-        return ops.pack_weight(w, w.shape[1], Cs_phys, w.shape[0], taps, True, w.shape[1])
+        return ops.pack_weight(w, w.shape[1], Cs_phys, w.shape[0], taps, True, w.shape[1], tc=tc)
     if u.kind == "convT":     # [Cin][Cout][tap] -> [tap][Cin][Cout]
-        return ops.pack_weight(w, w.shape[0], Cs_phys, w.shape[1], taps, False, w.shape[1])
-    return ops.pack_weight(w, w.shape[1], Cs_phys, w.shape[0], 1, True, w.shape[1])  # [out][in] -> [in_pad][out]
+        return ops.pack_weight(w, w.shape[0], Cs_phys, w.shape[1], taps, False, w.shape[1], tc=tc)
+    return ops.pack_weight(w, w.shape[1], Cs_phys, w.shape[0], 1, True, w.shape[1], tc=tc)  # [out][in] -> [in_pad][out]
 
 
-def _pack_dgrad(u, grad_cols):
+def _pack_dgrad(u, grad_cols, tc=False):
     """weights for the input-gradient: [tap][C_of_dy][C_of_dx]."""
     w = u.mod.weight
     taps = u.k * u.k
     if u.kind == "conv":      # [Cout][Cin][tap] -> [tap][Cout][Cin]
-        return ops.pack_weight(w, w.shape[0], w.shape[0], w.shape[1], taps, False, w.shape[1])
+        return ops.pack_weight(w, w.shape[0], w.shape[0], w.shape[1], taps, False, w.shape[1], tc=tc)
     if u.kind == "convT":     # [Cin][Cout][tap] -> [tap][Cout][Cin]
-        return ops.pack_weight(w, w.shape[1], w.shape[1], w.shape[0], taps, True, w.shape[1])
-    if grad_cols == w.shape[1]:
+        return ops.pack_weight(w, w.shape[1], w.shape[1], w.shape[0], taps, True, w.shape[1], tc=tc)
+    if grad_cols == w.shape[1] and not tc:
         return w                                  # [out][in] already is [C_of_dy][C_of_dx]
-    return ops.pack_weight(w, w.shape[0], w.shape[0], grad_cols, 1, False, w.shape[1])  # [out][in] -> [out][cols]
+    return ops.pack_weight(w, w.shape[0], w.shape[0], grad_cols, 1, False, w.shape[1], tc=tc)  # [out][in] -> [out][cols]
+
+
+def _min_phase_rows(N, Hd, Wd, stride, scatter):
+    """rows (output pixels) of the smallest GEMM the layer decomposes into."""
+    return N * (Hd // stride) * (Wd // stride) if scatter else N * Hd * Wd
 
 
 def _unit_fwd(u, S, train, keep):
     N, Hs, Ws, Cs = S.t.shape
     Hd, Wd, Cd = u.out_geom(Hs, Ws)
-    wt = _pack_fwd(u, Cs)
     mode = L.MODE_SCATTER if u.kind == "convT" else L.MODE_GATHER
+    tc = ops.tc_eligible(Cs, Cd, _min_phase_rows(N, Hd, Wd, u.stride, mode == L.MODE_SCATTER))
+    wt = _pack_fwd(u, Cs, tc)
     bn_train = u.bn is not None and (u.bn.training or not u.bn.track_running_stats)
     stats = ops.zeros(2 * Cd, dtype=torch.float64, like=S.t) if bn_train else None
     y = ops.conv_gather(S.t, wt, u.mod.bias, (Hd, Wd, Cd), u.k, u.stride, u.pad, mode, in_x=S.x,
-                        epi=L.EPI_STATS if bn_train else L.EPI_PLAIN, stats=stats)
+                        epi=L.EPI_STATS if bn_train else L.EPI_PLAIN, stats=stats, tc=tc)
     rec = _Rec()
     rec.S_in, rec.y, rec.mean, rec.rstd, rec.sig = S, y, None, None, None
     slope = u.act if isinstance(u.act, float) else 1.0
@@ -173,15 +179,16 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
     if not need_dx:
         return None
     cols = Cs if grad_cols is None else grad_cols
-    wt = _pack_dgrad(u, cols)
     mode = L.MODE_GATHER if u.kind == "convT" else L.MODE_SCATTER
+    tc = ops.tc_eligible(Cd, cols, _min_phase_rows(N, Hs, Ws, u.stride, mode == L.MODE_SCATTER))
+    wt = _pack_dgrad(u, cols, tc)
     if prev_entry is not None and not prev_entry.x.identity:
         return ops.conv_gather(dy, wt, None, (Hs, Ws, cols), u.k, u.stride, u.pad, mode, epi=L.EPI_DACT,
-                               epi_ref=prev_entry.t, epi_add=add, epi_x=prev_entry.x, stats=prev_stats)
+                               epi_ref=prev_entry.t, epi_add=add, epi_x=prev_entry.x, stats=prev_stats, tc=tc)
     if add is not None:
         return ops.conv_gather(dy, wt, None, (Hs, Ws, cols), u.k, u.stride, u.pad, mode, epi=L.EPI_DACT,
-                               epi_ref=add, epi_add=add, epi_x=IDENT, stats=None)
-    return ops.conv_gather(dy, wt, None, (Hs, Ws, cols), u.k, u.stride, u.pad, mode)
+                               epi_ref=add, epi_add=add, epi_x=IDENT, stats=None, tc=tc)
+    return ops.conv_gather(dy, wt, None, (Hs, Ws, cols), u.k, u.stride, u.pad, mode, tc=tc)
 
 
 def _entry(chain, recs, i):

@@ -499,7 +499,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
-static int build_geom(const cvae_conv_params_t* p, GatherArgs& g) {
+int build_geom(const cvae_conv_params_t* p, GatherArgs& g) {
   if (p->kh * p->kw > 16 || p->kh < 1 || p->kw < 1 || p->stride < 1 || p->stride > 2) return CVAE_ERR_UNSUPPORTED_SHAPE;
   g.wtaps = p->kh * p->kw;
   if (p->mode == CVAE_CONV_GATHER) {

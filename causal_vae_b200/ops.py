@@ -3,6 +3,8 @@
 No autograd here: these functions take and return raw CUDA tensors.  Image activations are plain
 contiguous [N, H, W, C] tensors (NHWC); matrices are [rows, cols].
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -38,7 +40,23 @@ class XF:
 IDENT = XF()
 
 
-def pack_weight(w, A, A_pad, B, taps, src_bat, src_ld):
+# tensor-core (tcgen05, 3xTF32) path for the GEMM-shaped layers; CVAE_TC=0 forces the fp32 SIMT kernels
+_TC = os.environ.get("CVAE_TC", "1") != "0"
+
+
+_TC_MIN_ROWS = int(os.environ.get("CVAE_TC_MIN_ROWS", "1024"))   # below this a 128-row tile grid cannot fill the GPU
+
+
+def tc_eligible(Cs, Cd, M):
+    return _TC and M >= _TC_MIN_ROWS and bool(L.lib.cvae_tc_eligible(int(Cs), int(Cd), int(M)))
+
+
+def pack_weight(w, A, A_pad, B, taps, src_bat, src_ld, tc=False):
+    if tc:
+        out = empty(L.lib.cvae_tc_pack_floats(A_pad, B, taps), like=w)
+        L.check(L.lib.cvae_tc_pack_weight(L.ptr(w), L.ptr(out), A, A_pad, B, taps, int(src_bat), src_ld, L.stream()),
+                "tc_pack_weight")
+        return out
     out = empty(taps, A_pad, B, like=w)
     L.check(L.lib.cvae_pack_weight(L.ptr(w), L.ptr(out), A, A_pad, B, taps, int(src_bat), src_ld, L.stream()),
             "pack_weight")
@@ -46,27 +64,32 @@ def pack_weight(w, A, A_pad, B, taps, src_bat, src_ld):
 
 
 def conv_gather(src, wt, bias, out_hw_c, k, stride, pad, mode, in_x=IDENT, epi=L.EPI_PLAIN, epi_ref=None,
-                epi_add=None, epi_x=IDENT, stats=None, out=None):
+                epi_add=None, epi_x=IDENT, stats=None, out=None, tc=False):
     N, Hs, Ws, Cs = src.shape
     Hd, Wd, Cd = out_hw_c
     dst = out if out is not None else empty(N, Hd, Wd, Cd, like=src)
     p = L.ConvParams(L.ptr(src), L.ptr(wt), L.ptr(bias), L.ptr(dst), in_x.c(), epi, L.ptr(epi_ref),
                      L.ptr(epi_add), epi_x.c(), L.ptr(stats), N, Hs, Ws, Cs, Hd, Wd, Cd, k, k, stride, pad, mode)
-    L.check(L.lib.cvae_conv_gather(p, L.stream()), f"conv_gather N={N} {Hs}x{Ws}x{Cs}->{Hd}x{Wd}x{Cd} k{k}s{stride} mode{mode}")
+    fn = L.lib.cvae_conv_gather_tc if tc else L.lib.cvae_conv_gather
+    L.check(fn(p, L.stream()), f"conv_gather tc={int(tc)} N={N} {Hs}x{Ws}x{Cs}->{Hd}x{Wd}x{Cd} k{k}s{stride} mode{mode}")
     return dst
 
 
-def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulate=False):
+def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulate=False, tc=None):
     """grad_out (torch layout [Cb][Ca_real][k*k]) = sum_pix xa(ga[gather]) (x) xb(db)."""
     N, Ha, Wa, Ca = ga.shape
     _, Hq, Wq, Cb = db.shape
     taps = k * k
     rows = taps * Ca
-    splits = L.lib.cvae_wgrad_splits(N * Hq * Wq, rows, Cb)
+    pixels = N * Hq * Wq
+    if tc is None:
+        tc = _TC and bool(L.lib.cvae_wgrad_tc_eligible(pixels, rows, Cb))
+    splits = (L.lib.cvae_wgrad_tc_splits if tc else L.lib.cvae_wgrad_splits)(pixels, rows, Cb)
     partial = empty(splits, rows, Cb, like=ga)
     p = L.WgradParams(L.ptr(ga), L.ptr(db), xa.c(), xb.c(), L.ptr(partial), splits, N, Ha, Wa, Ca, Hq, Wq, Cb,
                       k, k, stride, pad)
-    L.check(L.lib.cvae_conv_wgrad(p, L.stream()), f"conv_wgrad {Ha}x{Wa}x{Ca} / {Hq}x{Wq}x{Cb} k{k}s{stride}")
+    fn = L.lib.cvae_conv_wgrad_tc if tc else L.lib.cvae_conv_wgrad
+    L.check(fn(p, L.stream()), f"conv_wgrad tc={int(tc)} {Ha}x{Wa}x{Ca} / {Hq}x{Wq}x{Cb} k{k}s{stride}")
     L.check(L.lib.cvae_wgrad_reduce(L.ptr(partial), splits, taps, Ca, Ca if ca_real is None else ca_real, Cb,
                                     L.ptr(grad_out), int(accumulate), L.stream()), "wgrad_reduce")
     return grad_out

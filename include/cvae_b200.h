@@ -116,6 +116,26 @@ int cvae_wgrad_reduce(const float* partial, int splits, int taps, int ca, int ca
 int cvae_pack_weight(const float* src, float* dst, int A, int A_pad, int B, int taps, int src_bat,
                      int src_ld, cvae_stream_t s);
 
+/* ---- tensor-core (tcgen05 / TMEM, 3xTF32) variant of the gather family ----------------------------
+ * Same contract and parameter block as cvae_conv_gather, for layers with Cs % 16 == 0 and
+ * Cd % 16 == 0 (the GEMM-shaped ones: vit_backbone.py:74-90 stem.3..12, :124-156 decoder.0..15 and
+ * ResBlocks, the ViT / adapter nn.Linear layers).  `wt` must have been produced by
+ * cvae_tc_pack_weight: [tap][ceil(A_pad/32)][hi|lo][B][32] floats, each value split into
+ * tf32 hi + lo and each 128-byte row swizzled, i.e. the shared-memory image of the UMMA B operand.
+ * Accuracy: hi*hi + lo*hi + hi*lo with fp32 accumulation, ~2^-21 relative per product. */
+int cvae_tc_eligible(int Cs, int Cd, int64_t M);          /* 1 when cvae_conv_gather_tc accepts the shape */
+int64_t cvae_tc_pack_floats(int A_pad, int B, int taps);  /* size of the packed weight buffer, in floats */
+int cvae_tc_pack_weight(const float* src, float* dst, int A, int A_pad, int B, int taps, int src_bat,
+                        int src_ld, cvae_stream_t s);     /* arguments as cvae_pack_weight */
+int cvae_conv_gather_tc(const cvae_conv_params_t* p, cvae_stream_t s);
+/* Tensor-core weight gradient: same contract, parameter block and partial layout as cvae_conv_wgrad
+ * (followed by cvae_wgrad_reduce), for Cb % 16 == 0.  The gathered operand is staged straight into
+ * tensor memory (lane = (tap, ca) row, columns = pixels); the split count must come from
+ * cvae_wgrad_tc_splits (it also bounds the length of one accumulation chain). */
+int cvae_wgrad_tc_eligible(int pixels, int rows, int Cb);
+int cvae_wgrad_tc_splits(int pixels, int rows, int Cb);
+int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s);
+
 /* ---- BatchNorm (training mode: batch statistics; eval: running statistics) -------------------
  * nn.BatchNorm2d / nn.BatchNorm1d, eps 1e-5, momentum 0.1 (vit_backbone.py:76-89;
  * vessel_analysis/00_core/models.py:227,237; causal_cascade/models.py:36). */

@@ -24,7 +24,7 @@ def built():
 def test_header_symbols_exported():
     from causal_vae_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "cvae_b200.h")).read()
-    declared = set(re.findall(r"^\s*int\s+(cvae_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t)\s+(cvae_\w+)\s*\(", hdr, flags=re.M))
     assert declared, "no declarations parsed"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:

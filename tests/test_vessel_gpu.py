@@ -144,8 +144,14 @@ def test_graph_replay_equals_eager():
     for _ in range(3):
         tb.load_batch(x, m, t, eps)
         lb.append(float(tb.replay()[0]))
+    # step 1 is the same computation (only atomic ordering differs).  Later steps diverge by chaotic
+    # amplification, not by a replay defect: Adam at lr 1e-3 moves every parameter by ~lr * sign(g)
+    # in its first steps, and the sign of rounding-noise gradients (e.g. biases feeding a BatchNorm,
+    # whose true gradient is 0) differs run to run -- two EAGER runs differ by the same amount
+    # (scripts/diag_determinism.py).
+    assert abs(la[0] - lb[0]) <= 1e-6 * abs(la[0]), (la, lb)
     for a, b in zip(la, lb):
-        assert abs(a - b) <= 1e-5 * abs(a), (la, lb)
+        assert abs(a - b) <= 3e-4 * abs(a), (la, lb)
     assert la[2] < la[0]
     # Adam's g/sqrt(v) amplifies last-bit (atomic-order) differences of tiny gradients: loose bound
     for (k, pa), (_, pb) in zip(model_a.state_dict().items(), model_b.state_dict().items()):
