@@ -111,15 +111,20 @@ def run_reference(args):
 
 
 def dominant_kernel_probe(torch, ops, L):
-    """Time the FLOP-dominant kernel (implicit-GEMM gather, 64-channel tile) alone on its heaviest
-    instance of the step: ResBlock(64) 3x3 conv at 32x32, B = 64 (4.83 GFLOP per launch)."""
-    N, Hh, C = B_PER_GPU, 32, 64
+    """Time the dominant kernel alone, live, with CUDA events on the launching stream: the tcgen05
+    implicit-GEMM gather kernel on its heaviest instance of the step, a ResBlock(64) 3x3 conv at
+    64x64, B = 64 (19.3 GFLOP of algorithmic work per launch; 3xTF32 issues 3x that on the tensor
+    cores), with the BatchNorm+LeakyReLU operand transform and the statistics epilogue it runs with
+    inside the step.  L2 is flushed between launches."""
+    N, Hh, C = B_PER_GPU, 64, 64
     src = torch.randn(N, Hh, Hh, C, device="cuda")
-    wt = torch.randn(9, C, C, device="cuda") * 0.05
+    w = torch.randn(C, C, 9, device="cuda") * 0.05            # torch layout [Cout][Cin][taps]
+    wt = ops.pack_weight(w, C, C, C, 9, True, C, tc=True)
     scale, shift, cen = (torch.randn(C, device="cuda") for _ in range(3))
     stats = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
     xf = ops.XF(scale, shift, 0.2, cen)
-    run = lambda: ops.conv_gather(src, wt, None, (Hh, Hh, C), 3, 1, 1, L.MODE_GATHER, in_x=xf, epi=L.EPI_STATS, stats=stats)
+    run = lambda: ops.conv_gather(src, wt, None, (Hh, Hh, C), 3, 1, 1, L.MODE_GATHER, in_x=xf, epi=L.EPI_STATS,
+                                  stats=stats, tc=True)
     for _ in range(3):
         run()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -234,9 +239,10 @@ def run_native(args):
         "gpu_launches": per_step_calls * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_burst, "unit": "TFLOP/s", "frac": tf / bf16_burst,
-                     "traffic": None, "kernel": "igemm_gather_kernel<64> (ResBlock(64) conv3x3 @32x32, B=64)",
+                     "traffic": None, "kernel": "igemm_tc_kernel (tcgen05 3xTF32; ResBlock(64) conv3x3 @64x64, B=64)",
                      "flops_per_launch": k_flops, "ms_per_launch": k_ms,
-                     "peak_source": f"{how} bf16 burst (fp32-exact math: the TF32 rate is ~half of it)"},
+                     "peak_source": f"{how} bf16 burst; fp32-grade 3xTF32 math can reach at most 1/6 of it "
+                                    "(tf32 = half the bf16 rate, three MMAs per product)"},
         "step_roofline": {"bound": "hbm", "bytes_per_sample": BYTES_PER_SAMPLE, "peak_gbs": hbm,
                           "roofline_samples_per_s_per_gpu": hbm * 1e9 / BYTES_PER_SAMPLE,
                           "frac": (value / world) / (hbm * 1e9 / BYTES_PER_SAMPLE),

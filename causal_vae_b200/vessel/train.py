@@ -4,6 +4,7 @@ import torch
 
 from .. import functional as F
 from ..optim import FlatParams, FusedClipAdam
+from ..parallel import allreduce_gradients
 from .models import CONFIG
 
 
@@ -52,7 +53,7 @@ class VesselTrainer:
 
     def _allreduce(self):
         if self.distributed:
-            torch.distributed.all_reduce(self.flat.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            allreduce_gradients(self.flat.grad, group=self.pg)
 
     def step(self, x, m, t, eps=None):
         self.model.train()
