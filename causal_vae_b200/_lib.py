@@ -94,6 +94,12 @@ _SIGS = {
     "cvae_bce_fwd": [vp, vp, i64, vp, vp],
     "cvae_bce_bwd": [vp, vp, i64, vp, f32, vp, vp],
     "cvae_finish_scalar": [vp, f32, vp, vp],
+    "cvae_argmax_rows": [vp, i64, i32, vp, vp],
+    "cvae_one_hot": [vp, i64, i32, vp, vp],
+    "cvae_softmax_ce_fwd": [vp, vp, i64, i32, vp, vp],
+    "cvae_softmax_ce_bwd": [vp, vp, i64, i32, vp, f32, vp, vp],
+    "cvae_uniform_kl_fwd": [vp, i64, i32, vp, vp],
+    "cvae_uniform_kl_bwd": [vp, i64, i32, vp, f32, vp, vp],
     "cvae_do_expand": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
     "cvae_rowdiff_l2": [vp, vp, vp, i64, i64, i32, vp],
     "cvae_sumsq": [vp, i64, vp, vp],

@@ -462,3 +462,72 @@ def mse_sum(a, b, mul=1.0):
 
 def bce_sum(p, y, mul=1.0):
     return _PairLoss.apply(p, y, 1, float(mul))
+
+
+def mse_mean(a, b):
+    """F.mse_loss(a, b, reduction='mean') (latent_translator/engine.py:25)."""
+    return _PairLoss.apply(a, b, 0, 1.0 / a.numel())
+
+
+def kld_mean(mu, logvar):
+    """-0.5 * mean(1 + logvar - mu^2 - exp(logvar)) (latent_translator/engine.py:26)."""
+    return _Kld.apply(mu, logvar, 1.0 / mu.numel())
+
+
+# ---- treatment labels -------------------------------------------------------------------------------
+def argmax_rows(t):
+    """torch.argmax(t, dim=1) -> int64 [rows] (mnist_test/01_baseline_causal_vae/train.py:38)."""
+    tc = t.contiguous()
+    rows, T = tc.shape
+    out = torch.empty(rows, dtype=torch.int64, device=tc.device)
+    L.check(L.lib.cvae_argmax_rows(L.ptr(tc), rows, T, L.ptr(out), L.stream()), "argmax_rows")
+    return out
+
+
+def one_hot(idx, T):
+    """F.one_hot(idx, T).float() (causal_cascade/models.py:71)."""
+    if idx.dtype != torch.int64:
+        raise RuntimeError(f"one_hot expects int64 class indices, got {idx.dtype}")
+    ic = idx.contiguous()
+    out = ops.empty(ic.numel(), T, like=ic)
+    L.check(L.lib.cvae_one_hot(L.ptr(ic), ic.numel(), T, L.ptr(out), L.stream()), "one_hot")
+    return out
+
+
+class _SoftmaxLoss(torch.autograd.Function):
+    """kind 0: F.cross_entropy(logits, target) (mean over rows); kind 1:
+    F.kl_div(log_softmax(logits), U(1/T), reduction='batchmean'); both times `mul`."""
+
+    @staticmethod
+    def forward(ctx, logits, target, kind, mul):
+        lc = logits.contiguous()
+        rows, T = lc.shape
+        acc = ops.zeros(1, dtype=torch.float64, like=lc)
+        if kind == 0:
+            L.check(L.lib.cvae_softmax_ce_fwd(L.ptr(lc), L.ptr(target), rows, T, L.ptr(acc), L.stream()), "ce_fwd")
+        else:
+            L.check(L.lib.cvae_uniform_kl_fwd(L.ptr(lc), rows, T, L.ptr(acc), L.stream()), "ukl_fwd")
+        ctx.save_for_backward(lc)
+        ctx.target, ctx.kind, ctx.scale = target, kind, mul / rows
+        return ops.finish_scalar(acc, mul / rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        (lc,) = ctx.saved_tensors
+        rows, T = lc.shape
+        d = torch.empty_like(lc)
+        if ctx.kind == 0:
+            L.check(L.lib.cvae_softmax_ce_bwd(L.ptr(lc), L.ptr(ctx.target), rows, T, L.ptr(g.contiguous()), ctx.scale,
+                                              L.ptr(d), L.stream()), "ce_bwd")
+        else:
+            L.check(L.lib.cvae_uniform_kl_bwd(L.ptr(lc), rows, T, L.ptr(g.contiguous()), ctx.scale, L.ptr(d),
+                                              L.stream()), "ukl_bwd")
+        return d, None, None, None
+
+
+def cross_entropy(logits, target):
+    return _SoftmaxLoss.apply(logits, target.contiguous(), 0, 1.0)
+
+
+def uniform_kl_batchmean(logits, mul=1.0):
+    return _SoftmaxLoss.apply(logits, None, 1, float(mul))

@@ -1,0 +1,54 @@
+"""The adversarial training step of mnist_test/01_baseline_causal_vae/train.py:36-89 (06 variant:
+mnist_test/06_model_experiment/train.py:41-96) on the native kernels: discriminator step
+(cross-entropy on argmax(t)) then VAE step (BCE_sum + beta*KL + morph + confusion loss)."""
+import torch
+
+from .. import functional as F
+from ..optim import FlatParams, FusedClipAdam
+from .models import CONFIG
+
+
+def vae_loss(vae, disc, x, m, t, eps=None, eps_adv=None, beta=None, lambda_adv=None):
+    """(loss, recon, kld, morph, adv) of train.py:65-87; 6-tuple models use the Gaussian NLL morph term."""
+    beta = CONFIG["BETA"] if beta is None else beta
+    lambda_adv = CONFIG["LAMBDA_ADV"] if lambda_adv is None else lambda_adv
+    out = vae(x, m, t, eps)
+    recon_x, m_hat, mu, logvar = out[:4]
+    l_rec = F.bce_sum(recon_x.reshape(-1, 784), x.reshape(-1, 784))
+    l_kld = F.kld_loss(mu, logvar, beta)
+    if len(out) == 4:
+        l_m = F.mse_sum(m_hat, m, 100.0)
+    else:
+        l_m = F.gauss_nll_loss(m, out[4], out[5])
+    logits = disc(vae.reparameterize(mu, logvar, eps_adv))
+    l_adv = F.uniform_kl_batchmean(logits, lambda_adv * 100.0)
+    return l_rec + l_kld + l_m + l_adv, l_rec, l_kld, l_m, l_adv
+
+
+def disc_loss(vae, disc, x, m, t, eps=None):
+    """train.py:41-55: z from a no-grad VAE pass, CE(D(z), argmax t)."""
+    with torch.no_grad():
+        _, _, z = vae.encode(x, m, t, eps)
+    return F.cross_entropy(disc(z), F.argmax_rows(t))
+
+
+class AdversarialTrainer:
+    """opt_d / opt_vae = Adam(lr=CONFIG['LR']) over flat parameter buffers (train.py:21-22)."""
+
+    def __init__(self, vae, disc, lr=None):
+        lr = CONFIG["LR"] if lr is None else lr
+        self.vae, self.disc = vae, disc
+        self.opt_vae = FusedClipAdam(FlatParams(vae), lr)
+        self.opt_d = FusedClipAdam(FlatParams(disc), lr)
+
+    def step(self, x, m, t, eps_d=None, eps=None, eps_adv=None):
+        self.vae.train(); self.disc.train()
+        self.opt_d.zero_grad()
+        loss_d = disc_loss(self.vae, self.disc, x, m, t, eps_d)
+        loss_d.backward()
+        self.opt_d.step()
+        self.opt_vae.zero_grad()
+        losses = vae_loss(self.vae, self.disc, x, m, t, eps, eps_adv)
+        losses[0].backward()
+        self.opt_vae.step()
+        return loss_d, losses

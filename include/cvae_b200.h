@@ -267,6 +267,22 @@ int cvae_bce_bwd(const float* p, const float* y, int64_t n, const float* g, floa
 /* double accumulator -> float scalar (optionally scaled) */
 int cvae_finish_scalar(const double* acc, float mul, float* out, cvae_stream_t s);
 
+/* ---- treatment labels: argmax / one-hot (integer, bit-exact) and softmax losses on [rows, T] logits -----
+ * torch.argmax(t, dim=1) (first maximum; mnist_test/01_baseline_causal_vae/train.py:38),
+ * F.one_hot(t, T).float() (causal_cascade/models.py:71),
+ * F.cross_entropy(logits, idx) summed over rows (train.py:55; the caller scales by 1/rows), and
+ * F.kl_div(log_softmax(logits), U(1/T), 'batchmean') * rows (train.py:78-82).  Backward writes
+ * dlogits = (softmax - onehot) * g*gmul  resp.  (softmax - 1/T) * g*gmul; g is a device scalar or NULL. */
+int cvae_argmax_rows(const float* t, int64_t rows, int T, int64_t* out, cvae_stream_t s);
+int cvae_one_hot(const int64_t* idx, int64_t rows, int T, float* out, cvae_stream_t s);
+int cvae_softmax_ce_fwd(const float* logits, const int64_t* target, int64_t rows, int T, double* sum,
+                        cvae_stream_t s);
+int cvae_softmax_ce_bwd(const float* logits, const int64_t* target, int64_t rows, int T, const float* g,
+                        float gmul, float* dlogits, cvae_stream_t s);
+int cvae_uniform_kl_fwd(const float* logits, int64_t rows, int T, double* sum, cvae_stream_t s);
+int cvae_uniform_kl_bwd(const float* logits, int64_t rows, int T, const float* g, float gmul,
+                        float* dlogits, cvae_stream_t s);
+
 /* ---- counterfactual: do(M_k := M_k + delta | M_k := value) over all K concepts ------------------
  * (generate_counterfactual.py:86-88; analyze_vessel.py:101-104).  Builds the decoder-adapter input
  * rows [m' | z] for S sources x K concepts: row (s*K + k) = cat(do_k(m[s]), z[s]). */
