@@ -79,10 +79,12 @@ def _pack_fwd(u, Cs_phys, tc=False):
     return ops.pack_weight(w, w.shape[1], Cs_phys, w.shape[0], 1, True, w.shape[1], tc=tc)  # [out][in] -> [in_pad][out]
 
 
-def _pack_dgrad(u, grad_cols, tc=False):
+def _pack_dgrad(u, grad_cols, tc=False, dy_cols=None):
     """weights for the input-gradient: [tap][C_of_dy][C_of_dx]."""
     w = u.mod.weight
     taps = u.k * u.k
+    if u.kind == "linear" and dy_cols is not None and dy_cols != w.shape[0]:
+        return ops.pack_weight(w, w.shape[0], dy_cols, grad_cols, 1, False, w.shape[1], tc=tc)  # zero rows for padded dy
     if u.kind == "conv":      # [Cout][Cin][tap] -> [tap][Cout][Cin]
         return ops.pack_weight(w, w.shape[0], w.shape[0], w.shape[1], taps, False, w.shape[1], tc=tc)
     if u.kind == "convT":     # [Cin][Cout][tap] -> [tap][Cout][Cin]
@@ -180,8 +182,16 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
         return None
     cols = Cs if grad_cols is None else grad_cols
     mode = L.MODE_GATHER if u.kind == "convT" else L.MODE_SCATTER
+    dy_cols = None
+    if u.kind == "linear" and (Cd % 4 != 0 or Cd < 8):
+        # narrow heads (e.g. 10 treatment logits, 4 concepts): the gather kernels read 128-bit channel
+        # vectors of at least 8 channels, so the gradient rows are zero-padded (matching zero weight rows)
+        dy_cols = max(8, (Cd + 3) // 4 * 4)
+        dyp = ops.zeros(N, 1, 1, dy_cols, like=dy)
+        ops.copy_cols(dy, Cd, 0, dyp, dy_cols, 0, N, Cd)
+        dy, Cd = dyp, dy_cols
     tc = ops.tc_eligible(Cd, cols, _min_phase_rows(N, Hs, Ws, u.stride, mode == L.MODE_SCATTER))
-    wt = _pack_dgrad(u, cols, tc)
+    wt = _pack_dgrad(u, cols, tc, dy_cols)
     if prev_entry is not None and not prev_entry.x.identity:
         return ops.conv_gather(dy, wt, None, (Hs, Ws, cols), u.k, u.stride, u.pad, mode, epi=L.EPI_DACT,
                                epi_ref=prev_entry.t, epi_add=add, epi_x=prev_entry.x, stats=prev_stats, tc=tc)

@@ -593,14 +593,14 @@ extern "C" int cvae_conv_gather(const cvae_conv_params_t* p, cvae_stream_t s) {
     int gx = (maxM + 127) / 128;
     gx = min(gx, kNumSMs * 8);
     dim3 grid(gx, 1, g.nphase);
-    switch (p->Cd) {
-      case 1: conv_pix_kernel<1><<<grid, 128, smem, st>>>(g); break;
-      case 2: conv_pix_kernel<2><<<grid, 128, smem, st>>>(g); break;
-      case 4: conv_pix_kernel<4><<<grid, 128, smem, st>>>(g); break;
-      case 16: conv_pix_kernel<16><<<grid, 128, smem, st>>>(g); break;
-      case 32: conv_pix_kernel<32><<<grid, 128, smem, st>>>(g); break;
+#define CVAE_PIX_CASE(n) case n: conv_pix_kernel<n><<<grid, 128, smem, st>>>(g); break;
+    switch (p->Cd) {   // narrow heads (logits, morphology vectors): any width up to 16, and 32
+      CVAE_PIX_CASE(1) CVAE_PIX_CASE(2) CVAE_PIX_CASE(3) CVAE_PIX_CASE(4) CVAE_PIX_CASE(5) CVAE_PIX_CASE(6)
+      CVAE_PIX_CASE(7) CVAE_PIX_CASE(8) CVAE_PIX_CASE(9) CVAE_PIX_CASE(10) CVAE_PIX_CASE(11) CVAE_PIX_CASE(12)
+      CVAE_PIX_CASE(13) CVAE_PIX_CASE(14) CVAE_PIX_CASE(15) CVAE_PIX_CASE(16) CVAE_PIX_CASE(32)
       default: return CVAE_ERR_UNSUPPORTED_SHAPE;
     }
+#undef CVAE_PIX_CASE
   }
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;

@@ -41,7 +41,32 @@ def req(P):
     return P
 
 
-def check_grads(model, ref64, ref32=None, floor=1e-4, skip=()):
+def pert_response(oracle_grads, P, seeds=(1, 2, 3, 4, 5), eps=3e-6):
+    """Relative response of the fp32 oracle's gradients to `eps`-relative weight perturbations.
+    End-to-end gradients are discontinuous at fp32 rounding scale: ONE pre-activation that sits within
+    rounding distance of a ReLU / LeakyReLU kink (observed: cascade enc_fc.0 unit (1,19) = -6.2e-7 in
+    fp64, +1.5e-8 on the GPU) flips a derivative and moves whole gradient tensors by 1e-2..1e-1.  The
+    reference's own arithmetic shows the same response -- its fp32 gradients move by exactly that amount
+    under 3e-6-relative weight perturbations, i.e. perturbations BELOW the 1e-5 forward tolerance (and the
+    size of the 3xTF32 forward error, 2-6e-6) -- which therefore floors the tolerance per tensor."""
+    base = oracle_grads({k: v.clone() for k, v in P.items()})
+    resp = {k: 0.0 for k in base}
+    for seed in seeds:
+        gen = torch.Generator().manual_seed(seed)
+        Pp = {k: v.clone() for k, v in P.items()}
+        for k, v in Pp.items():
+            if v.is_floating_point() and "running" not in k:
+                v.mul_(1 + eps * torch.randn(v.shape, generator=gen))
+        gp = oracle_grads(Pp)
+        for k in resp:
+            if base[k] is not None:
+                resp[k] = max(resp[k], rel(gp[k], base[k]))
+    return resp
+
+
+def check_grads(model, ref64, ref32=None, floor=1e-4, skip=(), pert=None):
+    """1e-4 of each tensor's max |g| against the fp64 oracle, widened only where the reference's own
+    fp32 arithmetic does not reproduce to that level (4 x fp32-vs-fp64 discrepancy, 4 x kink response)."""
     worst = []
     for k, p in model.named_parameters():
         if k in skip:
@@ -52,7 +77,7 @@ def check_grads(model, ref64, ref32=None, floor=1e-4, skip=()):
             continue
         assert p.grad is not None, f"no grad for {k}"
         noise = rel(ref32[k].grad, g64) if ref32 is not None else 0.0
-        tol = max(floor, 4 * noise)
+        tol = max(floor, 4 * noise, 4 * (pert[k] if pert else 0.0))
         e = rel(p.grad, g64)
         worst.append((e / tol, k, e, noise))
     worst.sort(reverse=True)
@@ -228,7 +253,13 @@ def test_cascade_forward_loss_grads():
     for n, a, b in zip(["loss", "recon", "m_loss"], got, ref):
         closef(a, b)
         closef(a, g[n], 2e-5)
-    check_grads(model, P64, P32)
+
+    def og(Pp):
+        Pp = req(Pp)
+        o = O.cascade_forward(Pp, x, m, t, eps, train=True)
+        O.cascade_loss(o[0], x, o[1], m, o[2], o[3])[0].backward()
+        return {k: (v.grad if v.is_floating_point() else None) for k, v in Pp.items()}
+    check_grads(model, P64, P32, pert=pert_response(og, P))
     # BatchNorm1d running statistics of mechanism_net.1 after one training forward
     sd = model.state_dict()
     for k in ("mechanism_net.1.running_mean", "mechanism_net.1.running_var"):
@@ -283,7 +314,13 @@ def test_latent_translator_forward_loss_grads():
     for n, a, b in zip(["loss", "recon", "kld"], got, ref):
         closef(a, b)
         closef(a, g[n], 2e-5)
-    check_grads(model, P64, P32)
+
+    def og(Pp):
+        Pp = req(Pp)
+        r, _, mm, ll = O.lt_forward(Pp, x, eps, train=True)
+        O.lt_loss(r, x, mm, ll)[0].backward()
+        return {k: (v.grad if v.is_floating_point() else None) for k, v in Pp.items()}
+    check_grads(model, P64, P32, pert=pert_response(og, P))
 
     # encode-only path used by extract_vit_latents (engine.py:46-50), eval mode
     model.eval()
