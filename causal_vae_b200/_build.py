@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcvae_b200.so")
-SOURCES = ["conv.cu", "conv_tc.cu", "wgrad_tc.cu", "skinny.cu", "norm.cu", "attention.cu", "elementwise.cu", "loss_optim.cu", "classify.cu"]
+SOURCES = ["conv.cu", "conv_tc.cu", "conv_halo_tc.cu", "wgrad_tc.cu", "skinny.cu", "norm.cu", "attention.cu", "elementwise.cu", "loss_optim.cu", "classify.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -31,6 +31,8 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("CVAE_TIMING") == "1":       # role-level wait accounting in the tensor-core kernels (debug)
+        flags.append("-DCVAE_TIMING")
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))

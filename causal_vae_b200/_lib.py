@@ -100,6 +100,7 @@ _SIGS = {
     "cvae_softmax_ce_bwd": [vp, vp, i64, i32, vp, f32, vp, vp],
     "cvae_uniform_kl_fwd": [vp, i64, i32, vp, vp],
     "cvae_uniform_kl_bwd": [vp, i64, i32, vp, f32, vp, vp],
+    "cvae_debug_read": [vp, i32],
     "cvae_do_expand": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
     "cvae_rowdiff_l2": [vp, vp, vp, i64, i64, i32, vp],
     "cvae_sumsq": [vp, i64, vp, vp],

@@ -1,0 +1,502 @@
+// Halo-tile tcgen05 / TMEM implicit-GEMM convolution for sm_100a (3xTF32) -- second generation of
+// conv_tc.cu for conv-shaped layers (k > 1).
+//
+// conv_tc.cu gathers the A operand once per TAP (9x for a 3x3 conv): ncu showed it bound by the
+// producers' instruction stream (~100 warp instructions per 16-byte vector, tensor pipe 15 % busy).
+// Here an input HALO TILE is staged once per 32-channel block and every tap reads it through its own
+// shared-memory descriptor:
+//
+//   * an M tile is a 16 x 8 patch of output positions ("q-space") of one image; MMA row r = 8*rh + rw;
+//   * the halo tile is stored slot-major (slot = one pixel x 32 channels = 128 bytes, hi and lo tf32
+//     planes), row pitch C slots, with the 128B swizzle applied on ADDRESS bits (chunk ^= bits [7,10));
+//   * tap (di, dj) is the K-major SWIZZLE_128B operand whose start address is shifted by
+//     (di*C + dj) slots and whose 8-row-group pitch (stride byte offset) is C*128 bytes.  The tensor
+//     core applies the swizzle on absolute address bits (measured: scripts/umma_probe.cu -- any
+//     128-byte-aligned start and any 128-byte-multiple group pitch read back exactly, descriptor
+//     base_offset = 0), so all taps share one staged copy: producer work drops 6.4x for a 3x3 conv;
+//   * stride-2 gathers (Conv2d s2 forward, ConvTranspose2d input-gradient) stage the four input
+//     parity planes one after the other (a stage = one k-block of one plane), each tap reading the
+//     plane of its parity; scatter mode (ConvTranspose2d forward, Conv2d s2 input-gradient) keeps one
+//     TMEM accumulator per output phase, all fed from the same staged tile;
+//   * weights (pre-split, pre-swizzled image from tc_pack_weight_kernel) stream through their own
+//     TMA ring, one (tap, k-block) per stage;
+//   * epilogue as in conv_tc.cu (TMEM -> registers -> padded smem -> coalesced 128-bit stores with
+//     fused bias / BatchNorm statistics / activation-derivative + BN-backward sums).
+#include "common.cuh"
+#include "conv_args.cuh"
+#include "tc_common.cuh"
+
+namespace cvae {
+
+using namespace tc;
+
+constexpr int kHTH = 16, kHTW = 8;                 // q-space tile: 16 rows x 8 columns = 128 MMA rows
+constexpr int kHMaxSlots = 184;                    // (16+2)*(8+2) = 180, rounded so a half is 23 KiB
+constexpr int kHHalf = kHMaxSlots * 128;           // bytes of one tf32 plane (hi or lo) of an A stage
+constexpr int kHAStage = 2 * kHHalf;
+constexpr int kHNA = 2;                            // A ring depth
+constexpr int kHProdWarps = 8;
+constexpr int kHThreads = (kHProdWarps + 2 + 4) * 32;   // + MMA warp + weight-loader warp + 4 epilogue warps
+constexpr int kHItems = (kHMaxSlots * 8 + kHProdWarps * 32 - 1) / (kHProdWarps * 32);   // 16-byte vectors per producer thread
+constexpr int kHEpiLd = 36;
+constexpr int kHEpiBytes = 128 * kHEpiLd * 4 + 128 * 4;   // one staging tile + its row -> pixel table
+
+struct HaloTap { int off; int widx; int phase; };       // off: slot offset of the tap window inside the staged plane
+struct HaloPlane { int pr, pc, imin, jmin, ntaps; HaloTap taps[16]; };
+struct HaloPlan {
+  int nplanes, R, C;          // staged rows / columns (uniform over planes)
+  int tiles_h, tiles_w, tiles_n, BN, NB;
+  int Hq, Wq;                 // q-space extent per image
+  int ph[4], pw[4];           // output offset of each phase
+  HaloPlane plane[4];
+};
+
+#ifdef CVAE_TIMING
+// role-level wait accounting (debug builds only): clock64 deltas summed per role, read by cvae_debug_read
+__device__ unsigned long long g_halo_dbg[16];
+#define T_DECL unsigned long long t_acc[4] = {0, 0, 0, 0}; unsigned long long t_0 = clock64(), t_1;
+#define T_WAIT(i, stmt) { t_1 = clock64(); stmt; t_acc[i] += clock64() - t_1; }
+#define T_FLUSH(base, n) { for (int i_ = 0; i_ < n; ++i_) atomicAdd(&g_halo_dbg[base + i_], t_acc[i_]); atomicAdd(&g_halo_dbg[base + n], clock64() - t_0); }
+#else
+#define T_DECL
+#define T_WAIT(i, stmt) { stmt; }
+#define T_FLUSH(base, n) {}
+#endif
+
+__device__ __forceinline__ void hbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct HTile { int n, h0, w0, n0; };
+__device__ __forceinline__ HTile h_decode(const HaloPlan& p, int t) {
+  HTile o;
+  o.n0 = (t % p.tiles_n) * p.BN;
+  int sp = t / p.tiles_n;
+  o.w0 = (sp % p.tiles_w) * kHTW; sp /= p.tiles_w;
+  o.h0 = (sp % p.tiles_h) * kHTH;
+  o.n = sp / p.tiles_h;
+  return o;
+}
+
+__global__ void __launch_bounds__(kHThreads, 1)
+conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ HaloPlan p, const int total) {
+  extern __shared__ uint8_t dsm_raw[];
+  __shared__ __align__(8) uint64_t s_afull[kHNA], s_aempty[kHNA];
+  __shared__ __align__(8) uint64_t s_bfull[4], s_bempty[4];
+  __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ double s_part[4][64];
+  __shared__ double s_stat[512];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN, NB = p.NB;
+  const int KB = (a.Cs + 31) >> 5;
+  const uint32_t bstage = 256u * BN;
+  const uint32_t acc_cols = (uint32_t)(a.nphase * BN);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
+  uint8_t* dsm_gen = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
+  const uint32_t dsm = smem_u32(dsm_gen);
+  const uint32_t b_base = dsm + kHNA * kHAStage;
+  float* ebuf = reinterpret_cast<float*>(dsm_gen + kHNA * kHAStage + NB * bstage);
+
+  for (int i = tid; i < 512; i += kHThreads) s_stat[i] = 0.0;
+  if (warp == kHProdWarps) {
+    if (lane == 0) {
+      for (int i = 0; i < kHNA; ++i) { mbar_init(smem_u32(&s_afull[i]), kHProdWarps); mbar_init(smem_u32(&s_aempty[i]), 1); }
+      for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&s_bfull[i]), 1); mbar_init(smem_u32(&s_bempty[i]), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), 4); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&s_tmem), tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp < kHProdWarps) {
+    // ============================== A producers: halo tile -> swizzled hi / lo planes ==============================
+    const int chunk = tid & 7;
+    const int nslots = p.R * p.C;
+    int it_i[kHItems], it_j[kHItems], it_s[kHItems];
+#pragma unroll
+    for (int k = 0; k < kHItems; ++k) {
+      const int s = (tid >> 3) + k * (kHProdWarps * 4);
+      it_s[k] = s < nslots ? s : -1;
+      it_i[k] = s / p.C; it_j[k] = s % p.C;
+    }
+    uint32_t it = 0;
+    T_DECL
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const HTile tl = h_decode(p, t);
+      const size_t img = (size_t)tl.n * a.Hs * a.Ws;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int c = kb * 32 + chunk * 4;
+        const bool cok = c < a.Cs;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), ce = sh;
+        if (a.in_affine && cok) {
+          sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c));
+          sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c));
+          if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c));
+        }
+        for (int pl = 0; pl < p.nplanes; ++pl, ++it) {
+          const HaloPlane& P = p.plane[pl];
+          const int bh = (tl.h0 + P.imin) * a.is + P.pr, bw = (tl.w0 + P.jmin) * a.is + P.pc;
+          float4 v[kHItems];
+          uint32_t okm = 0;
+#pragma unroll
+          for (int k = 0; k < kHItems; ++k) {
+            const int ih = bh + it_i[k] * a.is, iw = bw + it_j[k] * a.is;
+            const bool ok = cok && it_s[k] >= 0 && (unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+              v[k] = __ldg(reinterpret_cast<const float4*>(a.src + (img + (size_t)ih * a.Ws + iw) * a.Cs + c));
+              okm |= 1u << k;
+            }
+          }
+          const int slot = it % kHNA;
+          T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / kHNA) & 1u) ^ 1u))
+          uint8_t* sA = dsm_gen + (size_t)slot * kHAStage;
+#pragma unroll
+          for (int k = 0; k < kHItems; ++k) {
+            if (it_s[k] < 0) continue;
+            float4 x = v[k];
+            if ((okm >> k) & 1u) {   // padding stays exactly 0
+              if (a.in_affine) {
+                x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
+                x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+              }
+              if (a.in_act) {
+                x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope);
+                x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope);
+              }
+            }
+            float4 hi, lo;
+            split4(x, hi, lo);
+            const uint32_t off = (uint32_t)it_s[k] * 128u + (uint32_t)(((chunk ^ it_s[k]) & 7) << 4);
+            *reinterpret_cast<float4*>(sA + off) = hi;
+            *reinterpret_cast<float4*>(sA + kHHalf + off) = lo;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_afull[slot]));
+        }
+      }
+    }
+    if (tid == 0) T_FLUSH(0, 1)
+  } else if (warp == kHProdWarps) {
+    // ============================== MMA issuer (one thread) ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      const uint32_t sbo = (uint32_t)p.C * 128u;
+      const uint64_t a_desc_hi = make_smem_desc(0, 16, sbo, kLayoutSw128);     // everything but the address
+      const uint64_t b_desc_hi = make_smem_desc(0, 16, 1024, kLayoutSw128);
+      uint32_t ita = 0, itb = 0, tcount = 0;
+      T_DECL
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        T_WAIT(0, mbar_wait(smem_u32(&s_tempty[acc]), ((tcount >> 1) & 1u) ^ 1u))
+        tc_fence_after();
+        const uint32_t d_base = tmem + acc * acc_cols;
+        uint32_t started = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          const int ksteps = min(32, a.Cs - kb * 32) >> 3;
+          for (int pl = 0; pl < p.nplanes; ++pl, ++ita) {
+            const HaloPlane& P = p.plane[pl];
+            const int aslot = ita % kHNA;
+            T_WAIT(1, mbar_wait(smem_u32(&s_afull[aslot]), (ita / kHNA) & 1u))
+            tc_fence_after();
+            const uint32_t a_hi0 = dsm + (uint32_t)aslot * kHAStage;
+            for (int tp = 0; tp < P.ntaps; ++tp, ++itb) {
+              const HaloTap tap = P.taps[tp];
+              const int bslot = itb % NB;
+              T_WAIT(2, mbar_wait(smem_u32(&s_bfull[bslot]), (itb / NB) & 1u))
+              tc_fence_after();
+              const uint32_t a_hi = a_hi0 + (uint32_t)tap.off * 128u;
+              const uint32_t b_hi = b_base + (uint32_t)bslot * bstage;
+              const uint32_t d_tmem = d_base + (uint32_t)(tap.phase * BN);
+              uint32_t accum = (started >> tap.phase) & 1u;
+              // descriptors differ only in their 14-bit address field: one 64-bit add per k-step
+              // (the issuing thread is latency-bound: rebuilding four descriptors per k-step capped
+              // the issue rate at ~1 MMA / 100 clk -- measured with the CVAE_TIMING build)
+              uint64_t dah = a_desc_hi | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
+              uint64_t dal = a_desc_hi | (uint64_t)(((a_hi + kHHalf) & 0x3FFFFu) >> 4);
+              uint64_t dbh = b_desc_hi | (uint64_t)((b_hi & 0x3FFFFu) >> 4);
+              uint64_t dbl = b_desc_hi | (uint64_t)(((b_hi + 128u * BN) & 0x3FFFFu) >> 4);
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {
+                mma_tf32(d_tmem, dal, dbh, idesc, accum);
+                mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                accum = 1u;
+                dah += 2; dal += 2; dbh += 2; dbl += 2;      // + 32 bytes (8 tf32) along K
+              }
+              started |= 1u << tap.phase;
+              mma_commit(smem_u32(&s_bempty[bslot]));
+            }
+            mma_commit(smem_u32(&s_aempty[aslot]));
+          }
+        }
+        mma_commit(smem_u32(&s_tfull[acc]));
+      }
+      T_FLUSH(2, 3)
+    }
+  } else if (warp == kHProdWarps + 1) {
+    // ============================== weight loader (TMA, one thread) ==============================
+    if (lane == 0) {
+      uint32_t itb = 0;
+      T_DECL
+      const uint32_t bbytes = 128u * BN;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n0 = (t % p.tiles_n) * BN;
+        for (int kb = 0; kb < KB; ++kb)
+          for (int pl = 0; pl < p.nplanes; ++pl) {
+            const HaloPlane& P = p.plane[pl];
+            for (int tp = 0; tp < P.ntaps; ++tp, ++itb) {
+              const int bslot = itb % NB;
+              T_WAIT(0, mbar_wait(smem_u32(&s_bempty[bslot]), ((itb / NB) & 1u) ^ 1u))
+              const uint32_t full = smem_u32(&s_bfull[bslot]);
+              const uint32_t sB = b_base + (uint32_t)bslot * bstage;
+              mbar_arrive_expect_tx(full, 2u * bbytes);
+              const float* wsrc = a.wt + (((size_t)P.taps[tp].widx * KB + kb) * 2) * (size_t)a.Cd * 32 + (size_t)n0 * 32;
+              bulk_g2s(sB, wsrc, bbytes, full);
+              bulk_g2s(sB + bbytes, wsrc + (size_t)a.Cd * 32, bbytes, full);
+            }
+          }
+      }
+      T_FLUSH(6, 1)
+    }
+  } else {
+    // ============================== epilogue warps ==============================
+    // Per 32-column chunk: TMEM -> registers -> padded shared tile (thread = accumulator row), one
+    // named barrier, then coalesced 128-bit global stores (thread = 4 channels x several rows).  The
+    // staging tile and the row -> pixel table are double-buffered when shared memory allows (BN <= 64),
+    // so a chunk costs ONE barrier.  A thread always owns the same channel group, so when the tile
+    // covers all channels in one chunk (BN <= 32, one n-tile) the BatchNorm sums stay in registers
+    // for the whole kernel; otherwise they are reduced per chunk into s_stat (absolute channel index).
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int ew = warp - (kHProdWarps + 2);
+    const int gt = ew * 32 + lane;
+    const int nchunks = (BN + 31) >> 5;
+    const int cw = min(32, BN);                     // BN in {16, 32, 64, 128}: every chunk has this width
+    const int cgs = cw >> 2, rstep = 128 / cgs;
+    const int cg = gt % cgs, r0 = gt / cgs;
+    const bool want_stats = a.epi != CVAE_EPI_PLAIN && a.stats != nullptr;
+    const bool reg_stats = want_stats && nchunks == 1 && p.tiles_n == 1;
+    const int nbuf = BN <= 64 ? 2 : 1;
+    int* s_out2 = reinterpret_cast<int*>(ebuf + nbuf * 128 * kHEpiLd);     // [nbuf][128] row -> output pixel
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    auto reduce_stats = [&](int chan0) {            // all 128 epilogue threads; sums -> s_stat[chan0 + ...]
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        for (int off = 16; off >= cgs; off >>= 1) {   // lanes sharing a channel group: lane, lane + cgs, ...
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+        }
+      }
+      if (lane < cgs) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_part[ew][cg * 4 + j] = s1[j]; s_part[ew][32 + cg * 4 + j] = s2[j]; }
+      }
+      hbar_sync(1, 128);
+      if (gt < 2 * cw) {
+        const int which = gt / cw, cc = gt % cw;
+        s_stat[which * 256 + chan0 + cc] += s_part[0][which * 32 + cc] + s_part[1][which * 32 + cc] +
+                                            s_part[2][which * 32 + cc] + s_part[3][which * 32 + cc];
+      }
+      hbar_sync(1, 128);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
+    };
+    uint32_t tcount = 0, cidx = 0;
+    T_DECL
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
+      const HTile tl = h_decode(p, t);
+      const uint32_t acc = tcount & 1u;
+      T_WAIT(0, mbar_wait(smem_u32(&s_tfull[acc]), (tcount >> 1) & 1u))
+      tc_fence_after();
+      for (int phs = 0; phs < a.nphase; ++phs) {
+        const uint32_t d_tmem = tmem + acc * acc_cols + (uint32_t)(phs * BN) + ((uint32_t)(q * 32) << 16);
+        for (int ch = 0; ch < nchunks; ++ch, ++cidx) {
+          float* eb = ebuf + (cidx % nbuf) * 128 * kHEpiLd;
+          int* so = s_out2 + (cidx % nbuf) * 128;
+          {  // TMEM -> padded shared tile (thread = accumulator row) + this row's output pixel
+            const int row = q * 32 + lane;
+            const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
+            int o = -1;
+            if (qh < p.Hq && qw < p.Wq) {
+              const int oh = qh * a.os + p.ph[phs], ow = qw * a.os + p.pw[phs];
+              if (oh < a.Hd && ow < a.Wd) o = (tl.n * a.Hd + oh) * a.Wd + ow;
+            }
+            so[row] = o;
+            for (int h = 0; h < cw; h += 16) {
+              float r16[16];
+              tmem_ld16(d_tmem + (uint32_t)(ch * 32 + h), r16);
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(eb + row * kHEpiLd + h + i) = make_float4(r16[i], r16[i + 1], r16[i + 2], r16[i + 3]);
+            }
+          }
+          if (phs == a.nphase - 1 && ch == nchunks - 1) {   // accumulators drained: hand the TMEM buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));
+          }
+          hbar_sync(1, 128);
+          const int col = tl.n0 + ch * 32 + cg * 4;
+          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), esc = make_float4(1.f, 1.f, 1.f, 1.f), esh = bias, ece = bias;
+          if (a.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(a.bias + col));
+          if (a.e_affine) {
+            esc = __ldg(reinterpret_cast<const float4*>(a.e_scale + col));
+            esh = __ldg(reinterpret_cast<const float4*>(a.e_shift + col));
+            if (a.e_center != nullptr) ece = __ldg(reinterpret_cast<const float4*>(a.e_center + col));
+          }
+          for (int p0 = 0; p0 < cgs; p0 += 4) {     // 4 rows per batch: their global loads overlap
+            int o[4];
+            float4 r4[4], d4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              o[u] = so[r0 + (p0 + u) * rstep];
+              r4[u] = make_float4(0.f, 0.f, 0.f, 0.f); d4[u] = r4[u];
+              if (a.epi == CVAE_EPI_DACT && o[u] >= 0) {
+                const size_t goff = (size_t)o[u] * a.Cd + col;
+                r4[u] = __ldg(reinterpret_cast<const float4*>(a.epi_ref + goff));
+                if (a.epi_add != nullptr) d4[u] = __ldg(reinterpret_cast<const float4*>(a.epi_add + goff));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (o[u] < 0) continue;
+              const float4 t4 = *reinterpret_cast<const float4*>(eb + (r0 + (p0 + u) * rstep) * kHEpiLd + cg * 4);
+              float x[4] = {t4.x + bias.x, t4.y + bias.y, t4.z + bias.z, t4.w + bias.w};
+              if (a.epi == CVAE_EPI_STATS) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s1[j] += (double)x[j]; s2[j] += (double)x[j] * (double)x[j]; }
+              } else if (a.epi == CVAE_EPI_DACT) {
+                const float refc[4] = {r4[u].x - ece.x, r4[u].y - ece.y, r4[u].z - ece.z, r4[u].w - ece.w};
+                x[0] += d4[u].x; x[1] += d4[u].y; x[2] += d4[u].z; x[3] += d4[u].w;
+                const float z[4] = {fmaf(refc[0], esc.x, esh.x), fmaf(refc[1], esc.y, esh.y), fmaf(refc[2], esc.z, esh.z),
+                                    fmaf(refc[3], esc.w, esh.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  x[j] = z[j] > 0.f ? x[j] : x[j] * a.e_slope;
+                  s1[j] += (double)x[j]; s2[j] += (double)x[j] * (double)refc[j];
+                }
+              }
+              *reinterpret_cast<float4*>(a.dst + (size_t)o[u] * a.Cd + col) = make_float4(x[0], x[1], x[2], x[3]);
+            }
+          }
+          if (want_stats && !reg_stats) reduce_stats(tl.n0 + ch * 32);   // its barriers also free the staging tile
+          else if (nbuf == 1) hbar_sync(1, 128);                         // single staging tile: free it for reuse
+        }
+      }
+    }
+    if (gt == 0) T_FLUSH(8, 1)
+    if (want_stats) {
+      if (reg_stats) reduce_stats(0);
+      else hbar_sync(1, 128);
+      for (int i = gt; i < 2 * a.Cd; i += 128) {
+        const int which = i / a.Cd, cc = i % a.Cd;
+        const double sv = s_stat[which * 256 + cc];
+        if (sv != 0.0) atomicAdd(a.stats + i, sv);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kHProdWarps) tmem_dealloc(tmem, tmem_cols);
+}
+
+int build_geom(const cvae_conv_params_t* p, GatherArgs& g);  // conv.cu
+
+static inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+// Build the staging plan from the phase / tap geometry.  Returns false when the shape is not covered.
+static bool build_halo_plan(const GatherArgs& g, HaloPlan& hp) {
+  const int is = g.is;
+  if (is != 1 && is != 2) return false;
+  if (is == 2 && g.nphase != 1) return false;
+  hp.nplanes = is * is;
+  for (int pl = 0; pl < 4; ++pl) { hp.plane[pl].ntaps = 0; hp.plane[pl].imin = 1 << 20; hp.plane[pl].jmin = 1 << 20; }
+  int imax[4] = {-(1 << 20), -(1 << 20), -(1 << 20), -(1 << 20)}, jmax[4] = {imax[0], imax[0], imax[0], imax[0]};
+  // pass 1: plane membership and extents
+  for (int ph = 0; ph < g.nphase; ++ph)
+    for (int t = 0; t < g.phase[ph].ntaps; ++t) {
+      const TapEntry& te = g.phase[ph].taps[t];
+      const int pr = is == 2 ? (te.dh & 1) : 0, pc = is == 2 ? (te.dw & 1) : 0;
+      const int di = is == 2 ? floordiv2(te.dh) : te.dh, dj = is == 2 ? floordiv2(te.dw) : te.dw;
+      HaloPlane& P = hp.plane[pr * is + pc];
+      P.pr = pr; P.pc = pc;
+      P.imin = min(P.imin, di); P.jmin = min(P.jmin, dj);
+      imax[pr * is + pc] = max(imax[pr * is + pc], di); jmax[pr * is + pc] = max(jmax[pr * is + pc], dj);
+    }
+  int eh = 0, ew = 0;
+  for (int pl = 0; pl < hp.nplanes; ++pl) {
+    if (hp.plane[pl].imin > imax[pl]) return false;      // a parity plane without taps (e.g. k = 1, s = 2)
+    eh = max(eh, imax[pl] - hp.plane[pl].imin); ew = max(ew, jmax[pl] - hp.plane[pl].jmin);
+  }
+  hp.R = kHTH + eh; hp.C = kHTW + ew;
+  if (hp.R * hp.C > kHMaxSlots) return false;
+  // pass 2: tap lists
+  for (int ph = 0; ph < g.nphase; ++ph)
+    for (int t = 0; t < g.phase[ph].ntaps; ++t) {
+      const TapEntry& te = g.phase[ph].taps[t];
+      const int pr = is == 2 ? (te.dh & 1) : 0, pc = is == 2 ? (te.dw & 1) : 0;
+      const int di = is == 2 ? floordiv2(te.dh) : te.dh, dj = is == 2 ? floordiv2(te.dw) : te.dw;
+      HaloPlane& P = hp.plane[pr * is + pc];
+      if (P.ntaps >= 16) return false;
+      P.taps[P.ntaps++] = {(di - P.imin) * hp.C + (dj - P.jmin), te.widx, ph};
+    }
+  for (int ph = 0; ph < g.nphase; ++ph) { hp.ph[ph] = g.phase[ph].ph; hp.pw[ph] = g.phase[ph].pw; }
+  return true;
+}
+
+// exported to conv_tc.cu: returns CVAE_OK when launched, 1 when the shape is not covered (caller falls
+// back to the per-tap gather kernel), < 0 on error.
+int launch_conv_halo_tc(const GatherArgs& g, cudaStream_t st) {
+  if (g.wtaps < 2) return 1;                       // 1x1 / Linear: nothing to share between taps
+  if (g.Cs % 16 != 0 || g.Cd % 16 != 0 || g.Cd > 256) return 1;
+  HaloPlan hp;
+  if (!build_halo_plan(g, hp)) return 1;
+  // q-space extent: identical for every phase of the layers covered here (even output sizes)
+  hp.Hq = g.phase[0].Hq; hp.Wq = g.phase[0].Wq;
+  for (int i = 1; i < g.nphase; ++i)
+    if (g.phase[i].Hq != hp.Hq || g.phase[i].Wq != hp.Wq) return 1;
+  int bn = 0;
+  for (int c : {128, 64, 32, 16})
+    if (g.Cd % c == 0 && 2 * g.nphase * c <= 512) { bn = c; break; }
+  if (bn == 0) return 1;
+  hp.BN = bn;
+  hp.NB = bn >= 128 ? 3 : 4;
+  hp.tiles_h = (hp.Hq + kHTH - 1) / kHTH; hp.tiles_w = (hp.Wq + kHTW - 1) / kHTW; hp.tiles_n = g.Cd / bn;
+  const long long total = (long long)g.N * hp.tiles_h * hp.tiles_w * hp.tiles_n;
+  if (total >= (1ll << 31)) return 1;
+  const size_t smem = (size_t)kHNA * kHAStage + (size_t)hp.NB * 256 * bn + (bn <= 64 ? 2 : 1) * kHEpiBytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_halo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024) != cudaSuccess)
+      return CVAE_ERR_LAUNCH;
+    attr_set = true;
+  }
+  conv_halo_tc_kernel<<<(int)min(total, (long long)kNumSMs), kHThreads, smem, st>>>(g, hp, (int)total);
+  if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); return CVAE_ERR_LAUNCH; }
+  return CVAE_OK;
+}
+
+}  // namespace cvae
+
+// Debug hook (timing builds): [0] producer wait-empty, [1] producer total, [2] mma wait-tmem-empty, [3] mma wait-A,
+// [4] mma wait-B, [5] mma total, [6] B-loader wait-empty, [7] B-loader total, [8] epilogue wait-full, [9] epilogue total
+// (clock cycles summed over CTAs).  Returns 0 when the library was built without CVAE_TIMING.
+extern "C" int cvae_debug_read(unsigned long long* out16, int reset) {
+#ifdef CVAE_TIMING
+  unsigned long long z[16] = {0};
+  if (out16 && cudaMemcpyFromSymbol(out16, cvae::g_halo_dbg, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(cvae::g_halo_dbg, z, sizeof(z)) != cudaSuccess) return -1;
+  return 1;
+#else
+  (void)out16; (void)reset;
+  return 0;
+#endif
+}

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace cvae {
 
@@ -397,6 +398,7 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ src, float* __re
 }
 
 int build_geom(const cvae_conv_params_t* p, GatherArgs& g);  // conv.cu
+int launch_conv_halo_tc(const GatherArgs& g, cudaStream_t st);   // conv_halo_tc.cu (conv-shaped layers, k > 1)
 
 static int tc_pick_bn(int Cd) {
   for (int bn = 256; bn >= 16; bn >>= 1)
@@ -449,6 +451,15 @@ extern "C" int cvae_conv_gather_tc(const cvae_conv_params_t* p, cvae_stream_t s)
   for (int i = 0; i < g.nphase; ++i) {
     if (g.phase[i].ntaps < 1) return CVAE_ERR_UNSUPPORTED_SHAPE;
     maxM = max(maxM, p->N * g.phase[i].Hq * g.phase[i].Wq);
+  }
+  {
+    // conv-shaped layers: the halo-tile kernel stages the input once for all taps (CVAE_HALO=0 forces
+    // the per-tap gather kernel below, kept for 1x1 / Linear layers and shapes the halo plan rejects)
+    static const bool halo_on = [] { const char* e = getenv("CVAE_HALO"); return !(e && e[0] == '0'); }();
+    if (halo_on) {
+      const int hr = launch_conv_halo_tc(g, as_stream(s));
+      if (hr <= 0) return hr;
+    }
   }
   const int BN = tc_pick_bn(p->Cd);
   if (BN == 0) return CVAE_ERR_UNSUPPORTED_SHAPE;

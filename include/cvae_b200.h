@@ -302,6 +302,10 @@ int cvae_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float max_norm, float lr, float beta1, float beta2, float eps, float grad_scale,
                    int64_t* step_count, cvae_stream_t s);
 
+/* ---- debug: role-level wait accounting of the tensor-core kernels (builds with -DCVAE_TIMING only;
+ * returns 0 and leaves out16 untouched otherwise).  Not part of the reference-facing surface. */
+int cvae_debug_read(unsigned long long* out16, int reset);
+
 #ifdef __cplusplus
 }
 #endif

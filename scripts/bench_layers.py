@@ -37,6 +37,19 @@ LAYERS = [
 ]
 
 
+def role_times(fn):
+    """timing builds (CVAE_TIMING=1): per-role wait / busy cycles of one launch, averaged over CTAs."""
+    import ctypes
+    buf = (ctypes.c_ulonglong * 16)()
+    if L.lib.cvae_debug_read(ctypes.cast(buf, ctypes.c_void_p), 1) != 1:
+        return ""
+    fn(); torch.cuda.synchronize()
+    L.lib.cvae_debug_read(ctypes.cast(buf, ctypes.c_void_p), 1)
+    v = [x / 148 / 1e3 for x in buf]
+    return (f"  [kclk/CTA] prod wait {v[0]:.0f}/{v[1]:.0f}  mma wT {v[2]:.0f} wA {v[3]:.0f} wB {v[4]:.0f} /{v[5]:.0f}"
+            f"  bload wait {v[6]:.0f}/{v[7]:.0f}  epi wait {v[8]:.0f}/{v[9]:.0f}")
+
+
 def timeit(fn, once, flush):
     if once:
         fn(); torch.cuda.synchronize()
@@ -102,7 +115,7 @@ def main():
                                       stats=stats, tc=tcf)
         ms = timeit(fwd, once, flush)
         by = 4.0 * (x.numel() + dy.numel())
-        print(f"{name:24s} {'fwd' + ('*' if tcf else ''):6s} {ms:8.3f} {flops / ms / 1e9:8.1f} {by / ms / 1e6:8.0f}")
+        print(f"{name:24s} {'fwd' + ('*' if tcf else ''):6s} {ms:8.3f} {flops / ms / 1e9:8.1f} {by / ms / 1e6:8.0f}" + (role_times(fwd) if tcf else ""))
         tot += ms
         # ---- input gradient (DACT epilogue: reads the producer's raw output) ----
         if Ci > 1:
@@ -116,7 +129,7 @@ def main():
                                           epi_x=exf, stats=stats_b, tc=tcb)
             ms = timeit(bwd, once, flush)
             by = 4.0 * (2 * x.numel() + dy.numel())
-            print(f"{name:24s} {'dgrad' + ('*' if tcb else ''):6s} {ms:8.3f} {flops / ms / 1e9:8.1f} {by / ms / 1e6:8.0f}")
+            print(f"{name:24s} {'dgrad' + ('*' if tcb else ''):6s} {ms:8.3f} {flops / ms / 1e9:8.1f} {by / ms / 1e6:8.0f}" + (role_times(bwd) if tcb else ""))
             tot += ms
         # ---- weight gradient (+ split-K reduce) ----
         gw = torch.empty_like(w)

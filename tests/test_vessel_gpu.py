@@ -99,12 +99,14 @@ def test_train_step_matches_oracle(cfg):
     # established per layer chain in test_ops_gpu.py and per segment in test_vessel_segments_gpu.py.
     pert = {k: 0.0 for k in g64}
     pert_tot = 0.0
-    for seed in (1, 2, 3):
+    # perturbation size 3e-6: BELOW the 1e-5 forward tolerance and the size of the 3xTF32 forward
+    # error (2-6e-6) -- the scale at which kink flips happen on the native path
+    for seed in (1, 2, 3, 4, 5):
         Pp = {k: v.clone() for k, v in sd.items()}
         gen = torch.Generator().manual_seed(seed)
         for k, v in Pp.items():
             if v.is_floating_point() and "running" not in k:
-                v.mul_(1 + 3e-7 * torch.randn(v.shape, generator=gen))
+                v.mul_(1 + 3e-6 * torch.randn(v.shape, generator=gen))
         _, gp, totp = O.vessel_train_step(Pp, {}, 1, x, m, t, eps)
         pert_tot = max(pert_tot, abs(float(totp) - float(tot32)) / float(tot32))
         for k in pert:
