@@ -472,16 +472,80 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ Wgra
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int ca,
-                                    int ca_real, int cb, float* __restrict__ dst, int accumulate) {
-  const int total = cb * ca_real * taps;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int tap = i % taps, t = i / taps, a_ = t % ca_real, b_ = t / ca_real;
-    const size_t stride = (size_t)taps * ca * cb;
-    const float* p = partial + ((size_t)tap * ca + a_) * cb + b_;
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += p[k * stride];
-    dst[i] = accumulate ? dst[i] + s : s;
+// Sum the K-split partials.  A block owns 128 consecutive partial-order outputs j = (tap*ca + a)*cb + b
+// (a warp reads 512 contiguous bytes per split) and spreads the splits over 8 thread groups; the result
+// is written in torch layout dst[b][a][tap].  cb % 4 == 0 (vector path) or any cb (scalar path, V = 1).
+template <int V>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int ca,
+                                                           int ca_real, int cb, float* __restrict__ dst, int accumulate) {
+  __shared__ float red[8][32 * V + 1];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const size_t stride = (size_t)taps * ca * cb;
+  const int total = taps * ca * cb;
+  for (int j0 = blockIdx.x * 32 * V; j0 < total; j0 += gridDim.x * 32 * V) {
+    const int j = j0 + lane * V;
+    float s[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] = 0.f;
+    if (j < total) {
+      for (int k = grp; k < splits; k += 8) {
+        if constexpr (V == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(partial + (size_t)k * stride + j);
+          s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w;
+        } else {
+          s[0] += partial[(size_t)k * stride + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[grp][lane * V + i] = s[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * V; e += 256) {
+      const int jj = j0 + e;
+      if (jj < total) {
+        const float t = ((red[0][e] + red[1][e]) + (red[2][e] + red[3][e])) + ((red[4][e] + red[5][e]) + (red[6][e] + red[7][e]));
+        const int b_ = jj % cb, q = jj / cb, a_ = q % ca, tap = q / ca;
+        if (a_ < ca_real) {
+          const size_t o = ((size_t)b_ * ca_real + a_) * taps + tap;
+          dst[o] = accumulate ? dst[o] + t : t;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Large weight tensors (Linear 512 -> 16384: 8.4 M outputs): the torch layout dst[b][a][tap] is the
+// transpose of the partial layout [tap][a][b], so a block sums the splits for a 32(a) x 32(b) tile of
+// every tap with coalesced row reads, stages it in shared memory and writes contiguous runs of dst.
+template <int TA>
+__global__ void __launch_bounds__(256) wgrad_reduce_tile_kernel(const float* __restrict__ partial, int splits, int taps,
+                                                                int ca, int ca_real, int cb, float* __restrict__ dst,
+                                                                int accumulate) {
+  extern __shared__ float tile[];                   // [32 b][TA a][taps] (+1 pad per b row)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a0 = blockIdx.x * TA, b0 = blockIdx.y * 32;
+  const size_t stride = (size_t)taps * ca * cb;
+  const int ld = TA * taps + 1;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int al = warp; al < TA; al += 8) {
+      const int a_ = a0 + al, b_ = b0 + lane;
+      float s = 0.f;
+      if (a_ < ca && b_ < cb) {
+        const float* p = partial + ((size_t)tap * ca + a_) * cb + b_;
+        for (int k = 0; k < splits; ++k) s += p[(size_t)k * stride];
+      }
+      tile[lane * ld + al * taps + tap] = s;
+    }
+  __syncthreads();
+  const int na = min(TA, ca_real - a0);             // rows a >= ca_real are padding and dropped
+  if (na <= 0) return;
+  const int run = na * taps;
+  for (int bl = warp; bl < 32; bl += 8) {
+    const int b_ = b0 + bl;
+    if (b_ >= cb) continue;
+    float* o = dst + ((size_t)b_ * ca_real + a0) * taps;
+    for (int i = lane; i < run; i += 32) o[i] = accumulate ? o[i] + tile[bl * ld + i] : tile[bl * ld + i];
   }
 }
 
@@ -663,10 +727,27 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_params_t* p, cvae_stream_t s) {
 extern "C" int cvae_wgrad_reduce(const float* partial, int splits, int taps, int ca, int ca_real, int cb,
                                  float* dst, int accumulate, cvae_stream_t s) {
   if (!partial || !dst || splits < 1 || ca_real > ca) return CVAE_ERR_BAD_ARG;
-  const int total = cb * ca_real * taps;
-  int blocks = (total + 255) / 256;
-  blocks = min(blocks, kNumSMs * 8);
-  wgrad_reduce_kernel<<<blocks, 256, 0, as_stream(s)>>>(partial, splits, taps, ca, ca_real, cb, dst, accumulate);
+  const int total = cb * ca * taps;
+  if (((ca + 31) / 32) * ((cb + 31) / 32) >= 128 && splits <= 32 && taps <= 16) {
+    if (taps <= 9) {
+      const size_t smem = sizeof(float) * 32 * (32 * taps + 1);
+      wgrad_reduce_tile_kernel<32><<<dim3((ca + 31) / 32, (cb + 31) / 32), 256, smem, as_stream(s)>>>(
+          partial, splits, taps, ca, ca_real, cb, dst, accumulate);
+    } else {
+      const size_t smem = sizeof(float) * 32 * (16 * taps + 1);
+      wgrad_reduce_tile_kernel<16><<<dim3((ca + 15) / 16, (cb + 31) / 32), 256, smem, as_stream(s)>>>(
+          partial, splits, taps, ca, ca_real, cb, dst, accumulate);
+    }
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+  }
+  if (cb % 4 == 0) {
+    const int blocks = min((total + 127) / 128, kNumSMs * 16);
+    wgrad_reduce_kernel<4><<<blocks, 256, 0, as_stream(s)>>>(partial, splits, taps, ca, ca_real, cb, dst, accumulate);
+  } else {
+    const int blocks = min((total + 31) / 32, kNumSMs * 16);
+    wgrad_reduce_kernel<1><<<blocks, 256, 0, as_stream(s)>>>(partial, splits, taps, ca, ca_real, cb, dst, accumulate);
+  }
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

@@ -41,13 +41,19 @@ constexpr int kHItems = (kHMaxSlots * 8 + kHProdWarps * 32 - 1) / (kHProdWarps *
 constexpr int kHEpiLd = 36;
 constexpr int kHEpiBytes = 128 * kHEpiLd * 4 + 128 * 4;   // one staging tile + its row -> pixel table
 
-struct HaloTap { int off; int widx; int phase; };       // off: slot offset of the tap window inside the staged plane
+// A tap GROUP: the taps (of different output phases) that read the same staged window.  They run as ONE
+// MMA whose B operand stacks their weight tiles along N and whose D spans their (adjacent) accumulators:
+// a kind::tf32 MMA costs ~96 clk whatever N <= 128 is (scripts/umma_rate.cu), so the 9 taps of a
+// stride-2 transposed conv take 4 MMAs per k-step instead of 9.  Gather mode: one tap per group.
+struct HaloTap { int off; int nsub; int pos0; int widx[4]; };   // off: slot offset of the window; pos0: first accumulator
 struct HaloPlane { int pr, pc, imin, jmin, ntaps; HaloTap taps[16]; };
 struct HaloPlan {
   int nplanes, R, C;          // staged rows / columns (uniform over planes)
   int tiles_h, tiles_w, tiles_n, BN, NB;
   int Hq, Wq;                 // q-space extent per image
   int ph[4], pw[4];           // output offset of each phase
+  int pos[4];                 // accumulator position (TMEM column block) of each phase
+  int bslot_bytes;            // weight ring slot: 256 * BN * (largest group)
   HaloPlane plane[4];
 };
 
@@ -89,7 +95,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN, NB = p.NB;
   const int KB = (a.Cs + 31) >> 5;
-  const uint32_t bstage = 256u * BN;
+  const uint32_t bstage = (uint32_t)p.bslot_bytes;
   const uint32_t acc_cols = (uint32_t)(a.nphase * BN);
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
@@ -187,7 +193,6 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   } else if (warp == kHProdWarps) {
     // ============================== MMA issuer (one thread) ==============================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
       const uint32_t sbo = (uint32_t)p.C * 128u;
       const uint64_t a_desc_hi = make_smem_desc(0, 16, sbo, kLayoutSw128);     // everything but the address
       const uint64_t b_desc_hi = make_smem_desc(0, 16, 1024, kLayoutSw128);
@@ -212,17 +217,20 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
               const int bslot = itb % NB;
               T_WAIT(2, mbar_wait(smem_u32(&s_bfull[bslot]), (itb / NB) & 1u))
               tc_fence_after();
+              const uint32_t ng = (uint32_t)(tap.nsub * BN);                 // N of this group's MMA
+              const uint32_t idesc = make_idesc_tf32(128, (int)ng, 0, 0);
               const uint32_t a_hi = a_hi0 + (uint32_t)tap.off * 128u;
               const uint32_t b_hi = b_base + (uint32_t)bslot * bstage;
-              const uint32_t d_tmem = d_base + (uint32_t)(tap.phase * BN);
-              uint32_t accum = (started >> tap.phase) & 1u;
+              const uint32_t d_tmem = d_base + (uint32_t)(tap.pos0 * BN);
+              const uint32_t gmask = ((1u << tap.nsub) - 1u) << tap.pos0;
+              uint32_t accum = (started & gmask) ? 1u : 0u;                  // host plan: never mixed within a group
               // descriptors differ only in their 14-bit address field: one 64-bit add per k-step
               // (the issuing thread is latency-bound: rebuilding four descriptors per k-step capped
               // the issue rate at ~1 MMA / 100 clk -- measured with the CVAE_TIMING build)
               uint64_t dah = a_desc_hi | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
               uint64_t dal = a_desc_hi | (uint64_t)(((a_hi + kHHalf) & 0x3FFFFu) >> 4);
               uint64_t dbh = b_desc_hi | (uint64_t)((b_hi & 0x3FFFFu) >> 4);
-              uint64_t dbl = b_desc_hi | (uint64_t)(((b_hi + 128u * BN) & 0x3FFFFu) >> 4);
+              uint64_t dbl = b_desc_hi | (uint64_t)(((b_hi + 128u * ng) & 0x3FFFFu) >> 4);
 #pragma unroll 4
               for (int k = 0; k < ksteps; ++k) {
                 mma_tf32(d_tmem, dal, dbh, idesc, accum);
@@ -231,7 +239,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
                 accum = 1u;
                 dah += 2; dal += 2; dbh += 2; dbl += 2;      // + 32 bytes (8 tf32) along K
               }
-              started |= 1u << tap.phase;
+              started |= gmask;
               mma_commit(smem_u32(&s_bempty[bslot]));
             }
             mma_commit(smem_u32(&s_aempty[aslot]));
@@ -257,10 +265,14 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
               T_WAIT(0, mbar_wait(smem_u32(&s_bempty[bslot]), ((itb / NB) & 1u) ^ 1u))
               const uint32_t full = smem_u32(&s_bfull[bslot]);
               const uint32_t sB = b_base + (uint32_t)bslot * bstage;
-              mbar_arrive_expect_tx(full, 2u * bbytes);
-              const float* wsrc = a.wt + (((size_t)P.taps[tp].widx * KB + kb) * 2) * (size_t)a.Cd * 32 + (size_t)n0 * 32;
-              bulk_g2s(sB, wsrc, bbytes, full);
-              bulk_g2s(sB + bbytes, wsrc + (size_t)a.Cd * 32, bbytes, full);
+              const HaloTap tap = P.taps[tp];
+              const uint32_t ng = (uint32_t)(tap.nsub * BN);
+              mbar_arrive_expect_tx(full, 2u * 128u * ng);
+              for (int sb = 0; sb < tap.nsub; ++sb) {        // stack the sub-taps' weight tiles along N
+                const float* wsrc = a.wt + (((size_t)tap.widx[sb] * KB + kb) * 2) * (size_t)a.Cd * 32 + (size_t)n0 * 32;
+                bulk_g2s(sB + (uint32_t)sb * bbytes, wsrc, bbytes, full);
+                bulk_g2s(sB + 128u * ng + (uint32_t)sb * bbytes, wsrc + (size_t)a.Cd * 32, bbytes, full);
+              }
             }
           }
       }
@@ -316,7 +328,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       T_WAIT(0, mbar_wait(smem_u32(&s_tfull[acc]), (tcount >> 1) & 1u))
       tc_fence_after();
       for (int phs = 0; phs < a.nphase; ++phs) {
-        const uint32_t d_tmem = tmem + acc * acc_cols + (uint32_t)(phs * BN) + ((uint32_t)(q * 32) << 16);
+        const uint32_t d_tmem = tmem + acc * acc_cols + (uint32_t)(p.pos[phs] * BN) + ((uint32_t)(q * 32) << 16);
         for (int ch = 0; ch < nchunks; ++ch, ++cidx) {
           float* eb = ebuf + (cidx % nbuf) * 128 * kHEpiLd;
           int* so = s_out2 + (cidx % nbuf) * 128;
@@ -413,23 +425,28 @@ int build_geom(const cvae_conv_params_t* p, GatherArgs& g);  // conv.cu
 static inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 // Build the staging plan from the phase / tap geometry.  Returns false when the shape is not covered.
-static bool build_halo_plan(const GatherArgs& g, HaloPlan& hp) {
+// max_sub: how many taps may be stacked along N in one MMA (1 = no grouping).
+static bool build_halo_plan(const GatherArgs& g, HaloPlan& hp, int max_sub) {
   const int is = g.is;
   if (is != 1 && is != 2) return false;
   if (is == 2 && g.nphase != 1) return false;
   hp.nplanes = is * is;
   for (int pl = 0; pl < 4; ++pl) { hp.plane[pl].ntaps = 0; hp.plane[pl].imin = 1 << 20; hp.plane[pl].jmin = 1 << 20; }
   int imax[4] = {-(1 << 20), -(1 << 20), -(1 << 20), -(1 << 20)}, jmax[4] = {imax[0], imax[0], imax[0], imax[0]};
+  auto plane_of = [&](const TapEntry& te, int& di, int& dj) {
+    const int pr = is == 2 ? (te.dh & 1) : 0, pc = is == 2 ? (te.dw & 1) : 0;
+    di = is == 2 ? floordiv2(te.dh) : te.dh; dj = is == 2 ? floordiv2(te.dw) : te.dw;
+    hp.plane[pr * is + pc].pr = pr; hp.plane[pr * is + pc].pc = pc;
+    return pr * is + pc;
+  };
   // pass 1: plane membership and extents
   for (int ph = 0; ph < g.nphase; ++ph)
     for (int t = 0; t < g.phase[ph].ntaps; ++t) {
-      const TapEntry& te = g.phase[ph].taps[t];
-      const int pr = is == 2 ? (te.dh & 1) : 0, pc = is == 2 ? (te.dw & 1) : 0;
-      const int di = is == 2 ? floordiv2(te.dh) : te.dh, dj = is == 2 ? floordiv2(te.dw) : te.dw;
-      HaloPlane& P = hp.plane[pr * is + pc];
-      P.pr = pr; P.pc = pc;
+      int di, dj;
+      const int pl = plane_of(g.phase[ph].taps[t], di, dj);
+      HaloPlane& P = hp.plane[pl];
       P.imin = min(P.imin, di); P.jmin = min(P.jmin, dj);
-      imax[pr * is + pc] = max(imax[pr * is + pc], di); jmax[pr * is + pc] = max(jmax[pr * is + pc], dj);
+      imax[pl] = max(imax[pl], di); jmax[pl] = max(jmax[pl], dj);
     }
   int eh = 0, ew = 0;
   for (int pl = 0; pl < hp.nplanes; ++pl) {
@@ -438,17 +455,89 @@ static bool build_halo_plan(const GatherArgs& g, HaloPlan& hp) {
   }
   hp.R = kHTH + eh; hp.C = kHTW + ew;
   if (hp.R * hp.C > kHMaxSlots) return false;
-  // pass 2: tap lists
+  for (int ph = 0; ph < g.nphase; ++ph) { hp.ph[ph] = g.phase[ph].ph; hp.pw[ph] = g.phase[ph].pw; hp.pos[ph] = ph; }
+
+  // pass 2: windows (plane, off) with the (phase, widx) pairs that read them
+  struct Win { int pl, off, n, phase[4], widx[4]; };
+  Win win[64];
+  int nwin = 0;
   for (int ph = 0; ph < g.nphase; ++ph)
     for (int t = 0; t < g.phase[ph].ntaps; ++t) {
+      int di, dj;
       const TapEntry& te = g.phase[ph].taps[t];
-      const int pr = is == 2 ? (te.dh & 1) : 0, pc = is == 2 ? (te.dw & 1) : 0;
-      const int di = is == 2 ? floordiv2(te.dh) : te.dh, dj = is == 2 ? floordiv2(te.dw) : te.dw;
-      HaloPlane& P = hp.plane[pr * is + pc];
-      if (P.ntaps >= 16) return false;
-      P.taps[P.ntaps++] = {(di - P.imin) * hp.C + (dj - P.jmin), te.widx, ph};
+      const int pl = plane_of(te, di, dj);
+      const int off = (di - hp.plane[pl].imin) * hp.C + (dj - hp.plane[pl].jmin);
+      int w = 0;
+      while (w < nwin && !(win[w].pl == pl && win[w].off == off)) ++w;
+      if (w == nwin) { if (nwin == 64) return false; win[nwin++] = {pl, off, 0, {0, 0, 0, 0}, {0, 0, 0, 0}}; }
+      if (win[w].n == 4) return false;                   // one window is read at most once per phase
+      win[w].phase[win[w].n] = ph; win[w].widx[win[w].n] = te.widx; ++win[w].n;
     }
-  for (int ph = 0; ph < g.nphase; ++ph) { hp.ph[ph] = g.phase[ph].ph; hp.pw[ph] = g.phase[ph].pw; }
+  // pass 3: choose accumulator positions so that every window's phases are adjacent (try all orders),
+  // split windows wider than max_sub, and order the groups so that a group never mixes first-touch and
+  // accumulate positions (largest windows first)
+  int perm[4] = {0, 1, 2, 3}, best[4] = {0, 1, 2, 3};
+  bool found = max_sub <= 1 || g.nphase == 1;
+  if (!found) {
+    int idx[4] = {0, 1, 2, 3};
+    auto contiguous = [&](const int* pos) {
+      for (int w = 0; w < nwin; ++w) {
+        int lo = 4, hi = -1;
+        for (int i = 0; i < win[w].n; ++i) { lo = min(lo, pos[win[w].phase[i]]); hi = max(hi, pos[win[w].phase[i]]); }
+        if (hi - lo + 1 != win[w].n) return false;
+      }
+      return true;
+    };
+    // all permutations of up to 4 phases (Heap-free brute force)
+    for (int a0 = 0; a0 < g.nphase && !found; ++a0)
+      for (int a1 = 0; a1 < g.nphase && !found; ++a1)
+        for (int a2 = 0; a2 < g.nphase && !found; ++a2)
+          for (int a3 = 0; a3 < g.nphase && !found; ++a3) {
+            idx[0] = a0; idx[1] = a1; idx[2] = a2; idx[3] = a3;
+            bool ok = true;
+            for (int i = 0; i < g.nphase && ok; ++i)
+              for (int j = i + 1; j < g.nphase; ++j)
+                if (idx[i] == idx[j]) { ok = false; break; }
+            if (!ok) continue;
+            for (int i = 0; i < g.nphase; ++i) perm[i] = idx[i];     // perm[phase] = position
+            if (contiguous(perm)) { found = true; for (int i = 0; i < 4; ++i) best[i] = perm[i]; }
+          }
+  }
+  const bool grouped = found && max_sub > 1 && g.nphase > 1;
+  if (grouped) for (int ph = 0; ph < g.nphase; ++ph) hp.pos[ph] = best[ph];
+  // emit groups: windows sorted by size (descending) within each plane
+  uint32_t started = 0;
+  int max_group = 1;
+  for (int pass = 4; pass >= 1; --pass)
+    for (int w = 0; w < nwin; ++w) {
+      if (win[w].n != pass) continue;
+      HaloPlane& P = hp.plane[win[w].pl];
+      // sub-taps in accumulator-position order
+      int order[4] = {0, 1, 2, 3};
+      for (int i = 0; i < win[w].n; ++i)
+        for (int j = i + 1; j < win[w].n; ++j)
+          if (hp.pos[win[w].phase[order[j]]] < hp.pos[win[w].phase[order[i]]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+      const int chunk = grouped ? max_sub : 1;
+      for (int i0 = 0; i0 < win[w].n; i0 += chunk) {
+        if (P.ntaps >= 16) return false;
+        HaloTap& T = P.taps[P.ntaps++];
+        T.off = win[w].off; T.nsub = min(chunk, win[w].n - i0); T.pos0 = hp.pos[win[w].phase[order[i0]]];
+        for (int i = 0; i < 4; ++i) T.widx[i] = i < T.nsub ? win[w].widx[order[i0 + i]] : 0;
+        const uint32_t gmask = ((1u << T.nsub) - 1u) << T.pos0;
+        max_group = max(max_group, T.nsub);
+        (void)started; (void)gmask;
+      }
+    }
+  // the kernel derives one accumulate flag per group from the positions already written: verify that
+  // no group mixes written and unwritten positions in ISSUE order (k-block major, plane, tap)
+  for (int pl = 0; pl < hp.nplanes; ++pl)
+    for (int t = 0; t < hp.plane[pl].ntaps; ++t) {
+      const HaloTap& T = hp.plane[pl].taps[t];
+      const uint32_t gmask = ((1u << T.nsub) - 1u) << T.pos0;
+      if ((started & gmask) != 0 && (started & gmask) != gmask) return false;
+      started |= gmask;
+    }
+  hp.bslot_bytes = max_group;     // finished by the caller (x 256 * BN)
   return true;
 }
 
@@ -457,22 +546,26 @@ static bool build_halo_plan(const GatherArgs& g, HaloPlan& hp) {
 int launch_conv_halo_tc(const GatherArgs& g, cudaStream_t st) {
   if (g.wtaps < 2) return 1;                       // 1x1 / Linear: nothing to share between taps
   if (g.Cs % 16 != 0 || g.Cd % 16 != 0 || g.Cd > 256) return 1;
-  HaloPlan hp;
-  if (!build_halo_plan(g, hp)) return 1;
-  // q-space extent: identical for every phase of the layers covered here (even output sizes)
-  hp.Hq = g.phase[0].Hq; hp.Wq = g.phase[0].Wq;
-  for (int i = 1; i < g.nphase; ++i)
-    if (g.phase[i].Hq != hp.Hq || g.phase[i].Wq != hp.Wq) return 1;
   int bn = 0;
   for (int c : {128, 64, 32, 16})
     if (g.Cd % c == 0 && 2 * g.nphase * c <= 512) { bn = c; break; }
   if (bn == 0) return 1;
+  HaloPlan hp;
+  // stack up to 128 output columns per MMA (weight-ring slot <= 32 KiB); fall back to one tap per MMA
+  const int max_sub = g.nphase > 1 ? max(1, min(4, 128 / bn)) : 1;
+  if (!build_halo_plan(g, hp, max_sub) && !build_halo_plan(g, hp, 1)) return 1;
+  // q-space extent: identical for every phase of the layers covered here (even output sizes)
+  hp.Hq = g.phase[0].Hq; hp.Wq = g.phase[0].Wq;
+  for (int i = 1; i < g.nphase; ++i)
+    if (g.phase[i].Hq != hp.Hq || g.phase[i].Wq != hp.Wq) return 1;
   hp.BN = bn;
-  hp.NB = bn >= 128 ? 3 : 4;
+  hp.bslot_bytes *= 256 * bn;
+  hp.NB = hp.bslot_bytes >= 32768 ? (bn >= 128 ? 3 : 2) : 4;
+  if (hp.bslot_bytes == 32768 && bn < 128) hp.NB = 2;
   hp.tiles_h = (hp.Hq + kHTH - 1) / kHTH; hp.tiles_w = (hp.Wq + kHTW - 1) / kHTW; hp.tiles_n = g.Cd / bn;
   const long long total = (long long)g.N * hp.tiles_h * hp.tiles_w * hp.tiles_n;
   if (total >= (1ll << 31)) return 1;
-  const size_t smem = (size_t)kHNA * kHAStage + (size_t)hp.NB * 256 * bn + (bn <= 64 ? 2 : 1) * kHEpiBytes + 1024;
+  const size_t smem = (size_t)kHNA * kHAStage + (size_t)hp.NB * hp.bslot_bytes + (bn <= 64 ? 2 : 1) * kHEpiBytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_halo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024) != cudaSuccess)

@@ -44,6 +44,9 @@ IDENT = XF()
 _TC = os.environ.get("CVAE_TC", "1") != "0"
 
 
+_TILE = os.environ.get("CVAE_WGRAD_TILE", "1") != "0"   # smem-tiled fp32 weight gradient for few-channel 3x3 layers
+
+
 _TC_MIN_ROWS = int(os.environ.get("CVAE_TC_MIN_ROWS", "1024"))   # below this a 128-row tile grid cannot fill the GPU
 
 
@@ -82,13 +85,17 @@ def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulat
     taps = k * k
     rows = taps * Ca
     pixels = N * Hq * Wq
+    tile_splits = L.lib.cvae_wgrad_tile_splits(pixels, Ca, Cb, k, stride, pad) if (_TILE and tc is None) else 0
     if tc is None:
         tc = _TC and bool(L.lib.cvae_wgrad_tc_eligible(pixels, rows, Cb))
-    splits = (L.lib.cvae_wgrad_tc_splits if tc else L.lib.cvae_wgrad_splits)(pixels, rows, Cb)
+    if tile_splits > 0:        # few channels x many pixels: shared-memory tiled fp32 kernel (wgrad_tile.cu)
+        splits, fn, tc = tile_splits, L.lib.cvae_conv_wgrad_tile, 2
+    else:
+        splits = (L.lib.cvae_wgrad_tc_splits if tc else L.lib.cvae_wgrad_splits)(pixels, rows, Cb)
+        fn = L.lib.cvae_conv_wgrad_tc if tc else L.lib.cvae_conv_wgrad
     partial = empty(splits, rows, Cb, like=ga)
     p = L.WgradParams(L.ptr(ga), L.ptr(db), xa.c(), xb.c(), L.ptr(partial), splits, N, Ha, Wa, Ca, Hq, Wq, Cb,
                       k, k, stride, pad)
-    fn = L.lib.cvae_conv_wgrad_tc if tc else L.lib.cvae_conv_wgrad
     L.check(fn(p, L.stream()), f"conv_wgrad tc={int(tc)} {Ha}x{Wa}x{Ca} / {Hq}x{Wq}x{Cb} k{k}s{stride}")
     L.check(L.lib.cvae_wgrad_reduce(L.ptr(partial), splits, taps, Ca, Ca if ca_real is None else ca_real, Cb,
                                     L.ptr(grad_out), int(accumulate), L.stream()), "wgrad_reduce")

@@ -136,6 +136,13 @@ int cvae_wgrad_tc_eligible(int pixels, int rows, int Cb);
 int cvae_wgrad_tc_splits(int pixels, int rows, int Cb);
 int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s);
 
+/* Shared-memory tiled fp32 weight gradient for 3x3 (pad 1, stride 1 | 2) layers with few channels and
+ * many pixels (Ca in {1,16,32}, Cb in {1,16,32,64}: vit_backbone.py:74-78 stem.0/stem.3, :136-156
+ * decoder.8..18): same contract and partial layout as cvae_conv_wgrad, followed by cvae_wgrad_reduce.
+ * cvae_wgrad_tile_splits returns the K-split count to allocate (> 0) when the shape is covered, else 0. */
+int cvae_wgrad_tile_splits(int pixels, int Ca, int Cb, int k, int stride, int pad);
+int cvae_conv_wgrad_tile(const cvae_wgrad_params_t* p, cvae_stream_t s);
+
 /* ---- BatchNorm (training mode: batch statistics; eval: running statistics) -------------------
  * nn.BatchNorm2d / nn.BatchNorm1d, eps 1e-5, momentum 0.1 (vit_backbone.py:76-89;
  * vessel_analysis/00_core/models.py:227,237; causal_cascade/models.py:36). */

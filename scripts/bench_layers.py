@@ -111,8 +111,9 @@ def main():
             wt_f = ops.pack_weight(w, Ci, Ci, Co, taps, True, Ci, tc=tcf)
         stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
         in_x = xf if Ci > 1 else ops.IDENT
-        fwd = lambda: ops.conv_gather(x, wt_f, None, (Hd, Wd, Co), k, st, pad, mode_f, in_x=in_x, epi=L.EPI_STATS,
-                                      stats=stats, tc=tcf)
+        epi_f = L.EPI_STATS if Co > 1 else L.EPI_PLAIN      # the image head feeds the loss directly (no BatchNorm)
+        fwd = lambda: ops.conv_gather(x, wt_f, None, (Hd, Wd, Co), k, st, pad, mode_f, in_x=in_x, epi=epi_f,
+                                      stats=stats if Co > 1 else None, tc=tcf)
         ms = timeit(fwd, once, flush)
         by = 4.0 * (x.numel() + dy.numel())
         print(f"{name:24s} {'fwd' + ('*' if tcf else ''):6s} {ms:8.3f} {flops / ms / 1e9:8.1f} {by / ms / 1e6:8.0f}" + (role_times(fwd) if tcf else ""))

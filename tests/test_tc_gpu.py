@@ -236,3 +236,75 @@ def test_tc_wgrad_vs_simt_and_fp64(case):
     print(f"wgrad {case}: simt err {e0:.2e}  tc err {e1:.2e}")
     assert e0 <= 1e-5
     assert e1 <= 1e-5, f"tensor-core wgrad off by {e1:.3e} (SIMT {e0:.3e})"
+
+
+TILE_WGRAD_CASES = [
+    # N, Ha, Wa, Ca, Cb, stride, xform_a, xform_b   (3x3, pad 1; pixels >= 32768 routes to wgrad_tile.cu)
+    (8, 128, 128, 16, 16, 2, False, True),     # decoder ConvT 16->16: ga = dL/dout, db = layer input (BN+LReLU on load)
+    (8, 128, 128, 16, 32, 2, False, True),     # decoder ConvT 32->16
+    (8, 64, 64, 32, 32, 1, True, False),       # ResBlock(32)
+    (8, 128, 128, 32, 64, 2, True, False),     # stem.3 32->64 (two cb slices)
+    (2, 256, 256, 16, 1, 1, True, False),      # image head 16->1
+    (8, 128, 128, 1, 32, 2, False, False),     # stem.0 1->32
+    (3, 131, 127, 16, 16, 1, True, True),      # ragged patches (edge tiles partly outside the image)
+    (16, 90, 94, 32, 16, 2, True, False),      # ragged, stride 2
+]
+
+
+@pytest.mark.parametrize("case", TILE_WGRAD_CASES)
+def test_tiled_wgrad_vs_simt_and_fp64(case):
+    L, ops = _ops()
+    N, Ha, Wa, Ca, Cb, stride, xfa, xfb = case
+    k, pad = 3, 1
+    Hq, Wq = (Ha + 2 * pad - k) // stride + 1, (Wa + 2 * pad - k) // stride + 1
+    assert L.lib.cvae_wgrad_tile_splits(N * Hq * Wq, Ca, Cb, k, stride, pad) > 0
+    ga = gen(N, Ha, Wa, Ca, seed=1).cuda()
+    db = gen(N, Hq, Wq, Cb, seed=2).cuda()
+    xa, xb, ra, rb = ops.IDENT, ops.IDENT, None, None
+    if xfa:
+        s_, h_, c_ = (gen(Ca, seed=3).abs() + 0.5).cuda(), gen(Ca, seed=4).cuda(), gen(Ca, seed=5).cuda()
+        xa, ra = ops.XF(s_, h_, 0.01, c_), (s_.cpu().double(), h_.cpu().double(), 0.01, c_.cpu().double())
+    if xfb:
+        s_, h_, c_ = (gen(Cb, seed=6).abs() + 0.5).cuda(), gen(Cb, seed=7).cuda(), gen(Cb, seed=8).cuda()
+        xb, rb = ops.XF(s_, h_, 0.2, c_), (s_.cpu().double(), h_.cpu().double(), 0.2, c_.cpu().double())
+
+    def apply(x, r):
+        x = x.cpu().double()
+        if r is None:
+            return x
+        y = (x - r[3]) * r[0] + r[1]
+        return torch.where(y > 0, y, y * r[2])
+    A, B = apply(ga, ra).permute(0, 3, 1, 2), apply(db, rb).permute(0, 3, 1, 2)
+    want = torch.nn.grad.conv2d_weight(A, (Cb, Ca, k, k), B, stride=stride, padding=pad).reshape(Cb, Ca, k * k)
+    g_tile = torch.empty(Cb, Ca, k * k, device="cuda")
+    ops.conv_wgrad(ga, db, xa, xb, k, stride, pad, g_tile)              # default dispatch -> tiled kernel
+    g_simt = torch.empty(Cb, Ca, k * k, device="cuda")
+    ops.conv_wgrad(ga, db, xa, xb, k, stride, pad, g_simt, tc=False)    # reference SIMT split-K kernel
+    torch.cuda.synchronize()
+    e_t, e_s = rel(g_tile, want), rel(g_simt, want)
+    print(f"tiled wgrad {case}: tile err {e_t:.2e}  simt err {e_s:.2e}")
+    assert e_s <= 1e-5
+    assert e_t <= 1e-5, f"tiled wgrad off by {e_t:.3e}"
+
+
+def test_image_sized_stem_head_tiled_kernels():
+    """Image-sized 1-channel layers route to the shared-memory tiled kernels (skinny.cu *_tile,
+    wgrad_tile.cu): stem.0 (1 -> 32, stride 2, statistics epilogue) and the decoder tail
+    ConvT(16 -> 16)-BN-LReLU-Conv(16 -> 1) (head forward, head input gradient with the fused
+    activation-derivative epilogue, 16x1 / 1x32 / 16x16 weight gradients).  BatchNorm makes the
+    whole chain differentiable end to end; inputs are dense noise so no activation sits on a kink by
+    construction of the check (kink-robust tolerance of run_pair)."""
+    from causal_vae_b200 import nn
+    stem = nn.Sequential(nn.Conv2d(1, 32, 3, 2, 1), nn.BatchNorm2d(32), nn.LeakyReLU(),
+                         nn.Conv2d(32, 16, 3, 2, 1))
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in stem.state_dict().items()}, seed=21)
+    x = (gen(4, 1, 256, 256, seed=22) > 0.8).float()
+    lr = torch.nn.functional.leaky_relu
+    run_pair(stem, sd, lambda P, xx: O._conv(P, "3", lr(O._bn(P, "1", O._conv(P, "0", xx, 2, 1), True), 0.01), 2, 1),
+             x, need_dx=False)
+
+    tail = nn.Sequential(nn.ConvTranspose2d(16, 16, 3, 2, 1, 1), nn.BatchNorm2d(16), nn.LeakyReLU(),
+                         nn.Conv2d(16, 1, 3, padding=1))
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in tail.state_dict().items()}, seed=23)
+    x = gen(2, 16, 128, 128, seed=24)
+    run_pair(tail, sd, lambda P, xx: O._conv(P, "3", lr(O._bn(P, "1", O._convT(P, "0", xx, 2, 1, 1), True), 0.01), 1, 1), x)
