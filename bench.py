@@ -25,6 +25,9 @@ H = W = 256
 B_PER_GPU = 64
 FLOP_PER_SAMPLE = 5.057e9          # fwd+bwd matmul/conv FLOPs (2*MAC), measured on the reference
 BYTES_PER_SAMPLE = 77e6 + 8.8e6    # irreducible fp32 activation + parameter/optimizer traffic
+# dram__bytes_read.sum + dram__bytes_write.sum of the probed launch (decoder.12 input gradient, B = 64) from the
+# `ncu --set full` capture summarised in profiles/r1_ncu_halo_raw.txt; algorithmic bytes of that launch: 402.7e6
+NCU_TRAFFIC_BYTES = 390.9e6
 
 
 def peaks():
@@ -110,33 +113,87 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def dominant_kernel_probe(torch, ops, L):
-    """Time the dominant kernel alone, live, with CUDA events on the launching stream: the tcgen05
-    implicit-GEMM gather kernel on its heaviest instance of the step, a ResBlock(64) 3x3 conv at
-    64x64, B = 64 (19.3 GFLOP of algorithmic work per launch; 3xTF32 issues 3x that on the tensor
-    cores), with the BatchNorm+LeakyReLU operand transform and the statistics epilogue it runs with
-    inside the step.  L2 is flushed between launches."""
-    N, Hh, C = B_PER_GPU, 64, 64
-    src = torch.randn(N, Hh, Hh, C, device="cuda")
-    w = torch.randn(C, C, 9, device="cuda") * 0.05            # torch layout [Cout][Cin][taps]
-    wt = ops.pack_weight(w, C, C, C, 9, True, C, tc=True)
-    scale, shift, cen = (torch.randn(C, device="cuda") for _ in range(3))
-    stats = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
-    xf = ops.XF(scale, shift, 0.2, cen)
-    run = lambda: ops.conv_gather(src, wt, None, (Hh, Hh, C), 3, 1, 1, L.MODE_GATHER, in_x=xf, epi=L.EPI_STATS,
-                                  stats=stats, tc=True)
-    for _ in range(3):
-        run()
+def _time_launch(torch, fn, reps=10):
+    """CUDA-event duration of one launch (launching stream = torch's current stream), L2 flushed before
+    each repetition with a 256 MiB write; the host-side call overhead is excluded by enqueueing a
+    ~1 ms spin of device work first, so the GPU is never idle waiting for the launch."""
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    busy = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        fn()
     ts = []
-    for _ in range(10):
+    for _ in range(reps):
         flush.zero_()
+        busy.add_(1.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    ms = sum(ts) / len(ts)
-    flops = 2.0 * N * Hh * Hh * C * C * 9
-    return flops / (ms * 1e-3) / 1e12, ms, flops
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def dominant_kernel_probe(torch, ops, L):
+    """The dominant kernel of the step is conv_halo_tc_kernel (31 % of the device time in
+    profiles/r1_launches_final_summary.txt).  It is timed live on its two heaviest instances of the
+    vessel step at B = 64, with the operand transform / epilogue each runs with inside the step:
+      * decoder.12 input gradient (ConvT 16->16, 256^2 -> 128^2, stride-2 gather + activation-derivative
+        epilogue): HBM-bound -- algorithmic bytes = dL/dout (268 MB) + dL/din (67 MB) + the producer's raw
+        output re-read by the epilogue (67 MB);
+      * stem.6 forward (Conv 64->128 s2 @64^2, BatchNorm+LeakyReLU on load, statistics epilogue):
+        tensor-bound -- 9.66 GFLOP algorithmic, 3x that issued as tf32 MMAs."""
+    N = B_PER_GPU
+    # ---- HBM-bound instance ----
+    dy = torch.randn(N, 256, 256, 16, device="cuda")
+    ref = torch.randn(N, 128, 128, 16, device="cuda")
+    w = torch.randn(16, 16, 9, device="cuda") * 0.05              # ConvTranspose2d weight [Cin][Cout][taps]
+    wt = ops.pack_weight(w, 16, 16, 16, 9, True, 16, tc=True)
+    esc, esh, ece = (torch.rand(16, device="cuda") + 0.5, torch.randn(16, device="cuda"), torch.randn(16, device="cuda"))
+    st = torch.zeros(32, dtype=torch.float64, device="cuda")
+    hbm_fn = lambda: ops.conv_gather(dy, wt, None, (128, 128, 16), 3, 2, 1, L.MODE_GATHER, epi=L.EPI_DACT, epi_ref=ref,
+                                     epi_x=ops.XF(esc, esh, 0.01, ece), stats=st, tc=True)
+    ms_h = _time_launch(torch, hbm_fn)
+    bytes_h = 4.0 * (dy.numel() + 2 * ref.numel())
+    del dy, ref
+    # ---- tensor-bound instance ----
+    x = torch.randn(N, 64, 64, 64, device="cuda")
+    w2 = torch.randn(128, 64, 9, device="cuda") * 0.05            # Conv2d weight [Cout][Cin][taps]
+    wt2 = ops.pack_weight(w2, 64, 64, 128, 9, True, 64, tc=True)
+    sc, sh, ce = (torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda"), torch.randn(64, device="cuda"))
+    st2 = torch.zeros(256, dtype=torch.float64, device="cuda")
+    tc_fn = lambda: ops.conv_gather(x, wt2, None, (32, 32, 128), 3, 2, 1, L.MODE_GATHER, in_x=ops.XF(sc, sh, 0.01, ce),
+                                    epi=L.EPI_STATS, stats=st2, tc=True)
+    ms_t = _time_launch(torch, tc_fn)
+    flops_t = 2.0 * N * 32 * 32 * 64 * 128 * 9
+    return {"hbm_ms": ms_h, "hbm_bytes": bytes_h, "tc_ms": ms_t, "tc_flops": flops_t}
+
+
+def counterfactual_rate(torch, model, sources=256, chunk=32):
+    """BASELINE configs[4]: do(M_k += 5) on every concept k of every source, decode, reduce each image to
+    ||x_cf - x_base||_2 on device (vessel_analysis/04_generate_counterfactual/generate_counterfactual.py:83-99,
+    analyze_vessel.py:101-115).  A bounded sample of the 65536-source job: `sources` sources x 12 concepts,
+    streamed in chunks; inputs resident in HBM, eval mode."""
+    from causal_vae_b200 import counterfactual as CF
+    from causal_vae_b200.vessel import models
+    model.eval()
+    K, Z = models.CONFIG["M_DIM"], models.CONFIG["Z_DIM"]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    m = torch.randn(sources, K, device="cuda", generator=g)
+    z = torch.randn(sources, Z, device="cuda", generator=g)
+    with torch.no_grad():
+        for _ in range(2):
+            CF.counterfactual_sweep(model, m[:chunk], z[:chunk], delta=5.0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        acc = 0.0
+        for i in range(0, sources, chunk):
+            l2, _, _ = CF.counterfactual_sweep(model, m[i:i + chunk], z[i:i + chunk], delta=5.0)
+            acc = acc + l2.sum()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    model.train()
+    return sources * K / (ms * 1e-3), ms, float(acc)
 
 
 def run_native(args):
@@ -148,6 +205,7 @@ def run_native(args):
     dist = world > 1
     if dist:
         import torch.distributed as td
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line (no "NCCL version" banner)
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
     from causal_vae_b200 import _lib as L
     from causal_vae_b200 import ops
@@ -208,22 +266,29 @@ def run_native(args):
     ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 * 0.0)
     h2d = sum(a.numel() * a.element_size() for a in pin)
 
+    # ---- counterfactual generation (every rank decodes its own shard of sources; no collective) ----
+    barrier()
+    cf_rate, cf_ms, _ = counterfactual_rate(torch, model)
+    barrier()
+
     if dist:
-        tt = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([ms, ms_e2e, cf_ms], device="cuda", dtype=torch.float64)
         td.all_reduce(tt, op=td.ReduceOp.MAX)
-        ms, ms_e2e = tt.tolist()
+        ms, ms_e2e, cf_ms = tt.tolist()
+    cf_rate = 256 * 12 / (cf_ms * 1e-3)                 # per-GPU rate at the slowest rank
     if rank != 0:
-        if dist:
-            td.destroy_process_group()
+        _finish(dist)
         return
 
     hbm, bf16_burst, bf16_sus, how = peaks()
     ms_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
     e2e_v = world * B * args.steps / (ms_e2e * 1e-3)
-    tf, k_ms, k_flops = dominant_kernel_probe(torch, ops, L)
+    probe = dominant_kernel_probe(torch, ops, L)
     threads = os.cpu_count() or 1
     cpu_v, cpu_ms = cpu_reference_step_rate(2, 1, 16, threads)
+    ach_gbs = probe["hbm_bytes"] / (probe["hbm_ms"] * 1e-3) / 1e9
+    ach_tf = probe["tc_flops"] / (probe["tc_ms"] * 1e-3) / 1e12
     line = {
         "metric": "train samples/sec (fwd+bwd+step)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -232,27 +297,51 @@ def run_native(args):
                                "fwd+loss+bwd+clip_grad_norm(5)+Adam(1e-4), data-parallel grad all-reduce (SUM)",
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "per-step working set (~5 GB of fp32 activations at B=64) is >> the 126 MB L2; "
-                         "the kernel probe flushes L2 with a 256 MiB write between launches"},
+                         "the kernel probes flush L2 with a 256 MiB write between launches"},
         "loss": loss,
         "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": per_step_calls * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_burst, "unit": "TFLOP/s", "frac": tf / bf16_burst,
-                     "traffic": None, "kernel": "igemm_tc_kernel (tcgen05 3xTF32; ResBlock(64) conv3x3 @64x64, B=64)",
-                     "flops_per_launch": k_flops, "ms_per_launch": k_ms,
-                     "peak_source": f"{how} bf16 burst; fp32-grade 3xTF32 math can reach at most 1/6 of it "
-                                    "(tf32 = half the bf16 rate, three MMAs per product)"},
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
+                     "traffic": NCU_TRAFFIC_BYTES,
+                     "kernel": "conv_halo_tc_kernel (tcgen05 3xTF32, halo-tile staging) on its longest launch of the step: "
+                               "decoder.12 ConvT(16->16) input gradient, 256^2 -> 128^2, B=64",
+                     "bytes_per_launch": probe["hbm_bytes"], "ms_per_launch": probe["hbm_ms"],
+                     "peak_source": f"{how} copy bandwidth (burst: kernel timed alone)",
+                     "traffic_source": "profiles/r1_ncu_halo_raw.txt (dram__bytes_read.sum + dram__bytes_write.sum, same launch)"},
+        "roofline_tensor": {"bound": "tensor", "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s",
+                            "frac": ach_tf / bf16_burst,
+                            "kernel": "conv_halo_tc_kernel on stem.6 forward (Conv 64->128 s2 @64^2, B=64)",
+                            "flops_per_launch": probe["tc_flops"], "ms_per_launch": probe["tc_ms"],
+                            "peak_source": f"{how} bf16 burst; fp32-grade 3xTF32 issues 3 tf32 MMAs per product and a "
+                                           "kind::tf32 MMA (K=8) costs >= 96 clk from shared memory whatever N <= 128 is "
+                                           "(scripts/umma_rate.cu, profiles/r1_umma_probes.txt): ceiling = 128*N*8 MAC / 96 clk / 3"},
         "step_roofline": {"bound": "hbm", "bytes_per_sample": BYTES_PER_SAMPLE, "peak_gbs": hbm,
                           "roofline_samples_per_s_per_gpu": hbm * 1e9 / BYTES_PER_SAMPLE,
                           "frac": (value / world) / (hbm * 1e9 / BYTES_PER_SAMPLE),
                           "achieved_tflops": value / world * FLOP_PER_SAMPLE / 1e12},
+        "counterfactual": {"metric": "counterfactuals/sec (do(M_k += 5) over all 12 concepts, decode 256x256, "
+                                     "per-image L2 effect reduced on device)",
+                           "value": cf_rate * world, "unit": "images/s", "n_gpus": world,
+                           "sample": "256 sources x 12 concepts per GPU in chunks of 32 sources (bounded sample of the "
+                                     "65536-source job of BASELINE configs[4]; sources shard across GPUs with no collective)",
+                           "ms": cf_ms},
         "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": "2 timed steps of batch 16 at 256x256 (oracle port of the reference step)"},
     }
     print(json.dumps(line))
+    _finish(dist)
+
+
+def _finish(dist):
+    """Leave without tearing NCCL down: destroying a process group whose communicator is still referenced by
+    the captured CUDA graph blocked both ranks at exit (observed at N = 2); nothing is pending after the
+    last all-reduce, so the ranks flush and exit."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if dist:
-        td.destroy_process_group()
+        os._exit(0)
 
 
 def main():

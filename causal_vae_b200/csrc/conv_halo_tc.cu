@@ -543,9 +543,19 @@ static bool build_halo_plan(const GatherArgs& g, HaloPlan& hp, int max_sub) {
 
 // exported to conv_tc.cu: returns CVAE_OK when launched, 1 when the shape is not covered (caller falls
 // back to the per-tap gather kernel), < 0 on error.
-int launch_conv_halo_tc(const GatherArgs& g, cudaStream_t st) {
-  if (g.wtaps < 2) return 1;                       // 1x1 / Linear: nothing to share between taps
-  if (g.Cs % 16 != 0 || g.Cd % 16 != 0 || g.Cd > 256) return 1;
+int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
+  GatherArgs g = g_in;
+  if (g.wtaps < 2) {
+    // 1x1 / Linear: a plain GEMM over M = N*H*W rows.  Viewed as ONE image of M/8 x 8 positions, a
+    // 16 x 8 tile is 128 consecutive rows and the single "tap" is the tile itself (no halo).
+    const long long M = (long long)g.N * g.Hs * g.Ws;
+    if (g.nphase != 1 || g.is != 1 || g.os != 1 || g.Hs != g.Hd || g.Ws != g.Wd || M % 8 != 0 || M >= (1ll << 31)) return 1;
+    if (g.phase[0].ntaps != 1 || g.phase[0].taps[0].dh != 0 || g.phase[0].taps[0].dw != 0) return 1;
+    g.N = 1; g.Hs = g.Hd = (int)(M / 8); g.Ws = g.Wd = 8;
+    g.phase[0].Hq = g.Hs; g.phase[0].Wq = 8;
+  }
+  if (g.Cs % 16 != 0 || g.Cd % 16 != 0) return 1;
+  if (g.Cd > 256 && g.epi != CVAE_EPI_PLAIN && g.stats != nullptr) return 1;   // s_stat holds 256 channels
   int bn = 0;
   for (int c : {128, 64, 32, 16})
     if (g.Cd % c == 0 && 2 * g.nphase * c <= 512) { bn = c; break; }
