@@ -25,6 +25,7 @@ struct WgradArgs {
   float* partial;
   int N, Ha, Wa, Ca, Hq, Wq, Cb;
   int kw, stride, pad, rows, kchunk, K;
+  int seg;   // wgrad_tc A-loader variant: 32 / 16 / 8 = whole output-row segments per stage, -1 = Linear, 0 = general
 };
 
 // skinny.cu: 1-channel layers as pure HBM streams.  Each returns false when the shape is not covered.

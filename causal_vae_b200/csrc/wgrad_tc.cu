@@ -25,6 +25,45 @@ constexpr int kWgThreads = 13 * 32;   // 8 A warps + 4 B warps + 1 MMA warp
 constexpr int kWgStages = 4;
 constexpr int kWgKPix = 32;           // pixels (K) per stage
 
+// A-operand loaders: 32 consecutive pixels of one (tap, channel) row into registers; bit p of the
+// returned mask is set where the value is real data (padding / out-of-range pixels stay exactly 0).
+// wg_load_seg: the stage is made of 32/SEG whole output-row segments (Wq % SEG == 0, stages start on
+// multiples of 32 pixels), so row / image coordinates and the vertical bound are computed once per
+// segment instead of once per pixel (the per-pixel form, ~25 instructions per value, made this
+// producer the bottleneck of the kernel).  wg_load_lin: 1x1 / Linear (pixel = row of the matrix).
+template <int SEG>
+__device__ __forceinline__ uint32_t wg_load_seg(const WgradArgs& a, int kb, int kend, bool row_ok, int dh, int dw, int ca,
+                                                float (&v)[32]) {
+  uint32_t okm = 0;
+#pragma unroll
+  for (int sg = 0; sg < 32 / SEG; ++sg) {
+    const int pixs = kb + sg * SEG;
+    const int qw0 = pixs % a.Wq, t = pixs / a.Wq, qh = t % a.Hq, n = t / a.Hq;
+    const int ih = qh * a.stride + dh;
+    const bool hok = row_ok && pixs < kend && (unsigned)ih < (unsigned)a.Ha;
+    const float* rowp = a.ga + (((size_t)n * a.Ha + (hok ? ih : 0)) * a.Wa) * a.Ca + ca;
+    int iw = qw0 * a.stride + dw;
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      const bool ok = hok && (unsigned)iw < (unsigned)a.Wa;
+      v[sg * SEG + j] = 0.f;
+      if (ok) { v[sg * SEG + j] = __ldg(rowp + (size_t)iw * a.Ca); okm |= 1u << (sg * SEG + j); }
+      iw += a.stride;
+    }
+  }
+  return okm;
+}
+__device__ __forceinline__ uint32_t wg_load_lin(const WgradArgs& a, int kb, int kend, bool row_ok, int ca, float (&v)[32]) {
+  uint32_t okm = 0;
+  const float* src = a.ga + (size_t)kb * a.Ca + ca;
+#pragma unroll
+  for (int p = 0; p < 32; ++p) {
+    v[p] = 0.f;
+    if (row_ok && kb + p < kend) { v[p] = __ldg(src + (size_t)p * a.Ca); okm |= 1u << p; }
+  }
+  return okm;
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradArgs a, const int BN) {
   extern __shared__ uint8_t dsm_raw[];
   __shared__ __align__(8) uint64_t s_full[kWgStages];
@@ -74,19 +113,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     for (int st = par; st < nst; st += 2) {
       const int slot = st % kWgStages;
       const int kb = kbeg + st * kWgKPix;
-      int qw = kb % a.Wq, t = kb / a.Wq, qh = t % a.Hq, n = t / a.Hq;
       float v[kWgKPix];
       uint32_t okm = 0;                          // padding / out-of-range pixels stay exactly 0
+      if (a.seg == 32) okm = wg_load_seg<32>(a, kb, kend, row_ok, dh, dw, ca, v);
+      else if (a.seg == 16) okm = wg_load_seg<16>(a, kb, kend, row_ok, dh, dw, ca, v);
+      else if (a.seg == 8) okm = wg_load_seg<8>(a, kb, kend, row_ok, dh, dw, ca, v);
+      else if (a.seg == -1) okm = wg_load_lin(a, kb, kend, row_ok, ca, v);
+      else {
+        int qw = kb % a.Wq, t = kb / a.Wq, qh = t % a.Hq, n = t / a.Hq;
 #pragma unroll
-      for (int p = 0; p < kWgKPix; ++p) {
-        const int ih = qh * a.stride + dh, iw = qw * a.stride + dw;
-        const bool ok = row_ok && (kb + p) < kend && (unsigned)ih < (unsigned)a.Ha && (unsigned)iw < (unsigned)a.Wa;
-        v[p] = 0.f;
-        if (ok) {
-          v[p] = __ldg(a.ga + (((size_t)n * a.Ha + ih) * a.Wa + iw) * a.Ca + ca);
-          okm |= 1u << p;
+        for (int p = 0; p < kWgKPix; ++p) {
+          const int ih = qh * a.stride + dh, iw = qw * a.stride + dw;
+          const bool ok = row_ok && (kb + p) < kend && (unsigned)ih < (unsigned)a.Ha && (unsigned)iw < (unsigned)a.Wa;
+          v[p] = 0.f;
+          if (ok) {
+            v[p] = __ldg(a.ga + (((size_t)n * a.Ha + ih) * a.Wa + iw) * a.Ca + ca);
+            okm |= 1u << p;
+          }
+          if (++qw == a.Wq) { qw = 0; if (++qh == a.Hq) { qh = 0; ++n; } }
         }
-        if (++qw == a.Wq) { qw = 0; if (++qh == a.Hq) { qh = 0; ++n; } }
       }
       uint32_t hi[kWgKPix];
 #pragma unroll
@@ -267,6 +312,12 @@ extern "C" int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s)
   int chunk = (a.K + p->splits - 1) / p->splits;
   chunk = ((chunk + kWgKPix - 1) / kWgKPix) * kWgKPix;
   a.kchunk = chunk;
+  // fast A-operand loaders (see wg_load_seg / wg_load_lin)
+  a.seg = 0;
+  if (p->kh == 1 && p->kw == 1 && p->Ha == 1 && p->Wa == 1 && p->stride == 1 && p->pad == 0) a.seg = -1;
+  else if (p->Wq % 32 == 0) a.seg = 32;
+  else if (p->Wq == 16) a.seg = 16;
+  else if (p->Wq == 8) a.seg = 8;
   const size_t smem = (size_t)kWgStages * 2 * kWgKPix * 128 * ((BN + 31) / 32) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
