@@ -1,5 +1,6 @@
 """causal_cascade/train.py:5-40 on the native kernels: loss_function and the inner training step."""
 from .. import functional as F
+from ..chain import direct_grads
 from ..optim import FlatParams, FusedClipAdam
 
 
@@ -23,6 +24,7 @@ class CascadeTrainer:
         self.opt.zero_grad()
         recon_x, m_hat, mu, logvar = self.model(x, m, t, eps)
         loss, l_recon, l_m = loss_function(recon_x, x, m_hat, m, mu, logvar, self.gamma)
-        loss.backward()
+        with direct_grads():
+            loss.backward()
         self.opt.step()
         return loss, l_recon, l_m

@@ -69,6 +69,29 @@ class _Rec:
     pass
 
 
+# Trainers that own zero_grad() (FlatParams) and use every parameter exactly once per backward set
+# DIRECT_GRADS[0] = True: parameter gradients are then written straight into `p.grad` by the kernels
+# that produce them and autograd receives None, which removes one accumulate launch (and one
+# temporary) per parameter tensor - 180 launches per vessel step.
+DIRECT_GRADS = [False]
+
+
+class direct_grads:
+    """with direct_grads(): loss.backward()  - see DIRECT_GRADS."""
+
+    def __enter__(self):
+        self.prev = DIRECT_GRADS[0]
+        DIRECT_GRADS[0] = True
+
+    def __exit__(self, *exc):
+        DIRECT_GRADS[0] = self.prev
+        return False
+
+
+def direct_ok(p):
+    return DIRECT_GRADS[0] and p is not None and p.requires_grad and p.grad is not None and p.grad.is_contiguous()
+
+
 def _pack_fwd(u, Cs_phys, tc=False):
     w = u.mod.weight
     taps = u.k * u.k
@@ -164,20 +187,28 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
     if u.bn is not None:
         if rec.mean is None:
             raise NotImplementedError("backward through eval-mode BatchNorm is not supported")
+        outs = tuple(p.grad if direct_ok(p) else None for p in (u.bn.weight, u.bn.bias, u.mod.bias))
         ca, cb, cc, dgamma, dbeta, dbias = ops.bn_bwd_finalize(stats, Cd, N * Hd * Wd, u.bn.weight, rec.mean,
-                                                               rec.rstd, has_bias)
+                                                               rec.rstd, has_bias, outs)
+        dgamma, dbeta = (None if o is not None else g for o, g in zip(outs[:2], (dgamma, dbeta)))
+        dbias = None if outs[2] is not None else dbias
         dy = ops.bn_bwd_apply(dz, y, ca, cb, cc, rec.mean)
     else:
         dy = dz
         dgamma = dbeta = None
-        dbias = ops.col_sum(dy, Cd) if has_bias else None
-    gw = torch.empty_like(w)
+        if has_bias and direct_ok(u.mod.bias):
+            ops.col_sum(dy, Cd, out=u.mod.bias.grad)
+            dbias = None
+        else:
+            dbias = ops.col_sum(dy, Cd) if has_bias else None
+    w_direct = direct_ok(w)
+    gw = w.grad if w_direct else torch.empty_like(w)
     if u.kind == "convT":
         ops.conv_wgrad(dy, S_in.t, IDENT, S_in.x, u.k, u.stride, u.pad, gw)
     else:
         ca_real = w.shape[1] if u.kind == "linear" else None
         ops.conv_wgrad(S_in.t, dy, S_in.x, IDENT, u.k, u.stride, u.pad, gw, ca_real=ca_real)
-    grads.append((gw, dbias, dgamma, dbeta))
+    grads.append((None if w_direct else gw, dbias, dgamma, dbeta))
     if not need_dx:
         return None
     cols = Cs if grad_cols is None else grad_cols
@@ -277,7 +308,7 @@ class ChainFn(torch.autograd.Function):
     def backward(ctx, gout):
         gout = gout.contiguous()
         dx, flat = chain_backward(ctx.chain, ctx.recs, ctx.final, gout, ctx.need_dx, ctx.grad_cols)
-        ctx.recs = None
+        ctx.recs = ctx.final = None
         if dx is not None and ctx.grad_cols is not None and ctx.grad_cols != ctx.x_cols:
             full = ops.zeros(*dx.shape[:-1], ctx.x_cols, like=dx)
             rows = dx.numel() // ctx.grad_cols

@@ -211,6 +211,7 @@ class _LayerNorm(torch.autograd.Function):
         y, mean, rstd = ops.layernorm_fwd(xr, gamma, beta, rows, D, xs, eps)
         ctx.save_for_backward(xr, gamma, mean, rstd)
         ctx.geom = (rows, D, xs)
+        ctx.params = (gamma, beta)
         return y.view(x.shape)
 
     @staticmethod
@@ -219,6 +220,11 @@ class _LayerNorm(torch.autograd.Function):
         rows, D, xs = ctx.geom
         g = g.contiguous()
         dx = ops.empty(rows, D, like=g)
+        from .chain import direct_ok
+        pg, pb = ctx.params
+        if direct_ok(pg) and direct_ok(pb):          # the kernel accumulates into the (zeroed) .grad views
+            ops.layernorm_bwd(g, xr, gamma, mean, rstd, rows, D, xs, dx, D, False, pg.grad, pb.grad)
+            return dx.view(g.shape), None, None, None
         dgamma, dbeta = ops.zeros(D, like=g), ops.zeros(D, like=g)
         ops.layernorm_bwd(g, xr, gamma, mean, rstd, rows, D, xs, dx, D, False, dgamma, dbeta)
         return dx.view(g.shape), dgamma, dbeta, None
@@ -268,6 +274,7 @@ class _Tokens(torch.autograd.Function):
         L.check(L.lib.cvae_tokens_fwd(L.ptr(feat.contiguous()), L.ptr(cls), L.ptr(posc), L.ptr(tok), B, n, D,
                                       L.stream()), "tokens_fwd")
         ctx.geom = (B, h, w, D, pos.shape[1])
+        ctx.params = (cls, pos)
         return tok
 
     @staticmethod
@@ -276,11 +283,17 @@ class _Tokens(torch.autograd.Function):
         n = h * w
         g = g.contiguous()
         dfeat = ops.empty(B, h, w, D, like=g) if ctx.needs_input_grad[0] else None
-        dcls = ops.empty(1, 1, D, like=g)
-        dpos = ops.zeros(1, npos, D, like=g) if npos != n + 1 else ops.empty(1, npos, D, like=g)
+        from .chain import direct_ok
+        pc, pp = ctx.params
+        direct = direct_ok(pc) and direct_ok(pp) and pc.grad.numel() == D and pp.grad.numel() == npos * D
+        if direct:                                   # rows of pos beyond n+1 keep their zero_grad() zeros
+            dcls, dpos = pc.grad, pp.grad
+        else:
+            dcls = ops.empty(1, 1, D, like=g)
+            dpos = ops.zeros(1, npos, D, like=g) if npos != n + 1 else ops.empty(1, npos, D, like=g)
         L.check(L.lib.cvae_tokens_bwd(L.ptr(g), L.ptr(dfeat), L.ptr(dcls), L.ptr(dpos), B, n, D, L.stream()),
                 "tokens_bwd")
-        return dfeat, dcls, dpos
+        return (dfeat, None, None) if direct else (dfeat, dcls, dpos)
 
 
 def tokens(feat_nhwc, cls, pos):

@@ -4,6 +4,7 @@ import numpy as np
 import torch
 
 from .. import functional as F
+from ..chain import direct_grads
 from ..optim import FlatParams, FusedClipAdam
 
 
@@ -27,7 +28,8 @@ class ViTVAETrainer:
         self.opt.zero_grad()
         recons, _, mu, log_var = self.model(x, eps)
         loss, rl, kl = loss_function(recons, x, mu, log_var, self.beta)
-        loss.backward()
+        with direct_grads():
+            loss.backward()
         self.opt.step()
         return loss, rl, kl
 

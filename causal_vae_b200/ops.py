@@ -127,9 +127,14 @@ def col_stats(y2d_rows, C, y, stats):
     L.check(L.lib.cvae_col_stats(L.ptr(y), y2d_rows, C, L.ptr(stats), L.stream()), "col_stats")
 
 
-def bn_bwd_finalize(stats, C, count, gamma, mean, rstd, want_dbias):
-    ca, cb, cc, dg, db = (empty(C, like=mean) for _ in range(5))
-    dbias = empty(C, like=mean) if want_dbias else None
+def bn_bwd_finalize(stats, C, count, gamma, mean, rstd, want_dbias, outs=(None, None, None)):
+    """outs: optional destination tensors for (dgamma, dbeta, dbias) (e.g. the parameters' .grad views)."""
+    ca, cb, cc = (empty(C, like=mean) for _ in range(3))
+    dg = outs[0] if outs[0] is not None else empty(C, like=mean)
+    db = outs[1] if outs[1] is not None else empty(C, like=mean)
+    dbias = None
+    if want_dbias:
+        dbias = outs[2] if outs[2] is not None else empty(C, like=mean)
     L.check(L.lib.cvae_bn_bwd_finalize(L.ptr(stats), C, float(count), L.ptr(gamma), L.ptr(mean), L.ptr(rstd),
                                        L.ptr(ca), L.ptr(cb), L.ptr(cc), L.ptr(dg), L.ptr(db), L.ptr(dbias),
                                        L.stream()), "bn_bwd_finalize")

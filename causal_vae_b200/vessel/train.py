@@ -3,6 +3,7 @@ train_one_epoch's inner step) on the native kernels, plus a CUDA-graph-captured 
 import torch
 
 from .. import functional as F
+from ..chain import direct_grads
 from ..optim import FlatParams, FusedClipAdam
 from ..parallel import allreduce_gradients
 from .models import CONFIG
@@ -48,7 +49,8 @@ class VesselTrainer:
         out = self.model(x, m, t, eps)
         recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
         loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
-        loss.backward()
+        with direct_grads():      # zero_grad() above zeroed the flat buffer; every parameter is used once
+            loss.backward()
         return loss, recon, kld, morph, sp
 
     def _allreduce(self):
@@ -89,6 +91,12 @@ class VesselTrainer:
                 if not v.is_floating_point() or k.endswith(("running_mean", "running_var")):
                     v.copy_(snap[1][k])
             self.opt.exp_avg.zero_(); self.opt.exp_avg_sq.zero_(); self.opt.step_count.zero_()
+        # Autograd graphs of the warm-up steps can survive in reference cycles; their AccumulateGrad nodes
+        # remember the warm-up stream, and a leaf node that receives no gradient (direct_grads) would make
+        # the capturing stream wait on that uncaptured stream.  Collect them so the capture pass builds
+        # fresh nodes on the capture stream.
+        import gc
+        gc.collect()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_losses = self._fwd_bwd(**self.static)

@@ -329,6 +329,36 @@ def test_dropout_statistics():
     assert torch.equal((x.grad != 0), (y != 0)), "backward must regenerate the same mask"
 
 
+@pytest.mark.parametrize("S,p", [(65, 0.0), (65, 0.3), (17, 0.1), (128, 0.2), (7, 0.0)])
+def test_attention_core_with_dropout(S, p):
+    """softmax(QK^T/sqrt(d)) (dropout) V and its gradient against fp64 torch, using the very mask the
+    kernel drew: forward saves it in the sign bits of the probabilities, backward reads it from there."""
+    from causal_vae_b200 import functional as F
+    from causal_vae_b200 import ops
+    B, H, d = 3, 8, 32
+    D = H * d
+    qkv = gen(B, S, 3 * D, seed=40, scale=0.7)
+    g = gen(B, S, D, seed=41)
+    F.manual_seed(77)
+    seed, off, cnt = F.next_rng() if p > 0 else (0, 0, None)
+    qg = qkv.cuda()
+    out, probs = ops.attention_fwd(qg, B, S, H, d, p, seed, off, cnt)
+    dq = ops.attention_bwd(qg, probs, g.cuda(), B, S, H, d, p, seed, off, cnt)
+    mask = (~torch.signbit(probs)).double().cpu()
+    if p > 0:
+        assert abs(mask.mean().item() - (1 - p)) < 0.02
+    else:
+        assert mask.min().item() == 1.0
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = (t.view(B, S, H, d).transpose(1, 2) for t in qr.chunk(3, dim=-1))
+    P = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    assert_close(probs.abs(), P, FWD_TOL, "probabilities")
+    o = ((P * mask / (1 - p)) @ v).transpose(1, 2).reshape(B, S, D)
+    assert_close(out, o, FWD_TOL, "attention out")
+    o.backward(g.double())
+    assert_close(dq, qr.grad, GRAD_TOL, "dqkv")
+
+
 def test_counterfactual_helpers():
     from causal_vae_b200.counterfactual import do_expand, rowdiff_l2
     S, K, Z = 5, 12, 128
