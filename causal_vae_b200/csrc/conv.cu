@@ -533,7 +533,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_tile_kernel(const float* __r
       float s = 0.f;
       if (a_ < ca && b_ < cb) {
         const float* p = partial + ((size_t)tap * ca + a_) * cb + b_;
-        for (int k = 0; k < splits; ++k) s += p[(size_t)k * stride];
+#pragma unroll 8
+        for (int k = 0; k < splits; ++k) s += __ldg(p + (size_t)k * stride);
       }
       tile[lane * ld + al * taps + tap] = s;
     }
@@ -729,7 +730,13 @@ extern "C" int cvae_wgrad_reduce(const float* partial, int splits, int taps, int
   if (!partial || !dst || splits < 1 || ca_real > ca) return CVAE_ERR_BAD_ARG;
   const int total = cb * ca * taps;
   if (((ca + 31) / 32) * ((cb + 31) / 32) >= 128 && splits <= 32 && taps <= 16) {
-    if (taps <= 9) {
+    if (taps == 1 && ((ca + 31) / 32) * ((cb + 31) / 32) < 1024) {
+      // mid-size Linear weights (256 x 512 ...): 32 x 32 tiles give < 1 block per SM and a serial chain of
+      // `splits` loads per thread; 8-row tiles quadruple the blocks in flight
+      const size_t smem = sizeof(float) * 32 * (8 * taps + 1);
+      wgrad_reduce_tile_kernel<8><<<dim3((ca + 7) / 8, (cb + 31) / 32), 256, smem, as_stream(s)>>>(
+          partial, splits, taps, ca, ca_real, cb, dst, accumulate);
+    } else if (taps <= 9) {
       const size_t smem = sizeof(float) * 32 * (32 * taps + 1);
       wgrad_reduce_tile_kernel<32><<<dim3((ca + 31) / 32, (cb + 31) / 32), 256, smem, as_stream(s)>>>(
           partial, splits, taps, ca, ca_real, cb, dst, accumulate);

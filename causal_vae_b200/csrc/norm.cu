@@ -230,6 +230,82 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
   }
 }
 
+// D <= 256, D % 32 == 0: a lane owns columns lane + 32 k and keeps their dgamma / dbeta sums in registers
+// across the rows of its warp (the generic kernel spends two shared-memory atomics per element, with
+// all 8 warps of a block contending for the same 2 D words); x, dy and gamma are read once per row.
+template <int NPL>
+__global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, float* __restrict__ dx,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                int64_t rows, int D, int64_t xs, int64_t dxs,
+                                                                int accumulate_dx) {
+  extern __shared__ float sm[];  // [2][D]
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int n = D >> 5;
+  float ga[NPL], pg[NPL], pb[NPL];
+#pragma unroll
+  for (int k = 0; k < NPL; ++k) { ga[k] = k < n ? gamma[lane + 32 * k] : 0.f; pg[k] = 0.f; pb[k] = 0.f; }
+  for (int64_t row = (int64_t)blockIdx.x * nw + w; row < rows; row += (int64_t)gridDim.x * nw) {
+    const float* xr = x + row * xs;
+    const float* dr = dy + row * D;
+    const float mu = mean[row], rs = rstd[row];
+    float d[NPL], xh[NPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      d[k] = k < n ? dr[lane + 32 * k] : 0.f;
+      xh[k] = k < n ? (xr[lane + 32 * k] - mu) * rs : 0.f;
+      const float g = d[k] * ga[k];
+      s1 += g; s2 = fmaf(g, xh[k], s2);
+    }
+    s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      if (k < n) {
+        const float v = rs * (d[k] * ga[k] - s1 - xh[k] * s2);
+        float* o = dx + row * dxs + lane + 32 * k;
+        *o = accumulate_dx ? *o + v : v;
+        pg[k] = fmaf(d[k], xh[k], pg[k]); pb[k] += d[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NPL; ++k)
+    if (k < n) { atomicAdd(sm + lane + 32 * k, pg[k]); atomicAdd(sm + D + lane + 32 * k, pb[k]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, sm[i]);
+    atomicAdd(dbeta + i, sm[D + i]);
+  }
+}
+
+// sum of a flat vector (column sum with C == 1, e.g. the bias gradient of the 1-channel image head):
+// 128-bit loads, double accumulation per thread, one float atomic per block.
+__global__ void __launch_bounds__(256) flat_sum_kernel(const float* __restrict__ p, int64_t n, float* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+    s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) s += (double)p[(n4 << 2) + threadIdx.x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, (float)t);
+  }
+}
+
 static inline XformDev make_x(cvae_xform_t x) {
   XformDev d;
   d.scale = x.scale; d.shift = x.shift; d.center = x.center; d.slope = x.slope;
@@ -330,6 +406,14 @@ extern "C" int cvae_col_sum(const float* x, int64_t rows, int C, float* out, int
   if (!accumulate) {
     if (cudaMemsetAsync(out, 0, sizeof(float) * C, as_stream(s)) != cudaSuccess) return CVAE_ERR_LAUNCH;
   }
+  if (C == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    int64_t blocks = (rows / 4 + 255) / 256;
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    if (blocks < 1) blocks = 1;
+    flat_sum_kernel<<<(unsigned)blocks, 256, 0, as_stream(s)>>>(x, rows, out);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+  }
   XformDev xf{};
   col_reduce_kernel<2><<<col_grid(rows, C), dim3(32, 8), 0, as_stream(s)>>>(x, nullptr, xf, nullptr, nullptr, out,
                                                                            rows, C, accumulate);
@@ -351,6 +435,14 @@ extern "C" int cvae_layernorm_bwd(const float* dy, const float* x, const float* 
                                   int64_t xs, int64_t dxs, int accumulate_dx, cvae_stream_t s) {
   if (!dy || !x || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || rows <= 0 || D <= 0) return CVAE_ERR_BAD_ARG;
   if (D > 1024) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  if (D % 32 == 0 && D <= 256) {
+    int64_t blocks = (rows + 15) / 16;             // two rows per warp: the register sums amortise over them
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    layernorm_bwd_reg_kernel<8><<<(unsigned)blocks, 256, 2 * D * sizeof(float), as_stream(s)>>>(
+        dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, D, xs, dxs, accumulate_dx);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+  }
   int64_t blocks = (rows + 31) / 32;
   if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
   layernorm_bwd_kernel<<<(unsigned)blocks, 256, 2 * D * sizeof(float), as_stream(s)>>>(

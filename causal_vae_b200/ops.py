@@ -17,8 +17,38 @@ def empty(*shape, dtype=f32, like=None):
     return torch.empty(shape, dtype=dtype, device=dev)
 
 
+# Per-step arena for the small fp64 accumulators (BatchNorm statistics, loss sums): a trainer brackets
+# its forward + backward with arena_begin() / arena_end(); begin zeroes the whole arena with ONE launch
+# and every zeros(..., dtype=float64) inside the bracket is a view of it (the vessel step used 41
+# separate fill launches).  Outside a bracket zeros() allocates as usual.
+_ARENA = {"buf": None, "off": 0, "on": False}
+_ARENA_DOUBLES = 1 << 15
+
+
+def arena_begin(device):
+    a = _ARENA
+    if a["buf"] is None or a["buf"].device != device:
+        a["buf"] = torch.zeros(_ARENA_DOUBLES, dtype=torch.float64, device=device)
+    else:
+        fill(a["buf"].view(f32), 0.0)
+    a["off"], a["on"] = 0, True
+
+
+def arena_end():
+    _ARENA["on"] = False
+
+
 def zeros(*shape, dtype=f32, like=None):
     dev = like.device if like is not None else torch.device("cuda", torch.cuda.current_device())
+    a = _ARENA
+    if a["on"] and dtype == torch.float64 and a["buf"].device == dev:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if a["off"] + n <= _ARENA_DOUBLES:
+            v = a["buf"][a["off"]:a["off"] + n].view(shape)
+            a["off"] += (n + 1) // 2 * 2
+            return v
     return torch.zeros(shape, dtype=dtype, device=dev)
 
 

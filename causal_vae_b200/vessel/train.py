@@ -3,6 +3,7 @@ train_one_epoch's inner step) on the native kernels, plus a CUDA-graph-captured 
 import torch
 
 from .. import functional as F
+from .. import ops
 from ..chain import direct_grads
 from ..optim import FlatParams, FusedClipAdam
 from ..parallel import allreduce_gradients
@@ -46,11 +47,15 @@ class VesselTrainer:
 
     def _fwd_bwd(self, x, m, t, eps):
         self.opt.zero_grad()
-        out = self.model(x, m, t, eps)
-        recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
-        loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
-        with direct_grads():      # zero_grad() above zeroed the flat buffer; every parameter is used once
-            loss.backward()
+        ops.arena_begin(self.flat.data.device)
+        try:
+            out = self.model(x, m, t, eps)
+            recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
+            loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
+            with direct_grads():      # zero_grad() above zeroed the flat buffer; every parameter is used once
+                loss.backward()
+        finally:
+            ops.arena_end()
         return loss, recon, kld, morph, sp
 
     def _allreduce(self):
