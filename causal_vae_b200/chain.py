@@ -126,9 +126,10 @@ def _unit_fwd(u, S, train, keep):
     N, Hs, Ws, Cs = S.t.shape
     Hd, Wd, Cd = u.out_geom(Hs, Ws)
     mode = L.MODE_SCATTER if u.kind == "convT" else L.MODE_GATHER
-    tc = ops.tc_eligible(Cs, Cd, _min_phase_rows(N, Hd, Wd, u.stride, mode == L.MODE_SCATTER))
-    wt = _pack_fwd(u, Cs, tc)
     bn_train = u.bn is not None and (u.bn.training or not u.bn.track_running_stats)
+    tc = ops.tc_eligible(Cs, Cd, _min_phase_rows(N, Hd, Wd, u.stride, mode == L.MODE_SCATTER)) and not \
+        ops.few_eligible(Cs, Cd, u.k, u.stride, u.pad, mode, N, Hs, Ws, Hd, Wd, L.EPI_STATS if bn_train else L.EPI_PLAIN)
+    wt = _pack_fwd(u, Cs, tc)
     stats = ops.zeros(2 * Cd, dtype=torch.float64, like=S.t) if bn_train else None
     y = ops.conv_gather(S.t, wt, u.mod.bias, (Hd, Wd, Cd), u.k, u.stride, u.pad, mode, in_x=S.x,
                         epi=L.EPI_STATS if bn_train else L.EPI_PLAIN, stats=stats, tc=tc)
@@ -221,7 +222,9 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
         dyp = ops.zeros(N, 1, 1, dy_cols, like=dy)
         ops.copy_cols(dy, Cd, 0, dyp, dy_cols, 0, N, Cd)
         dy, Cd = dyp, dy_cols
-    tc = ops.tc_eligible(Cd, cols, _min_phase_rows(N, Hs, Ws, u.stride, mode == L.MODE_SCATTER))
+    epi_b = L.EPI_DACT if ((prev_entry is not None and not prev_entry.x.identity) or add is not None) else L.EPI_PLAIN
+    tc = ops.tc_eligible(Cd, cols, _min_phase_rows(N, Hs, Ws, u.stride, mode == L.MODE_SCATTER)) and not \
+        ops.few_eligible(Cd, cols, u.k, u.stride, u.pad, mode, N, Hd, Wd, Hs, Ws, epi_b)
     wt = _pack_dgrad(u, cols, tc, dy_cols)
     if prev_entry is not None and not prev_entry.x.identity:
         return ops.conv_gather(dy, wt, None, (Hs, Ws, cols), u.k, u.stride, u.pad, mode, epi=L.EPI_DACT,

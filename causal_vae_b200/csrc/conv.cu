@@ -626,8 +626,13 @@ extern "C" int cvae_conv_gather(const cvae_conv_params_t* p, cvae_stream_t s) {
   for (int i = 0; i < g.nphase; ++i) maxM = max(maxM, p->N * g.phase[i].Hq * g.phase[i].Wq);
   cudaStream_t st = as_stream(s);
 
-  const bool tiled_ok = (p->Cs % 4 == 0) && (p->Cd % 4 == 0) && p->Cs >= 8 && p->Cd >= 8;
   g.ksplit = 1;
+  {  // image-sized 16 -> 16 stride-2 layers: fp32 tile kernels (conv_few.cu)
+    const int fr = launch_conv_few(p, g, st);
+    if (fr < 0) return fr;
+    if (fr == 1) { CVAE_LAUNCH_CHECK(); return CVAE_OK; }
+  }
+  const bool tiled_ok = (p->Cs % 4 == 0) && (p->Cd % 4 == 0) && p->Cs >= 8 && p->Cd >= 8;
   if (tiled_ok) {
     const int gx = (maxM + 127) / 128;
     const int bn = p->Cd >= 64 ? 64 : p->Cd >= 32 ? 32 : 16;

@@ -34,4 +34,7 @@ bool launch_conv_cd1(const GatherArgs& g, int maxM, cudaStream_t st);   // Cs % 
 bool launch_wgrad_cb1(const WgradArgs& a, int taps, cudaStream_t st);   // Cb == 1, Ca % 4 == 0, Ca <= 64
 bool launch_wgrad_ca1(const WgradArgs& a, int taps, cudaStream_t st);   // Ca == 1, Cb % 4 == 0, Cb <= 64
 
+// conv_few.cu: image-sized 16 -> 16 stride-2 layers.  1: launched, 0: not covered, < 0: error.
+int launch_conv_few(const cvae_conv_params_t* p, const GatherArgs& g, cudaStream_t st);
+
 }  // namespace cvae

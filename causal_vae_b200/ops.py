@@ -84,6 +84,16 @@ def tc_eligible(Cs, Cd, M):
     return _TC and M >= _TC_MIN_ROWS and bool(L.lib.cvae_tc_eligible(int(Cs), int(Cd), int(M)))
 
 
+_FEW = os.environ.get("CVAE_FEW", "1") != "0"   # fp32 tile kernels for image-sized 16 -> 16 stride-2 layers
+
+
+def few_eligible(Cs, Cd, k, stride, pad, mode, N, Hs, Ws, Hd, Wd, epi):
+    """True when cvae_conv_gather covers the layer with the few-channel tile kernels (then it must not go
+    to the tensor-core entry point, and its weights are packed in the fp32 layout)."""
+    return _FEW and bool(L.lib.cvae_conv_few_eligible(int(Cs), int(Cd), int(k), int(stride), int(pad), int(mode),
+                                                      int(N), int(Hs), int(Ws), int(Hd), int(Wd), int(epi)))
+
+
 def pack_weight(w, A, A_pad, B, taps, src_bat, src_ld, tc=False):
     if tc:
         out = empty(L.lib.cvae_tc_pack_floats(A_pad, B, taps), like=w)

@@ -116,6 +116,14 @@ int cvae_wgrad_reduce(const float* partial, int splits, int taps, int ca, int ca
 int cvae_pack_weight(const float* src, float* dst, int A, int A_pad, int B, int taps, int src_bat,
                      int src_ld, cvae_stream_t s);
 
+/* 1 when cvae_conv_gather runs the layer on the few-channel fp32 tile kernels (image-sized 16 -> 16
+ * channel 3x3 stride-2 layers: the decoder's last ConvTranspose2d, vit_backbone.py:146-150, and its
+ * input gradient).  Callers that would otherwise take the tensor-core entry point must not: at
+ * K = N = 16 the fp32 FMA pipes out-run 3xTF32 tcgen05 (csrc/conv_few.cu).  `wt` is the fp32
+ * cvae_pack_weight layout. */
+int cvae_conv_few_eligible(int Cs, int Cd, int k, int stride, int pad, int mode, int N, int Hs, int Ws,
+                           int Hd, int Wd, int epi);
+
 /* ---- tensor-core (tcgen05 / TMEM, 3xTF32) variant of the gather family ----------------------------
  * Same contract and parameter block as cvae_conv_gather, for layers with Cs % 16 == 0 and
  * Cd % 16 == 0 (the GEMM-shaped ones: vit_backbone.py:74-90 stem.3..12, :124-156 decoder.0..15 and

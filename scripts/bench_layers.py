@@ -104,14 +104,14 @@ def main():
             Mb = N * (Hs // st) * (Ws // st)
             flops = 2.0 * N * Hd * Wd * Ci * Co * taps
         # ---- forward (BN+LReLU of the producer on load, statistics epilogue) ----
-        tcf = ops.tc_eligible(Ci, Co, Mf)
+        epi_f = L.EPI_STATS if Co > 1 else L.EPI_PLAIN      # the image head feeds the loss directly (no BatchNorm)
+        tcf = ops.tc_eligible(Ci, Co, Mf) and not ops.few_eligible(Ci, Co, k, st, pad, mode_f, N, Hs, Ws, Hd, Wd, epi_f)
         if kind == "convT":
             wt_f = ops.pack_weight(w, Ci, Ci, Co, taps, False, Co, tc=tcf)
         else:
             wt_f = ops.pack_weight(w, Ci, Ci, Co, taps, True, Ci, tc=tcf)
         stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
         in_x = xf if Ci > 1 else ops.IDENT
-        epi_f = L.EPI_STATS if Co > 1 else L.EPI_PLAIN      # the image head feeds the loss directly (no BatchNorm)
         fwd = lambda: ops.conv_gather(x, wt_f, None, (Hd, Wd, Co), k, st, pad, mode_f, in_x=in_x, epi=epi_f,
                                       stats=stats if Co > 1 else None, tc=tcf)
         ms = timeit(fwd, once, flush)
@@ -120,7 +120,7 @@ def main():
         tot += ms
         # ---- input gradient (DACT epilogue: reads the producer's raw output) ----
         if Ci > 1:
-            tcb = ops.tc_eligible(Co, Ci, Mb)
+            tcb = ops.tc_eligible(Co, Ci, Mb) and not ops.few_eligible(Co, Ci, k, st, pad, mode_b, N, Hd, Wd, Hs, Ws, L.EPI_DACT)
             if kind == "convT":
                 wt_b = ops.pack_weight(w, Co, Co, Ci, taps, True, Co, tc=tcb)
             else:

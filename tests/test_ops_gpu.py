@@ -90,6 +90,8 @@ CONV_CASES = [
     (32, 64, 4, 2, 1, 14, 14, 3),     # mnist / cascade 4x4 s2
     (1, 32, 4, 2, 1, 28, 28, 2),
     (128, 256, 3, 2, 1, 8, 8, 5),
+    (16, 16, 3, 2, 1, 256, 256, 4),   # image-sized 16 -> 16 stride 2: fp32 tile kernel (conv_few.cu)
+    (16, 16, 3, 2, 1, 200, 144, 10),  # the same with ragged tiles
 ]
 
 
@@ -107,6 +109,8 @@ CONVT_CASES = [
     (256, 128, 3, 2, 1, 1, 4, 4, 3),
     (32, 16, 3, 2, 1, 1, 16, 12, 2),
     (16, 16, 3, 2, 1, 1, 16, 16, 2),
+    (16, 16, 3, 2, 1, 1, 128, 128, 4),   # decoder.12 at image size: fp32 tile kernels (conv_few.cu), fwd + input gradient
+    (16, 16, 3, 2, 1, 1, 100, 72, 10),   # the same with ragged tiles
     (64, 32, 4, 2, 1, 0, 7, 7, 3),    # mnist dec_conv.0
     (32, 1, 4, 2, 1, 0, 14, 14, 3),   # mnist dec_conv.2 (Cout = 1)
 ]
@@ -163,6 +167,32 @@ def test_decoder_like_chain_train():
         h = O._resblock(P, "3", h, True)
         h = lr(O._bn(P, "5", O._convT(P, "4", h, 2, 1, 1), True), 0.01)
         return O._conv(P, "7", h, 1, 1)
+    run_pair(seq, sd, ref, x)
+
+
+def test_image_sized_16_channel_tail_train():
+    """ConvT(32->16)-BN-LReLU -> ConvT(16->16)-BN-LReLU -> Conv(16->1) at a size where the 16 -> 16 layer runs
+    on the few-channel tile kernels: BatchNorm + LeakyReLU applied while staging, statistics epilogue
+    (forward), activation-derivative + BN-backward sums epilogue (input gradient)."""
+    from causal_vae_b200 import nn
+    seq = nn.Sequential(nn.ConvTranspose2d(32, 16, 3, 2, 1, 1), nn.BatchNorm2d(16), nn.LeakyReLU(),
+                        nn.ConvTranspose2d(16, 16, 3, 2, 1, 1), nn.BatchNorm2d(16), nn.LeakyReLU(),
+                        nn.Conv2d(16, 1, 3, padding=1))
+    sd = O.fill_state_dict({k: tuple(v.shape) for k, v in seq.state_dict().items()}, seed=31)
+    # 4.2 M activations per BatchNorm: with generic affine parameters one or two pre-activations land
+    # within fp32 rounding of the LeakyReLU kink and flip a derivative (see DESIGN.md section 2), which moves
+    # sum-type gradients by ~1e-3 whatever kernel computes them.  Keep every pre-activation at least 2
+    # away from the kink - gamma in [0.5, 1], beta = +-8 alternating, so both branches are exercised:
+    for bn in ("1", "4"):
+        sd[f"{bn}.weight"] = torch.linspace(0.5, 1.0, 16)
+        sd[f"{bn}.bias"] = torch.tensor([8.0, -8.0] * 8)
+    x = gen(16, 32, 32, 32, seed=32)
+
+    def ref(P, xx):
+        lr = torch.nn.functional.leaky_relu
+        h = lr(O._bn(P, "1", O._convT(P, "0", xx, 2, 1, 1), True), 0.01)
+        h = lr(O._bn(P, "4", O._convT(P, "3", h, 2, 1, 1), True), 0.01)
+        return O._conv(P, "6", h, 1, 1)
     run_pair(seq, sd, ref, x)
 
 

@@ -51,6 +51,11 @@ GATHER_CASES = [
     (2, 32, 32, 64, 64, 3, 1, 1, 0, False, "dact"),      # input-gradient epilogue with residual add
     (2, 16, 16, 128, 64, 3, 2, 1, 1, False, "dact"),     # conv dgrad (scatter) with DACT
     (1, 1, 1500, 512, 768, 1, 1, 0, 0, False, "plain"),  # N = 768 -> 3 tiles of 256, ragged rows
+    # image-sized 16 -> 16 stride-2 layers: the "simt" arm runs the fp32 tile kernels of conv_few.cu
+    (4, 128, 128, 16, 16, 3, 2, 1, 1, True, "stats"),    # decoder.12 forward: BN+LReLU on load, statistics
+    (10, 100, 72, 16, 16, 3, 2, 1, 1, False, "plain"),   # ragged tiles
+    (4, 256, 256, 16, 16, 3, 2, 1, 0, False, "dact"),    # decoder.12 input gradient: act' + BN-backward sums
+    (10, 200, 144, 16, 16, 3, 2, 1, 0, True, "stats"),   # stride-2 conv forward, ragged tiles
 ]
 
 
