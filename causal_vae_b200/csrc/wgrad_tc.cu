@@ -13,6 +13,7 @@
 //   * one thread issues, per 8 pixels, main += Ahi*Bhi and cross += Alo*Bhi + Ahi*Blo (separate
 //     accumulators: the tensor core truncates on accumulate, so the 2^-11-scaled cross terms must
 //     not share the long main chain); the epilogue adds them and writes the split-K partial tile.
+#include <cstdlib>
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
@@ -25,41 +26,103 @@ constexpr int kWgThreads = 13 * 32;   // 8 A warps + 4 B warps + 1 MMA warp
 constexpr int kWgStages = 4;
 constexpr int kWgKPix = 32;           // pixels (K) per stage
 
-// A-operand loaders: 32 consecutive pixels of one (tap, channel) row into registers; bit p of the
+// A-operand loaders: NP consecutive pixels of one (tap, channel) row into registers; bit p of the
 // returned mask is set where the value is real data (padding / out-of-range pixels stay exactly 0).
-// wg_load_seg: the stage is made of 32/SEG whole output-row segments (Wq % SEG == 0, stages start on
-// multiples of 32 pixels), so row / image coordinates and the vertical bound are computed once per
-// segment instead of once per pixel (the per-pixel form, ~25 instructions per value, made this
+// wg_load_seg: the run is made of whole output-row segments of min(SEG, NP) pixels (Wq % SEG == 0, runs
+// start on multiples of NP pixels), so row / image coordinates and the vertical bound are computed once
+// per segment instead of once per pixel (the per-pixel form, ~25 instructions per value, made this
 // producer the bottleneck of the kernel).  wg_load_lin: 1x1 / Linear (pixel = row of the matrix).
-template <int SEG>
+template <int SEG, int NP>
 __device__ __forceinline__ uint32_t wg_load_seg(const WgradArgs& a, int kb, int kend, bool row_ok, int dh, int dw, int ca,
-                                                float (&v)[32]) {
+                                                float (&v)[NP]) {
+  constexpr int L = SEG < NP ? SEG : NP;
   uint32_t okm = 0;
 #pragma unroll
-  for (int sg = 0; sg < 32 / SEG; ++sg) {
-    const int pixs = kb + sg * SEG;
+  for (int sg = 0; sg < NP / L; ++sg) {
+    const int pixs = kb + sg * L;
     const int qw0 = pixs % a.Wq, t = pixs / a.Wq, qh = t % a.Hq, n = t / a.Hq;
     const int ih = qh * a.stride + dh;
     const bool hok = row_ok && pixs < kend && (unsigned)ih < (unsigned)a.Ha;
     const float* rowp = a.ga + (((size_t)n * a.Ha + (hok ? ih : 0)) * a.Wa) * a.Ca + ca;
     int iw = qw0 * a.stride + dw;
 #pragma unroll
-    for (int j = 0; j < SEG; ++j) {
+    for (int j = 0; j < L; ++j) {
       const bool ok = hok && (unsigned)iw < (unsigned)a.Wa;
-      v[sg * SEG + j] = 0.f;
-      if (ok) { v[sg * SEG + j] = __ldg(rowp + (size_t)iw * a.Ca); okm |= 1u << (sg * SEG + j); }
+      v[sg * L + j] = 0.f;
+      if (ok) { v[sg * L + j] = __ldg(rowp + (size_t)iw * a.Ca); okm |= 1u << (sg * L + j); }
       iw += a.stride;
     }
   }
   return okm;
 }
-__device__ __forceinline__ uint32_t wg_load_lin(const WgradArgs& a, int kb, int kend, bool row_ok, int ca, float (&v)[32]) {
+template <int NP>
+__device__ __forceinline__ uint32_t wg_load_lin(const WgradArgs& a, int kb, int kend, bool row_ok, int ca, float (&v)[NP]) {
   uint32_t okm = 0;
   const float* src = a.ga + (size_t)kb * a.Ca + ca;
 #pragma unroll
-  for (int p = 0; p < 32; ++p) {
+  for (int p = 0; p < NP; ++p) {
     v[p] = 0.f;
     if (row_ok && kb + p < kend) { v[p] = __ldg(src + (size_t)p * a.Ca); okm |= 1u << p; }
+  }
+  return okm;
+}
+template <int NP>
+__device__ __forceinline__ uint32_t wg_load_any(const WgradArgs& a, int kb, int kend, bool row_ok, int dh, int dw, int ca,
+                                                float (&v)[NP]) {
+  if (a.seg == 32) return wg_load_seg<32, NP>(a, kb, kend, row_ok, dh, dw, ca, v);
+  if (a.seg == 16) return wg_load_seg<16, NP>(a, kb, kend, row_ok, dh, dw, ca, v);
+  if (a.seg == 8) return wg_load_seg<8, NP>(a, kb, kend, row_ok, dh, dw, ca, v);
+  if (a.seg == -1) return wg_load_lin<NP>(a, kb, kend, row_ok, ca, v);
+  uint32_t okm = 0;
+  int qw = kb % a.Wq, t = kb / a.Wq, qh = t % a.Hq, n = t / a.Hq;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int ih = qh * a.stride + dh, iw = qw * a.stride + dw;
+    const bool ok = row_ok && (kb + p) < kend && (unsigned)ih < (unsigned)a.Ha && (unsigned)iw < (unsigned)a.Wa;
+    v[p] = 0.f;
+    if (ok) {
+      v[p] = __ldg(a.ga + (((size_t)n * a.Ha + ih) * a.Wa + iw) * a.Ca + ca);
+      okm |= 1u << p;
+    }
+    if (++qw == a.Wq) { qw = 0; if (++qh == a.Hq) { qh = 0; ++n; } }
+  }
+  return okm;
+}
+
+// Stateful loader for the segment modes: the position (output column / row / image) of the NEXT run is
+// carried along and advanced incrementally (the div / mod form cost ~100 instructions per 16 pixels), and a
+// run that lies inside the input row is loaded with unpredicated strided loads (the predicated form spent
+// ~15 instructions per value on bounds, mask and 64-bit address arithmetic - ncu, profiles/).
+struct WgPos { int pix, qw, qh, n; };
+__device__ __forceinline__ void wg_advance(WgPos& p, int d, int Wq, int Hq) {
+  p.pix += d; p.qw += d;
+  while (p.qw >= Wq) { p.qw -= Wq; if (++p.qh == Hq) { p.qh = 0; ++p.n; } }
+}
+template <int L>
+__device__ __forceinline__ uint32_t wg_load_run(const WgradArgs& a, const WgPos& p, int kend, bool row_ok, int dh, int dw,
+                                                int ca, float* v) {
+  const int ih = p.qh * a.stride + dh;
+  const bool hok = row_ok && p.pix < kend && (unsigned)ih < (unsigned)a.Ha;
+  const int iw0 = p.qw * a.stride + dw;
+  if (!hok) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) v[j] = 0.f;
+    return 0u;
+  }
+  const float* ptr = a.ga + (((long long)p.n * a.Ha + ih) * a.Wa + iw0) * a.Ca + ca;   // dereferenced only where valid
+  const long long step = (long long)a.stride * a.Ca;
+  if (iw0 >= 0 && iw0 + (L - 1) * a.stride < a.Wa) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) v[j] = __ldg(ptr + j * step);
+    return L == 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+  }
+  uint32_t okm = 0;
+  int iw = iw0;
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    v[j] = 0.f;
+    if ((unsigned)iw < (unsigned)a.Wa) { v[j] = __ldg(ptr + j * step); okm |= 1u << j; }
+    iw += a.stride;
   }
   return okm;
 }
@@ -110,49 +173,76 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       if (a.a_center != nullptr) ce = __ldg(a.a_center + ca);
     }
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    for (int st = par; st < nst; st += 2) {
-      const int slot = st % kWgStages;
-      const int kb = kbeg + st * kWgKPix;
-      float v[kWgKPix];
-      uint32_t okm = 0;                          // padding / out-of-range pixels stay exactly 0
-      if (a.seg == 32) okm = wg_load_seg<32>(a, kb, kend, row_ok, dh, dw, ca, v);
-      else if (a.seg == 16) okm = wg_load_seg<16>(a, kb, kend, row_ok, dh, dw, ca, v);
-      else if (a.seg == 8) okm = wg_load_seg<8>(a, kb, kend, row_ok, dh, dw, ca, v);
-      else if (a.seg == -1) okm = wg_load_lin(a, kb, kend, row_ok, ca, v);
-      else {
-        int qw = kb % a.Wq, t = kb / a.Wq, qh = t % a.Hq, n = t / a.Hq;
+    // Software pipeline over HALF stages (16 pixels): while one half is transformed, split into tf32
+    // hi / lo and stored to tensor memory, the loads of the next two halves are in flight (ncu: 42 % of
+    // the stall samples of the unpipelined loop sat on the first use of the loaded values).  Three
+    // 16-value buffers + one 16-value store staging array = the register budget of the old 32 + 32.
+    constexpr int kH = kWgKPix / 2;
+    const int nmine = nst > par ? (nst - par + 1) / 2 : 0;      // stages par, par + 2, ...
+    const int nh = 2 * nmine;
+    WgPos pos;                                   // position of the next half to load (segment modes)
+    pos.pix = kbeg + par * kWgKPix;
+    pos.qw = pos.pix % a.Wq; { const int t = pos.pix / a.Wq; pos.qh = t % a.Hq; pos.n = t / a.Hq; }
+    auto load_half = [&](int u, float (&v)[kH]) -> uint32_t {
+      uint32_t m = 0;
+      if (a.seg >= 16) {                         // one 16-pixel run inside an output row
+        m = wg_load_run<16>(a, pos, kend, row_ok, dh, dw, ca, v);
+        wg_advance(pos, (u & 1) ? 16 + kWgKPix : 16, a.Wq, a.Hq);
+      } else if (a.seg == 8) {                   // two runs of 8 (8-wide feature maps)
+        m = wg_load_run<8>(a, pos, kend, row_ok, dh, dw, ca, v);
+        wg_advance(pos, 8, a.Wq, a.Hq);
+        m |= wg_load_run<8>(a, pos, kend, row_ok, dh, dw, ca, v + 8) << 8;
+        wg_advance(pos, (u & 1) ? 8 + kWgKPix : 8, a.Wq, a.Hq);
+      } else {
+        const int kb = kbeg + (par + 2 * (u >> 1)) * kWgKPix + (u & 1) * kH;
+        m = wg_load_any<kH>(a, kb, kend, row_ok, dh, dw, ca, v);
+      }
+      return m;
+    };
+    float b0[kH], b1[kH], b2[kH];
+    uint32_t m0 = 0, m1 = 0, m2 = 0;
+    if (nh > 0) m0 = load_half(0, b0);
+    if (nh > 1) m1 = load_half(1, b1);
+    for (int u = 0; u < nh; ++u) {
+      if (u + 2 < nh) m2 = load_half(u + 2, b2);
+      const int st = par + 2 * (u >> 1), slot = st % kWgStages, h = (u & 1) * kH;
+      if (m0 == 0xFFFFu) {                       // interior run (warp-uniform when Ca % 32 == 0)
 #pragma unroll
-        for (int p = 0; p < kWgKPix; ++p) {
-          const int ih = qh * a.stride + dh, iw = qw * a.stride + dw;
-          const bool ok = row_ok && (kb + p) < kend && (unsigned)ih < (unsigned)a.Ha && (unsigned)iw < (unsigned)a.Wa;
-          v[p] = 0.f;
-          if (ok) {
-            v[p] = __ldg(a.ga + (((size_t)n * a.Ha + ih) * a.Wa + iw) * a.Ca + ca);
-            okm |= 1u << p;
+        for (int p = 0; p < kH; ++p) {
+          if (a.a_affine) b0[p] = fmaf(b0[p] - ce, sc, sh);
+          if (a.a_act) b0[p] = lrelu(b0[p], a.a_slope);
+        }
+      } else if (m0 != 0u) {
+#pragma unroll
+        for (int p = 0; p < kH; ++p) {
+          if ((m0 >> p) & 1u) {                  // padding stays exactly 0
+            if (a.a_affine) b0[p] = fmaf(b0[p] - ce, sc, sh);
+            if (a.a_act) b0[p] = lrelu(b0[p], a.a_slope);
           }
-          if (++qw == a.Wq) { qw = 0; if (++qh == a.Hq) { qh = 0; ++n; } }
         }
       }
-      uint32_t hi[kWgKPix];
+      if ((u & 1) == 0) {
+        mbar_wait(smem_u32(&s_empty[slot]), (uint32_t)(((st / kWgStages) & 1) ^ 1));
+        tc_fence_after();
+      }
+      uint32_t t16[kH];
 #pragma unroll
-      for (int p = 0; p < kWgKPix; ++p) {
-        float x = v[p];
-        if ((okm >> p) & 1u) {
-          if (a.a_affine) x = fmaf(x - ce, sc, sh);
-          if (a.a_act) x = lrelu(x, a.a_slope);
-        }
-        const float h = tf32_rn(x);
-        hi[p] = __float_as_uint(h);
-        v[p] = tf32_rn(x - h);
+      for (int p = 0; p < kH; ++p) {
+        const float hi = tf32_rn(b0[p]);
+        t16[p] = __float_as_uint(hi);
+        b0[p] = tf32_rn(b0[p] - hi);
       }
-      mbar_wait(smem_u32(&s_empty[slot]), (uint32_t)(((st / kWgStages) & 1) ^ 1));
-      tc_fence_after();
-      tmem_st32(t_a + lane_sel + (uint32_t)(slot * 64), hi);
-      tmem_st32(t_a + lane_sel + (uint32_t)(slot * 64 + 32), reinterpret_cast<const uint32_t*>(v));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_full[slot]));
+      tmem_st16(t_a + lane_sel + (uint32_t)(slot * 64 + h), t16);
+      tmem_st16(t_a + lane_sel + (uint32_t)(slot * 64 + 32 + h), reinterpret_cast<const uint32_t*>(b0));
+      if (u & 1) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_full[slot]));
+      }
+#pragma unroll
+      for (int p = 0; p < kH; ++p) { b0[p] = b1[p]; b1[p] = b2[p]; }
+      m0 = m1; m1 = m2;
     }
 
     // ============================== epilogue: main + cross -> partial tile ==============================
@@ -286,10 +376,23 @@ extern "C" int cvae_wgrad_tc_splits(int pixels, int rows, int Cb) {
   const int bn = wg_pick_bn(Cb);
   if (bn == 0) return 1;
   const int tiles = ((rows + 127) / 128) * (Cb / bn);
-  int splits = (2 * kNumSMs + tiles - 1) / tiles;
-  splits = max(splits, (pixels + 4095) / 4096);
-  splits = min(splits, max(1, pixels / 256));
-  return max(1, min(splits, 4096));
+  // One CTA per SM: the grid runs in waves of 148, so 300 CTAs cost three waves (ncu: grid (5,1,60) ran
+  // 2 full waves + 4 CTAs).  Pick the split count that minimises waves x (stages per CTA + fixed
+  // prologue / epilogue cost) within [pixels / 4096, pixels / 256].
+  const int smin = max(1, (pixels + 4095) / 4096), smax = max(smin, min(4096, pixels / 256));
+  if (const char* e = getenv("CVAE_WG_SPLITS")) {            // tuning hook (scripts/bench_layers.py sweeps)
+    const int v = atoi(e);
+    if (v > 0) return max(smin, min(smax, v));
+  }
+  int best = smin;
+  long long best_cost = -1;
+  for (int sp = smin; sp <= smax; ++sp) {
+    const long long waves = ((long long)tiles * sp + kNumSMs - 1) / kNumSMs;
+    const long long stages = ((pixels + sp - 1) / sp + kWgKPix - 1) / kWgKPix + 8;   // + ~8 stages of fixed cost
+    const long long cost = waves * stages;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+  }
+  return best;
 }
 
 extern "C" int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s) {
