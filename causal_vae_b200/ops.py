@@ -94,7 +94,67 @@ def few_eligible(Cs, Cd, k, stride, pad, mode, N, Hs, Ws, Hd, Wd, epi):
                                                       int(N), int(Hs), int(Ws), int(Hd), int(Wd), int(epi)))
 
 
+class PackPlan:
+    """Weight packings of a training step, recorded once and replayed as ONE launch (csrc/pack_batch.cu).
+
+    While `recording`, pack_weight() packs as usual into a buffer the plan keeps and notes the job;
+    finalize() uploads the job table.  Afterwards run() re-packs every recorded weight from its current
+    values in one grid (call it before the forward pass, after the optimizer changed the weights) and
+    pack_weight() just returns the kept buffers.  A request the plan has not seen falls back to a
+    per-use pack, so a change of batch size or control flow stays correct."""
+
+    def __init__(self):
+        self.entries, self.jobs, self.recording = {}, [], True
+        self.table, self.nblocks = None, 0
+
+    @staticmethod
+    def key(w, A, A_pad, B, taps, src_bat, src_ld, tc):
+        return (w.data_ptr(), int(A), int(A_pad), int(B), int(taps), int(src_bat), int(src_ld), bool(tc))
+
+    def finalize(self):
+        import numpy as np
+        self.recording = False
+        if not self.jobs:
+            return
+        dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("A", "<i4"), ("A_pad", "<i4"), ("B", "<i4"), ("taps", "<i4"),
+                       ("src_bat", "<i4"), ("src_ld", "<i4"), ("tc", "<i4"), ("block0", "<i4")])
+        arr = np.zeros(len(self.jobs), dtype=dt)
+        b0 = 0
+        for i, (w, out, (_, A, A_pad, B, taps, src_bat, src_ld, tc)) in enumerate(self.jobs):
+            arr[i] = (w.data_ptr(), out.data_ptr(), A, A_pad, B, taps, src_bat, src_ld, int(tc), b0)
+            b0 += int(L.lib.cvae_pack_batch_blocks(A_pad, B, taps, int(tc)))
+        self.nblocks = b0
+        dev = self.jobs[0][1].device
+        self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+
+    def run(self):
+        if self.table is not None:
+            L.check(L.lib.cvae_pack_batch(L.ptr(self.table), len(self.jobs), self.nblocks, L.stream()), "pack_batch")
+
+
+_PLAN = [None]
+
+
+def set_pack_plan(plan):
+    _PLAN[0] = plan
+
+
 def pack_weight(w, A, A_pad, B, taps, src_bat, src_ld, tc=False):
+    plan = _PLAN[0]
+    if plan is not None:
+        k = PackPlan.key(w, A, A_pad, B, taps, src_bat, src_ld, tc)
+        hit = plan.entries.get(k)
+        if hit is not None:
+            return hit
+        if plan.recording:
+            out = _pack_weight_now(w, A, A_pad, B, taps, src_bat, src_ld, tc)
+            plan.entries[k] = out
+            plan.jobs.append((w, out, k))
+            return out
+    return _pack_weight_now(w, A, A_pad, B, taps, src_bat, src_ld, tc)
+
+
+def _pack_weight_now(w, A, A_pad, B, taps, src_bat, src_ld, tc=False):
     if tc:
         out = empty(L.lib.cvae_tc_pack_floats(A_pad, B, taps), like=w)
         L.check(L.lib.cvae_tc_pack_weight(L.ptr(w), L.ptr(out), A, A_pad, B, taps, int(src_bat), src_ld, L.stream()),

@@ -43,11 +43,15 @@ class VesselTrainer:
         self.distributed, self.pg = distributed, process_group
         self.graph = None
         self.static = None
+        self.pack_plan = ops.PackPlan()
         F.set_rng_counter(self.opt.step_count)
 
     def _fwd_bwd(self, x, m, t, eps):
         self.opt.zero_grad()
         ops.arena_begin(self.flat.data.device)
+        ops.set_pack_plan(self.pack_plan)
+        if not self.pack_plan.recording:
+            self.pack_plan.run()          # every weight layout of the step, one launch
         try:
             out = self.model(x, m, t, eps)
             recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
@@ -56,6 +60,9 @@ class VesselTrainer:
                 loss.backward()
         finally:
             ops.arena_end()
+            ops.set_pack_plan(None)
+        if self.pack_plan.recording:
+            self.pack_plan.finalize()
         return loss, recon, kld, morph, sp
 
     def _allreduce(self):

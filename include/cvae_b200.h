@@ -124,6 +124,17 @@ int cvae_pack_weight(const float* src, float* dst, int A, int A_pad, int B, int 
 int cvae_conv_few_eligible(int Cs, int Cd, int k, int stride, int pad, int mode, int N, int Hs, int Ws,
                            int Hd, int Wd, int epi);
 
+/* Batched weight packing: every cvae_pack_weight / cvae_tc_pack_weight call of a training step as one
+ * launch.  `jobs_dev` is a DEVICE array sorted by block0 (job i owns blocks [block0_i, block0_{i+1}),
+ * cvae_pack_batch_blocks(...) blocks each); tc != 0 selects the tensor-core layout.  The reference
+ * has no counterpart: its weights are consumed in torch layout by cuDNN / cuBLAS. */
+typedef struct {
+  const float* src; float* dst;
+  int32_t A, A_pad, B, taps, src_bat, src_ld, tc, block0;
+} cvae_pack_job_t;
+int cvae_pack_batch_blocks(int A_pad, int B, int taps, int tc);
+int cvae_pack_batch(const cvae_pack_job_t* jobs_dev, int njobs, int nblocks, cvae_stream_t s);
+
 /* ---- tensor-core (tcgen05 / TMEM, 3xTF32) variant of the gather family ----------------------------
  * Same contract and parameter block as cvae_conv_gather, for layers with Cs % 16 == 0 and
  * Cd % 16 == 0 (the GEMM-shaped ones: vit_backbone.py:74-90 stem.3..12, :124-156 decoder.0..15 and

@@ -248,7 +248,7 @@ TILE_WGRAD_CASES = [
     (8, 128, 128, 16, 16, 2, False, True),     # decoder ConvT 16->16: ga = dL/dout, db = layer input (BN+LReLU on load)
     (8, 128, 128, 16, 32, 2, False, True),     # decoder ConvT 32->16
     (8, 64, 64, 32, 32, 1, True, False),       # ResBlock(32)
-    (8, 128, 128, 32, 64, 2, True, False),     # stem.3 32->64 (two cb slices)
+    (8, 128, 128, 32, 64, 2, True, False),     # stem.3 32->64: 64 columns -> pipelined tensor-core kernel (wgrad_tc.cu)
     (2, 256, 256, 16, 1, 1, True, False),      # image head 16->1
     (8, 128, 128, 1, 32, 2, False, False),     # stem.0 1->32
     (3, 131, 127, 16, 16, 1, True, True),      # ragged patches (edge tiles partly outside the image)
@@ -262,7 +262,8 @@ def test_tiled_wgrad_vs_simt_and_fp64(case):
     N, Ha, Wa, Ca, Cb, stride, xfa, xfb = case
     k, pad = 3, 1
     Hq, Wq = (Ha + 2 * pad - k) // stride + 1, (Wa + 2 * pad - k) // stride + 1
-    assert L.lib.cvae_wgrad_tile_splits(N * Hq * Wq, Ca, Cb, k, stride, pad) > 0
+    tiled = L.lib.cvae_wgrad_tile_splits(N * Hq * Wq, Ca, Cb, k, stride, pad) > 0
+    assert tiled == (not (Cb == 64 and Ca >= 16))      # default dispatch: tile kernel, except 64-column layers
     ga = gen(N, Ha, Wa, Ca, seed=1).cuda()
     db = gen(N, Hq, Wq, Cb, seed=2).cuda()
     xa, xb, ra, rb = ops.IDENT, ops.IDENT, None, None
