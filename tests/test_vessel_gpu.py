@@ -62,6 +62,14 @@ def test_eval_forward_and_counterfactual(cfg):
         want = (xcf - ref[0]).flatten(1).norm(dim=1)
         assert rel(l2[:, k], want) <= 1e-4
     assert rel(l2[:, 5], torch.tensor(gold["eval"]["cf_l2_per_sample"])) <= 1e-4
+    # the graph-captured engine (static buffers, weight layouts packed once) gives the same effect sizes
+    eng = CF.CounterfactualEngine(model, B, delta=5.0)
+    for _ in range(2):
+        l2_g = eng(m.cuda(), z.cuda().float())
+    assert rel(l2_g, l2) <= 1e-6, rel(l2_g, l2)
+    l2_h = eng(m.cuda() * 0.5, z.cuda().float())          # different inputs through the same graph
+    l2_e, _, _ = CF.counterfactual_sweep(model, m.cuda() * 0.5, z.cuda().float(), delta=5.0)
+    assert rel(l2_h, l2_e) <= 1e-6
 
 
 @pytest.mark.parametrize("cfg", [(64, 64, 4), (128, 96, 8), (256, 256, 8)])
