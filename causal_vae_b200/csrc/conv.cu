@@ -632,6 +632,11 @@ extern "C" int cvae_conv_gather(const cvae_conv_params_t* p, cvae_stream_t s) {
     if (fr < 0) return fr;
     if (fr == 1) { CVAE_LAUNCH_CHECK(); return CVAE_OK; }
   }
+  {  // Linear layers with a handful of rows: N x K split kernels (linear_small.cu)
+    const int lr = launch_linear_small(g, st);
+    if (lr < 0) return lr;
+    if (lr == 1) { CVAE_LAUNCH_CHECK(); return CVAE_OK; }
+  }
   const bool tiled_ok = (p->Cs % 4 == 0) && (p->Cd % 4 == 0) && p->Cs >= 8 && p->Cd >= 8;
   if (tiled_ok) {
     const int gx = (maxM + 127) / 128;
@@ -707,6 +712,10 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_params_t* p, cvae_stream_t s) {
   chunk = ((chunk + 15) / 16) * 16;
   a.kchunk = chunk;
   cudaStream_t st = as_stream(s);
+  if (launch_wgrad_small(a, p->kh * p->kw, p->splits, st) == 1) {
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+  }
   if (p->splits == 1 && (launch_wgrad_cb1(a, p->kh * p->kw, st) || launch_wgrad_ca1(a, p->kh * p->kw, st))) {
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;

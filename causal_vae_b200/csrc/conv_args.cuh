@@ -37,4 +37,8 @@ bool launch_wgrad_ca1(const WgradArgs& a, int taps, cudaStream_t st);   // Ca ==
 // conv_few.cu: image-sized 16 -> 16 stride-2 layers.  1: launched, 0: not covered, < 0: error.
 int launch_conv_few(const cvae_conv_params_t* p, const GatherArgs& g, cudaStream_t st);
 
+// linear_small.cu: Linear layers / weight gradients with M <= 128 rows.  1: launched, 0: not covered, < 0: error.
+int launch_linear_small(const GatherArgs& g, cudaStream_t st);
+int launch_wgrad_small(const WgradArgs& a, int taps, int splits, cudaStream_t st);
+
 }  // namespace cvae

@@ -1,0 +1,191 @@
+// Linear layers with a handful of rows (M = batch <= 128): the adapters, the morphology head and
+// decoder_input of CausalViTVAE (vessel_analysis/00_core/models.py:225-250, vit_backbone.py:186-188), and
+// every Linear of the MNIST / cascade models.
+//
+// As [128-row tile] x [64-column tile] implicit GEMMs these ran on 1-8 CTAs with a serial K loop: 15-70 us
+// per launch for a few MFLOP (ncu launch list, profiles/), ~0.7 ms of the vessel step.  Here the work is cut
+// along N *and* K so that even a 64 x 512 x 256 product fills the GPU:
+//
+//   forward / input gradient:  y[m][n] (+)= sum_{k in chunk} xf(x[m][k]) * w[k][n]
+//     CTA = 32 columns x one 64-deep K chunk x all rows; x chunk staged in shared memory (transform applied),
+//     a lane owns one column (coalesced weight reads), a warp owns M/4 rows (x values are 128-bit shared
+//     broadcasts); K chunks meet in the pre-zeroed output with fp32 atomics.  Bias rides on chunk 0; the
+//     BatchNorm-statistics / activation-derivative epilogues run as a second tiny kernel over the finished
+//     [M, N] matrix.
+//   weight gradient:  P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb])   (one pass, no K split).
+#include "conv_args.cuh"
+
+namespace cvae {
+
+constexpr int kLsKC = 64;        // K chunk per CTA
+constexpr int kLsMaxM = 128;
+
+template <int R>   // rows per warp; M <= 4 R
+__global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant__ GatherArgs a, const int M) {
+  __shared__ __align__(16) float xs[4 * R * kLsKC];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x * 32 + lane, k0 = blockIdx.y * kLsKC;
+  // ---- stage x[:, k0 : k0 + 64] with the producer's BatchNorm + activation applied ----
+  // (unrolled: a CTA's whole life is a few dependent global round trips, so every loop keeps several loads in flight)
+#pragma unroll 8
+  for (int idx = tid; idx < 4 * R * (kLsKC / 4); idx += 128) {
+    const int m = idx / (kLsKC / 4), c4 = idx - m * (kLsKC / 4), k = k0 + c4 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M && k < a.Cs) {
+      v = __ldg(reinterpret_cast<const float4*>(a.src + (size_t)m * a.Cs + k));
+      if (a.in_affine) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + k));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + k));
+        float4 ce = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + k));
+        v.x = fmaf(v.x - ce.x, sc.x, sh.x); v.y = fmaf(v.y - ce.y, sc.y, sh.y);
+        v.z = fmaf(v.z - ce.z, sc.z, sh.z); v.w = fmaf(v.w - ce.w, sc.w, sh.w);
+      }
+      if (a.in_act) { v.x = lrelu(v.x, a.in_slope); v.y = lrelu(v.y, a.in_slope); v.z = lrelu(v.z, a.in_slope); v.w = lrelu(v.w, a.in_slope); }
+    }
+    *reinterpret_cast<float4*>(xs + m * kLsKC + c4 * 4) = v;
+  }
+  __syncthreads();
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  const bool nok = n < a.Cd;
+  const float* wp = a.wt + (size_t)k0 * a.Cd + (nok ? n : 0);
+  const float* xr = xs + warp * R * kLsKC;
+  const int kmax = min(kLsKC, a.Cs - k0);            // Cs % 4 == 0
+#pragma unroll 4
+  for (int kk = 0; kk < kmax; kk += 4) {
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+    if (nok) {
+      w0 = __ldg(wp + (size_t)(kk + 0) * a.Cd); w1 = __ldg(wp + (size_t)(kk + 1) * a.Cd);
+      w2 = __ldg(wp + (size_t)(kk + 2) * a.Cd); w3 = __ldg(wp + (size_t)(kk + 3) * a.Cd);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + r * kLsKC + kk);
+      acc[r] = fmaf(xv.x, w0, fmaf(xv.y, w1, fmaf(xv.z, w2, fmaf(xv.w, w3, acc[r]))));
+    }
+  }
+  if (!nok) return;
+  const float b = (blockIdx.y == 0 && a.bias != nullptr) ? __ldg(a.bias + n) : 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int m = warp * R + r;
+    if (m < M) atomicAdd(a.dst + (size_t)m * a.Cd + n, acc[r] + b);
+  }
+}
+
+// second pass over the finished [M, Cd] matrix: BatchNorm statistics, or activation derivative (+ residual
+// add) with the BN-backward sums.  Block = 32 columns x 4 row groups.
+__global__ void __launch_bounds__(128) linear_small_epi_kernel(const __grid_constant__ GatherArgs a, const int M) {
+  __shared__ double red[2][4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 32 + lane;
+  double s1 = 0.0, s2 = 0.0;
+  if (n < a.Cd) {
+    float esc = 1.f, esh = 0.f, ece = 0.f;
+    if (a.e_affine) { esc = __ldg(a.e_scale + n); esh = __ldg(a.e_shift + n); if (a.e_center) ece = __ldg(a.e_center + n); }
+#pragma unroll 8
+    for (int m = warp; m < M; m += 4) {
+      const size_t o = (size_t)m * a.Cd + n;
+      float x = a.dst[o];
+      if (a.epi == CVAE_EPI_STATS) {
+        s1 += (double)x; s2 += (double)x * (double)x;
+      } else {   // CVAE_EPI_DACT
+        const float refc = __ldg(a.epi_ref + o) - ece;
+        if (a.epi_add != nullptr) x += __ldg(a.epi_add + o);
+        const float z = fmaf(refc, esc, esh);
+        x = z > 0.f ? x : x * a.e_slope;
+        a.dst[o] = x;
+        s1 += (double)x; s2 += (double)x * (double)refc;
+      }
+    }
+  }
+  red[0][warp][lane] = s1; red[1][warp][lane] = s2;
+  __syncthreads();
+  if (warp == 0 && n < a.Cd && a.stats != nullptr) {
+    atomicAdd(a.stats + n, red[0][0][lane] + red[0][1][lane] + red[0][2][lane] + red[0][3][lane]);
+    atomicAdd(a.stats + a.Cd + n, red[1][0][lane] + red[1][1][lane] + red[1][2][lane] + red[1][3][lane]);
+  }
+}
+
+// 1: launched, 0: not covered
+int launch_linear_small(const GatherArgs& g, cudaStream_t st) {
+  if (g.wtaps != 1 || g.nphase != 1 || g.is != 1 || g.os != 1 || g.Hs != g.Hd || g.Ws != g.Wd) return 0;
+  if (g.phase[0].ntaps != 1 || g.phase[0].taps[0].dh != 0 || g.phase[0].taps[0].dw != 0) return 0;
+  const long long M = (long long)g.N * g.Hs * g.Ws;
+  if (M > kLsMaxM || (g.Cs & 3) || g.Cs < 4) return 0;
+  if ((reinterpret_cast<uintptr_t>(g.src) & 15) != 0) return 0;
+  if (g.in_affine && (((reinterpret_cast<uintptr_t>(g.in_scale) | reinterpret_cast<uintptr_t>(g.in_shift)) & 15) != 0 ||
+                      (g.in_center && (reinterpret_cast<uintptr_t>(g.in_center) & 15) != 0))) return 0;
+  if (cudaMemsetAsync(g.dst, 0, sizeof(float) * (size_t)M * g.Cd, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
+  const dim3 grid((g.Cd + 31) / 32, (g.Cs + kLsKC - 1) / kLsKC);
+  if (M <= 16) linear_small_kernel<4><<<grid, 128, 0, st>>>(g, (int)M);
+  else if (M <= 32) linear_small_kernel<8><<<grid, 128, 0, st>>>(g, (int)M);
+  else if (M <= 64) linear_small_kernel<16><<<grid, 128, 0, st>>>(g, (int)M);
+  else linear_small_kernel<32><<<grid, 128, 0, st>>>(g, (int)M);
+  if (g.epi != CVAE_EPI_PLAIN) linear_small_epi_kernel<<<(g.Cd + 31) / 32, 128, 0, st>>>(g, (int)M);
+  return 1;
+}
+
+// ---- weight gradient: P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb]),  m < M <= 128 ----------------------
+// CTA tile 32 (ca) x 64 (cb); thread = 2 ca x 4 cb.
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const __grid_constant__ WgradArgs a, const int M) {
+  __shared__ __align__(16) float As[kLsMaxM * 32];
+  __shared__ __align__(16) float Bs[kLsMaxM * 64];
+  const int tid = threadIdx.x;
+  const int ca0 = blockIdx.x * 32, cb0 = blockIdx.y * 64;
+#pragma unroll 8
+  for (int idx = tid; idx < M * 32; idx += 256) {
+    const int m = idx >> 5, c = ca0 + (idx & 31);
+    float v = 0.f;
+    if (c < a.Ca) {
+      v = __ldg(a.ga + (size_t)m * a.Ca + c);
+      if (a.a_affine) v = fmaf(v - (a.a_center ? __ldg(a.a_center + c) : 0.f), __ldg(a.a_scale + c), __ldg(a.a_shift + c));
+      if (a.a_act) v = lrelu(v, a.a_slope);
+    }
+    As[idx] = v;
+  }
+#pragma unroll 8
+  for (int idx = tid; idx < M * 64; idx += 256) {
+    const int m = idx >> 6, c = cb0 + (idx & 63);
+    float v = 0.f;
+    if (c < a.Cb) {
+      v = __ldg(a.db + (size_t)m * a.Cb + c);
+      if (a.b_affine) v = fmaf(v - (a.b_center ? __ldg(a.b_center + c) : 0.f), __ldg(a.b_scale + c), __ldg(a.b_shift + c));
+      if (a.b_act) v = lrelu(v, a.b_slope);
+    }
+    Bs[idx] = v;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 4
+  for (int m = 0; m < M; ++m) {
+    const float2 av = *reinterpret_cast<const float2*>(As + m * 32 + ty * 2);
+    const float4 bv = *reinterpret_cast<const float4*>(Bs + m * 64 + tx * 4);
+    acc[0][0] = fmaf(av.x, bv.x, acc[0][0]); acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
+    acc[0][2] = fmaf(av.x, bv.z, acc[0][2]); acc[0][3] = fmaf(av.x, bv.w, acc[0][3]);
+    acc[1][0] = fmaf(av.y, bv.x, acc[1][0]); acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
+    acc[1][2] = fmaf(av.y, bv.z, acc[1][2]); acc[1][3] = fmaf(av.y, bv.w, acc[1][3]);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ca = ca0 + ty * 2 + i;
+    if (ca >= a.Ca) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cb = cb0 + tx * 4 + j;
+      if (cb < a.Cb) a.partial[(size_t)ca * a.Cb + cb] = acc[i][j];
+    }
+  }
+}
+
+// 1: launched, 0: not covered.  Requires splits == 1 (the caller's partial buffer is [rows][Cb]).
+int launch_wgrad_small(const WgradArgs& a, int taps, int splits, cudaStream_t st) {
+  if (taps != 1 || splits != 1 || a.K > kLsMaxM || a.K < 1) return 0;
+  wgrad_small_kernel<<<dim3((a.Ca + 31) / 32, (a.Cb + 63) / 64), 256, 0, st>>>(a, a.K);
+  return 1;
+}
+
+}  // namespace cvae
