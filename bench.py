@@ -25,9 +25,10 @@ H = W = 256
 B_PER_GPU = 64
 FLOP_PER_SAMPLE = 5.057e9          # fwd+bwd matmul/conv FLOPs (2*MAC), measured on the reference
 BYTES_PER_SAMPLE = 77e6 + 8.8e6    # irreducible fp32 activation + parameter/optimizer traffic
-# dram__bytes_read.sum + dram__bytes_write.sum of the probed launch (decoder.12 input gradient, B = 64) from the
-# `ncu --set full` capture summarised in profiles/r1_ncu_halo_raw.txt; algorithmic bytes of that launch: 402.7e6
-NCU_TRAFFIC_BYTES = 390.9e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the probed launch (stem.3 input gradient, B = 64) from the
+# `ncu --set full` capture summarised in profiles/r1_ncu_halo_stem3_raw.txt (launch 1: 201.6 MB read + 98.5 MB
+# written); algorithmic bytes of that launch: 335.5e6 (part of the re-read reference tensor is served by L2)
+NCU_TRAFFIC_BYTES = 300.1e6
 
 
 def peaks():
@@ -133,23 +134,25 @@ def _time_launch(torch, fn, reps=10):
 
 
 def dominant_kernel_probe(torch, ops, L):
-    """The dominant kernel of the step is conv_halo_tc_kernel (31 % of the device time in
-    profiles/r1_launches_final_summary.txt).  It is timed live on its two heaviest instances of the
-    vessel step at B = 64, with the operand transform / epilogue each runs with inside the step:
-      * decoder.12 input gradient (ConvT 16->16, 256^2 -> 128^2, stride-2 gather + activation-derivative
-        epilogue): HBM-bound -- algorithmic bytes = dL/dout (268 MB) + dL/din (67 MB) + the producer's raw
-        output re-read by the epilogue (67 MB);
+    """The dominant kernel of the step is conv_halo_tc_kernel (34 % of the device time in
+    profiles/r1_launches_final_summary.txt).  It is timed live on its two heaviest kinds of instance in
+    the vessel step at B = 64, with the operand transform / epilogue each runs with inside the step:
+      * stem.3 input gradient (Conv2d 32->64 s2: scatter of dL/dout 64x64x64 into 128x128x32 with the
+        activation-derivative + BN-backward-sums epilogue) -- its longest launch, HBM-shaped: algorithmic
+        bytes = dL/dout (67 MB) + dL/din (134 MB) + the producer's raw output re-read by the epilogue (134 MB);
       * stem.6 forward (Conv 64->128 s2 @64^2, BatchNorm+LeakyReLU on load, statistics epilogue):
-        tensor-bound -- 9.66 GFLOP algorithmic, 3x that issued as tf32 MMAs."""
+        tensor-bound -- 9.66 GFLOP algorithmic, 3x that issued as tf32 MMAs.
+    A third probe times the fp32 tile kernel that took over the largest tensors of the step (decoder.12
+    forward, ConvTranspose2d 16->16 to 256^2: 67 MB in, 268 MB out), csrc/conv_few.cu."""
     N = B_PER_GPU
-    # ---- HBM-bound instance ----
-    dy = torch.randn(N, 256, 256, 16, device="cuda")
-    ref = torch.randn(N, 128, 128, 16, device="cuda")
-    w = torch.randn(16, 16, 9, device="cuda") * 0.05              # ConvTranspose2d weight [Cin][Cout][taps]
-    wt = ops.pack_weight(w, 16, 16, 16, 9, True, 16, tc=True)
-    esc, esh, ece = (torch.rand(16, device="cuda") + 0.5, torch.randn(16, device="cuda"), torch.randn(16, device="cuda"))
-    st = torch.zeros(32, dtype=torch.float64, device="cuda")
-    hbm_fn = lambda: ops.conv_gather(dy, wt, None, (128, 128, 16), 3, 2, 1, L.MODE_GATHER, epi=L.EPI_DACT, epi_ref=ref,
+    # ---- HBM-shaped instance of the dominant kernel ----
+    dy = torch.randn(N, 64, 64, 64, device="cuda")
+    ref = torch.randn(N, 128, 128, 32, device="cuda")
+    w = torch.randn(64, 32, 9, device="cuda") * 0.05              # Conv2d weight [Cout][Cin][taps]
+    wt = ops.pack_weight(w, 64, 64, 32, 9, False, 32, tc=True)    # input-gradient operand [tap][Cout][Cin]
+    esc, esh, ece = (torch.rand(32, device="cuda") + 0.5, torch.randn(32, device="cuda"), torch.randn(32, device="cuda"))
+    st = torch.zeros(64, dtype=torch.float64, device="cuda")
+    hbm_fn = lambda: ops.conv_gather(dy, wt, None, (128, 128, 32), 3, 2, 1, L.MODE_SCATTER, epi=L.EPI_DACT, epi_ref=ref,
                                      epi_x=ops.XF(esc, esh, 0.01, ece), stats=st, tc=True)
     ms_h = _time_launch(torch, hbm_fn)
     bytes_h = 4.0 * (dy.numel() + 2 * ref.numel())
@@ -164,7 +167,18 @@ def dominant_kernel_probe(torch, ops, L):
                                     epi=L.EPI_STATS, stats=st2, tc=True)
     ms_t = _time_launch(torch, tc_fn)
     flops_t = 2.0 * N * 32 * 32 * 64 * 128 * 9
-    return {"hbm_ms": ms_h, "hbm_bytes": bytes_h, "tc_ms": ms_t, "tc_flops": flops_t}
+    del x
+    # ---- fp32 tile kernel on the largest tensors of the step ----
+    x3 = torch.randn(N, 128, 128, 16, device="cuda")
+    w3 = torch.randn(16, 16, 9, device="cuda") * 0.05             # ConvTranspose2d weight [Cin][Cout][taps]
+    wt3 = ops.pack_weight(w3, 16, 16, 16, 9, False, 16)           # fp32 [tap][Cin][Cout]
+    sc3, sh3, ce3 = (torch.rand(16, device="cuda") + 0.5, torch.randn(16, device="cuda"), torch.randn(16, device="cuda"))
+    st3 = torch.zeros(32, dtype=torch.float64, device="cuda")
+    few_fn = lambda: ops.conv_gather(x3, wt3, None, (256, 256, 16), 3, 2, 1, L.MODE_SCATTER, in_x=ops.XF(sc3, sh3, 0.01, ce3),
+                                     epi=L.EPI_STATS, stats=st3)
+    ms_f = _time_launch(torch, few_fn)
+    bytes_f = 4.0 * (x3.numel() + N * 256 * 256 * 16)
+    return {"hbm_ms": ms_h, "hbm_bytes": bytes_h, "tc_ms": ms_t, "tc_flops": flops_t, "few_ms": ms_f, "few_bytes": bytes_f}
 
 
 def counterfactual_rate(torch, model, sources=256, chunk=32):
@@ -248,11 +262,11 @@ def run_native(args):
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.summary() if sampler else None
-    loss = float(trainer.static_losses[0])
+    loss = trainer.static_losses[0].detach().item()
 
     # ---- end-to-end: pinned host buffers -> H2D -> step -> D2H loss --------------------------------
     for _ in range(2):
-        trainer.load_batch(*pin); trainer.replay(); float(trainer.static_losses[0])
+        trainer.load_batch(*pin); trainer.replay(); trainer.static_losses[0].detach().item()
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -260,7 +274,7 @@ def run_native(args):
     for _ in range(args.steps):
         trainer.load_batch(*pin)
         trainer.replay()
-        loss_e2e = float(trainer.static_losses[0])      # D2H read of the step's loss
+        loss_e2e = trainer.static_losses[0].detach().item()      # D2H read of the step's loss
     e3.record()
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 * 0.0)
@@ -306,10 +320,17 @@ def run_native(args):
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
                      "traffic": NCU_TRAFFIC_BYTES,
                      "kernel": "conv_halo_tc_kernel (tcgen05 3xTF32, halo-tile staging) on its longest launch of the step: "
-                               "decoder.12 ConvT(16->16) input gradient, 256^2 -> 128^2, B=64",
+                               "stem.3 Conv2d(32->64, s2) input gradient, 64^2 -> 128^2, B=64",
                      "bytes_per_launch": probe["hbm_bytes"], "ms_per_launch": probe["hbm_ms"],
                      "peak_source": f"{how} copy bandwidth (burst: kernel timed alone)",
-                     "traffic_source": "profiles/r1_ncu_halo_raw.txt (dram__bytes_read.sum + dram__bytes_write.sum, same launch)"},
+                     "traffic_source": "profiles/r1_ncu_halo_stem3_raw.txt launch 1 (dram__bytes_read.sum + dram__bytes_write.sum)"},
+        "roofline_stream": {"bound": "hbm", "achieved": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9, "peak": hbm,
+                            "unit": "GB/s", "frac": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9 / hbm,
+                            "traffic": 286.5e6,
+                            "kernel": "convt16_up_kernel (fp32 SIMT tile kernel, csrc/conv_few.cu) on decoder.12 forward, "
+                                      "ConvTranspose2d(16->16) 128^2 -> 256^2, B=64: the largest tensors of the step",
+                            "bytes_per_launch": probe["few_bytes"], "ms_per_launch": probe["few_ms"],
+                            "traffic_source": "profiles/r1_ncu_few_raw.txt launch 0"},
         "roofline_tensor": {"bound": "tensor", "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s",
                             "frac": ach_tf / bf16_burst,
                             "kernel": "conv_halo_tc_kernel on stem.6 forward (Conv 64->128 s2 @64^2, B=64)",
