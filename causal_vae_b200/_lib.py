@@ -51,6 +51,8 @@ _SIGS = {
     "cvae_wgrad_reduce": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "cvae_pack_weight": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "cvae_conv_few_eligible": [i32] * 12,
+    "cvae_head_bwd_eligible": [i32, i32, i32, i32],
+    "cvae_head_bwd": [vp, vp, Xform, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "cvae_pack_batch_blocks": [i32, i32, i32, i32],
     "cvae_pack_batch": [vp, i32, i32, vp],
     "cvae_tc_eligible": [i32, i32, i64],

@@ -204,6 +204,13 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
             dbias = ops.col_sum(dy, Cd) if has_bias else None
     w_direct = direct_ok(w)
     gw = w.grad if w_direct else torch.empty_like(w)
+    if (u.kind == "conv" and u.k == 3 and u.stride == 1 and u.pad == 1 and Cd == 1 and u.bn is None and add is None
+            and need_dx and grad_cols is None and prev_entry is S_in and not S_in.x.identity and w.is_contiguous()
+            and dy.is_contiguous() and ops.head_bwd_eligible(N, Hs, Ws, Cs)):
+        # image head: weight gradient and input gradient share one pass over the (large) raw input
+        d_in = ops.head_bwd(dy, S_in.t, S_in.x, w, gw, prev_stats)
+        grads.append((None if w_direct else gw, dbias, dgamma, dbeta))
+        return d_in
     if u.kind == "convT":
         ops.conv_wgrad(dy, S_in.t, IDENT, S_in.x, u.k, u.stride, u.pad, gw)
     else:

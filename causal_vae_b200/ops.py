@@ -202,6 +202,23 @@ def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulat
     return grad_out
 
 
+_HEAD_FUSED = os.environ.get("CVAE_HEAD_FUSED", "1") != "0"
+
+
+def head_bwd_eligible(N, H, W, C):
+    return _HEAD_FUSED and bool(L.lib.cvae_head_bwd_eligible(int(N), int(H), int(W), int(C)))
+
+
+def head_bwd(g, y, xf, w, dw, stats):
+    """Image-head backward in one pass (csrc/head_bwd.cu): returns dz = conv^T(g) * act'(xf(y)); writes the
+    weight gradient `dw` (torch layout) and accumulates the BN-backward sums of the producer into `stats`."""
+    N, H, W, C = y.shape
+    dz = torch.empty_like(y)
+    L.check(L.lib.cvae_head_bwd(L.ptr(g), L.ptr(y), xf.c(), L.ptr(w), L.ptr(dz), L.ptr(stats), L.ptr(dw), N, H, W, C,
+                                L.stream()), f"head_bwd {N}x{H}x{W}x{C}")
+    return dz
+
+
 def bn_finalize(stats, C, count, bn, train_buffers=True):
     scale, shift, mean, rstd = (empty(C, like=stats) for _ in range(4))
     rm = bn.running_mean if (train_buffers and bn.track_running_stats) else None

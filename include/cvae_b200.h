@@ -124,6 +124,16 @@ int cvae_pack_weight(const float* src, float* dst, int A, int A_pad, int B, int 
 int cvae_conv_few_eligible(int Cs, int Cd, int k, int stride, int pad, int mode, int N, int Hs, int Ws,
                            int Hd, int Wd, int epi);
 
+/* Backward of the image head (nn.Conv2d(C, 1, 3, padding=1), vit_backbone.py:152-156) in one pass over its
+ * input: weight gradient and input gradient together, replacing cvae_conv_wgrad + cvae_wgrad_reduce +
+ * cvae_conv_gather(EPI_DACT) for this layer (cuDNN wgrad + dgrad in the reference's loss.backward()).
+ *   g  [N,H,W,1] dL/dout;  y [N,H,W,C] raw producer output, `x` its BatchNorm + LeakyReLU transform;
+ *   w  [1][C][3][3] torch layout;  dz [N,H,W,C] = conv^T(g) * act'(z);  stats [2C] += (sum dz, sum dz*(y-center));
+ *   dw [1][C][3][3] torch layout, overwritten. */
+int cvae_head_bwd_eligible(int N, int H, int W, int C);
+int cvae_head_bwd(const float* g, const float* y, cvae_xform_t x, const float* w, float* dz, double* stats,
+                  float* dw, int N, int H, int W, int C, cvae_stream_t s);
+
 /* Batched weight packing: every cvae_pack_weight / cvae_tc_pack_weight call of a training step as one
  * launch.  `jobs_dev` is a DEVICE array sorted by block0 (job i owns blocks [block0_i, block0_{i+1}),
  * cvae_pack_batch_blocks(...) blocks each); tc != 0 selects the tensor-core layout.  The reference
