@@ -88,6 +88,32 @@ class direct_grads:
         return False
 
 
+# Weight-gradient kernels on a side stream.  In backward a layer's weight gradient (and bias column sum) and
+# its input gradient are independent; the ViT / adapter layers launch grids of 66-132 CTAs on 148 SMs, so
+# running the two families concurrently fills the idle SMs (and overlaps the tails of the big layers).
+# Only used together with direct_grads (the kernels then write into the flat gradient buffer and autograd
+# never touches the result); the trainer joins the side stream before the optimizer.
+SIDE = {"stream": None, "keep": []}
+
+
+class side_wgrad:
+    """with direct_grads(), side_wgrad(stream): loss.backward()"""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        SIDE["stream"], SIDE["keep"] = self.stream, []
+
+    def __exit__(self, *exc):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)     # join before anything reads the gradients
+        # operands of the side-stream kernels were kept alive until here: blocks freed now can only be reused by
+        # work that is ordered after the join
+        SIDE["stream"], SIDE["keep"] = None, []
+        return False
+
+
 def direct_ok(p):
     return DIRECT_GRADS[0] and p is not None and p.requires_grad and p.grad is not None and p.grad.is_contiguous()
 
@@ -197,25 +223,39 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
     else:
         dy = dz
         dgamma = dbeta = None
-        if has_bias and direct_ok(u.mod.bias):
-            ops.col_sum(dy, Cd, out=u.mod.bias.grad)
-            dbias = None
-        else:
-            dbias = ops.col_sum(dy, Cd) if has_bias else None
+        bias_direct = has_bias and direct_ok(u.mod.bias)
+        dbias = ops.col_sum(dy, Cd) if (has_bias and not bias_direct) else None
     w_direct = direct_ok(w)
     gw = w.grad if w_direct else torch.empty_like(w)
+    side = SIDE["stream"] if w_direct else None
+    bias_direct = u.bn is None and has_bias and direct_ok(u.mod.bias)
+    if bias_direct and side is None:
+        ops.col_sum(dy, Cd, out=u.mod.bias.grad)
     if (u.kind == "conv" and u.k == 3 and u.stride == 1 and u.pad == 1 and Cd == 1 and u.bn is None and add is None
             and need_dx and grad_cols is None and prev_entry is S_in and not S_in.x.identity and w.is_contiguous()
             and dy.is_contiguous() and ops.head_bwd_eligible(N, Hs, Ws, Cs)):
         # image head: weight gradient and input gradient share one pass over the (large) raw input
+        if bias_direct and side is not None:
+            ops.col_sum(dy, Cd, out=u.mod.bias.grad)
         d_in = ops.head_bwd(dy, S_in.t, S_in.x, w, gw, prev_stats)
         grads.append((None if w_direct else gw, dbias, dgamma, dbeta))
         return d_in
-    if u.kind == "convT":
-        ops.conv_wgrad(dy, S_in.t, IDENT, S_in.x, u.k, u.stride, u.pad, gw)
+
+    def weight_side():
+        if bias_direct and side is not None:
+            ops.col_sum(dy, Cd, out=u.mod.bias.grad)
+        if u.kind == "convT":
+            ops.conv_wgrad(dy, S_in.t, IDENT, S_in.x, u.k, u.stride, u.pad, gw)
+        else:
+            ca_real = w.shape[1] if u.kind == "linear" else None
+            ops.conv_wgrad(S_in.t, dy, S_in.x, IDENT, u.k, u.stride, u.pad, gw, ca_real=ca_real)
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())     # dy (and the statistics it depends on) are complete
+        with torch.cuda.stream(side):
+            weight_side()
+        SIDE["keep"].append((dy, rec, gw))                # operands stay allocated until the join
     else:
-        ca_real = w.shape[1] if u.kind == "linear" else None
-        ops.conv_wgrad(S_in.t, dy, S_in.x, IDENT, u.k, u.stride, u.pad, gw, ca_real=ca_real)
+        weight_side()
     grads.append((None if w_direct else gw, dbias, dgamma, dbeta))
     if not need_dx:
         return None

@@ -4,7 +4,7 @@ import torch
 
 from .. import functional as F
 from .. import ops
-from ..chain import direct_grads
+from ..chain import direct_grads, side_wgrad
 from ..optim import FlatParams, FusedClipAdam
 from ..parallel import allreduce_gradients
 from .models import CONFIG
@@ -35,7 +35,7 @@ class VesselTrainer:
     the sum of shard gradients is the single-device gradient — SURVEY §8(e)) before the clip."""
 
     def __init__(self, model, lr=None, max_norm=5.0, beta=None, lambda_morph=1.0, process_group=None,
-                 distributed=False):
+                 distributed=False, overlap_wgrad=True):
         self.model = model
         self.flat = FlatParams(model)
         self.opt = FusedClipAdam(self.flat, CONFIG["LEARNING_RATE"] if lr is None else lr, max_norm)
@@ -44,6 +44,7 @@ class VesselTrainer:
         self.graph = None
         self.static = None
         self.pack_plan = ops.PackPlan()
+        self.side = torch.cuda.Stream() if overlap_wgrad else None
         F.set_rng_counter(self.opt.step_count)
 
     def _fwd_bwd(self, x, m, t, eps):
@@ -56,7 +57,9 @@ class VesselTrainer:
             out = self.model(x, m, t, eps)
             recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
             loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
-            with direct_grads():      # zero_grad() above zeroed the flat buffer; every parameter is used once
+            # zero_grad() above zeroed the flat buffer and every parameter is used once: gradients are written
+            # in place, the weight-gradient kernels on a side stream (joined on exit, before the optimizer)
+            with direct_grads(), side_wgrad(self.side):
                 loss.backward()
         finally:
             ops.arena_end()
