@@ -271,8 +271,11 @@ def run_native(args):
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
-        trainer.load_batch(*pin)
+    trainer.prefetch(*pin)                               # batch 0: its H2D copy is inside the timed region
+    for i in range(args.steps):
+        trainer.commit_prefetched()                      # staging -> graph inputs (D2D)
+        if i + 1 < args.steps:
+            trainer.prefetch(*pin)                       # H2D of batch i+1 (copy stream) overlaps the step of batch i
         trainer.replay()
         loss_e2e = trainer.static_losses[0].detach().item()      # D2H read of the step's loss
     e3.record()

@@ -79,6 +79,7 @@ _SIGS = {
     "cvae_act_bwd": [vp, vp, vp, i64, i32, f32, vp],
     "cvae_add": [vp, vp, vp, i64, vp],
     "cvae_dropout": [vp, vp, i64, f32, u64, u64, vp, vp],
+    "cvae_dropout_fused": [vp, vp, vp, i64, i32, i32, f32, f32, u64, u64, vp, vp],
     "cvae_clamp_fwd": [vp, vp, i64, f32, f32, vp],
     "cvae_clamp_bwd": [vp, vp, vp, i64, f32, f32, vp],
     "cvae_kld_fwd": [vp, vp, i64, vp, vp],

@@ -82,6 +82,56 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
   }
 }
 
+// Fused activation + dropout (ViT MLP: GELU -> Dropout, vit_backbone.py:33-35) and dropout + residual add.
+// The keep mask is the one dropout_kernel draws for the same (seed, offset): element e uses word e & 3 of
+// Philox counter e >> 2, so fusing changes launches, not random streams.
+// MODE 0: y = act(x) * m;   MODE 1 (backward): y = aux * act'(x) * m  (aux = dL/dy);   MODE 2: y = aux + x * m
+template <int MODE, int ACT>
+__global__ void dropout_fused_kernel(const float* __restrict__ x, const float* __restrict__ aux, float* __restrict__ y,
+                                     int64_t n, float slope, float p, uint64_t seed, uint64_t offset,
+                                     const int64_t* __restrict__ counter) {
+  if (counter) seed += (uint64_t)(*counter) * 0x9E3779B97F4A7C15ull;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, n4 = (n + 3) >> 2;
+  const float ks = 1.f / (1.f - p);
+  auto act = [&](float v) {
+    if (ACT == CVAE_ACT_LRELU) return lrelu(v, slope);
+    if (ACT == CVAE_ACT_GELU) return gelu_f(v);
+    return 1.0f / (1.0f + expf(-v));
+  };
+  auto dact = [&](float v) {
+    if (ACT == CVAE_ACT_LRELU) return v > 0.f ? 1.f : slope;
+    if (ACT == CVAE_ACT_GELU) return gelu_grad(v);
+    const float sg = 1.0f / (1.0f + expf(-v));
+    return sg * (1.0f - sg);
+  };
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint4 r = philox4x32(seed, (uint64_t)i, offset);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    float xv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool full = (i << 2) + 3 < n;
+    if (full) {
+      const float4 t = reinterpret_cast<const float4*>(x)[i];
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+      if (MODE != 0) { const float4 u = reinterpret_cast<const float4*>(aux)[i]; av[0] = u.x; av[1] = u.y; av[2] = u.z; av[3] = u.w; }
+    } else {
+      for (int u = 0; u < 4; ++u) {
+        const int64_t e = (i << 2) + u;
+        if (e < n) { xv[u] = x[e]; if (MODE != 0) av[u] = aux[e]; }
+      }
+    }
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float m = ((float)(w[u] >> 8) * (1.0f / 16777216.0f) >= p) ? ks : 0.f;
+      if (MODE == 0) o[u] = act(xv[u]) * m;
+      else if (MODE == 1) o[u] = av[u] * dact(xv[u]) * m;
+      else o[u] = av[u] + xv[u] * m;
+    }
+    if (full) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    else for (int u = 0; u < 4; ++u) { const int64_t e = (i << 2) + u; if (e < n) y[e] = o[u]; }
+  }
+}
+
 __global__ void tokens_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ cls,
                                   const float* __restrict__ pos, float* __restrict__ tok, int B, int n, int D) {
   const int64_t total = (int64_t)B * (n + 1) * D, stride = (int64_t)gridDim.x * blockDim.x;
@@ -333,6 +383,24 @@ extern "C" int cvae_dropout(const float* x, float* y, int64_t n, float p, uint64
     return CVAE_OK;
   }
   dropout_kernel<<<ew_blocks(n / 4 + 1), 256, 0, ST>>>(x, y, n, p, seed, offset, counter);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+
+// mode 0: y = act(x) * mask / (1-p);  mode 1: y = aux * act'(x) * mask / (1-p);  mode 2: y = aux + x * mask / (1-p)
+extern "C" int cvae_dropout_fused(const float* x, const float* aux, float* y, int64_t n, int mode, int act, float slope,
+                                  float p, uint64_t seed, uint64_t offset, const int64_t* counter, cvae_stream_t s) {
+  if (!x || !y || n <= 0 || p <= 0.f || p >= 1.f || mode < 0 || mode > 2 || (mode != 0 && !aux)) return CVAE_ERR_BAD_ARG;
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(aux)) & 15) != 0)
+    return CVAE_ERR_ALIGNMENT;
+  const int b = ew_blocks(n / 4 + 1);
+#define CVAE_DF(M, A) dropout_fused_kernel<M, A><<<b, 256, 0, ST>>>(x, aux, y, n, slope, p, seed, offset, counter)
+  if (mode == 2) CVAE_DF(2, CVAE_ACT_LRELU);
+  else if (act == CVAE_ACT_GELU) { if (mode == 0) CVAE_DF(0, CVAE_ACT_GELU); else CVAE_DF(1, CVAE_ACT_GELU); }
+  else if (act == CVAE_ACT_LRELU) { if (mode == 0) CVAE_DF(0, CVAE_ACT_LRELU); else CVAE_DF(1, CVAE_ACT_LRELU); }
+  else if (act == CVAE_ACT_SIGMOID) { if (mode == 0) CVAE_DF(0, CVAE_ACT_SIGMOID); else CVAE_DF(1, CVAE_ACT_SIGMOID); }
+  else return CVAE_ERR_BAD_ARG;
+#undef CVAE_DF
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

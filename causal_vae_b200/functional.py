@@ -161,6 +161,69 @@ def dropout(x, p, training):
     return y.permute(0, 3, 1, 2) if perm else y
 
 
+class _ActDropout(torch.autograd.Function):
+    """dropout(act(x)) as one kernel each way (same mask as _Dropout would draw at this point of the stream)."""
+
+    @staticmethod
+    def forward(ctx, x, act, slope, p):
+        xc = x.contiguous()
+        ctx.cfg = (act, slope, p, next_rng())
+        seed, off, cnt = ctx.cfg[3]
+        y = torch.empty_like(xc)
+        L.check(L.lib.cvae_dropout_fused(L.ptr(xc), None, L.ptr(y), xc.numel(), 0, act, slope, p, seed, off, L.ptr(cnt),
+                                         L.stream()), "act_dropout_fwd")
+        ctx.save_for_backward(xc)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        act, slope, p, (seed, off, cnt) = ctx.cfg
+        gc = g.contiguous()
+        dx = torch.empty_like(xc)
+        L.check(L.lib.cvae_dropout_fused(L.ptr(xc), L.ptr(gc), L.ptr(dx), xc.numel(), 1, act, slope, p, seed, off,
+                                         L.ptr(cnt), L.stream()), "act_dropout_bwd")
+        return dx.view(g.shape), None, None, None
+
+
+def act_dropout(x, act, p, training, slope=0.0):
+    """nn.Dropout(p)(activation(x))"""
+    if not training or p == 0.0:
+        return activation(x, act, slope)
+    v, perm = _elementwise_view(x)
+    y = _ActDropout.apply(v, act, float(slope), float(p))
+    return y.permute(0, 3, 1, 2) if perm else y
+
+
+class _DropoutAdd(torch.autograd.Function):
+    """res + dropout(x)"""
+
+    @staticmethod
+    def forward(ctx, x, res, p):
+        xc, rc = x.contiguous(), res.contiguous()
+        ctx.p, ctx.rng = p, next_rng()
+        seed, off, cnt = ctx.rng
+        y = torch.empty_like(xc)
+        L.check(L.lib.cvae_dropout_fused(L.ptr(xc), L.ptr(rc), L.ptr(y), xc.numel(), 2, 0, 0.0, p, seed, off, L.ptr(cnt),
+                                         L.stream()), "dropout_add")
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        seed, off, cnt = ctx.rng
+        gc = g.contiguous()
+        return ops.dropout(gc, ctx.p, seed, off, cnt).view(g.shape), g, None
+
+
+def dropout_add(x, res, p, training):
+    """res + nn.Dropout(p)(x)"""
+    if not training or p == 0.0:
+        return add(res, x)
+    if x.shape != res.shape or x.dim() == 4:
+        return add(res, dropout(x, p, training))
+    return _DropoutAdd.apply(x, res, float(p))
+
+
 class _Add(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):

@@ -130,6 +130,35 @@ class VesselTrainer:
         else:
             self.static["eps"].normal_()
 
+    # ---- double-buffered input: the H2D copy of batch i+1 overlaps the replay of batch i ------------------
+    def prefetch(self, x, m, t, eps=None):
+        """Start the host -> device copy of the NEXT batch on a copy stream into staging buffers
+        (pinned host tensors make it asynchronous).  commit_prefetched() hands it to the graph."""
+        if getattr(self, "_stage", None) is None:
+            self._stage = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._copy_done = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+        self._copy_stream.wait_event(self._stage_free)          # the previous commit has read the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            self._stage["x"].copy_(x, non_blocking=True)
+            self._stage["m"].copy_(m, non_blocking=True)
+            self._stage["t"].copy_(t, non_blocking=True)
+            if eps is not None:
+                self._stage["eps"].copy_(eps, non_blocking=True)
+            else:
+                self._stage["eps"].normal_()
+            self._copy_done.record()
+
+    def commit_prefetched(self):
+        """staging -> static graph inputs (device-to-device, ordered after the prefetch and before the replay)"""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copy_done)
+        for k, v in self.static.items():
+            v.copy_(self._stage[k], non_blocking=True)
+        self._stage_free.record(cur)
+
     def replay(self):
         self.graph.replay()
         return self.static_losses

@@ -3,6 +3,7 @@ state_dict keys as vessel_analysis/00_core/vit_backbone.py:7-199, on the native 
 import torch
 import torch.nn as tnn
 
+from .. import _lib as L
 from .. import functional as F
 from .. import nn
 
@@ -30,7 +31,11 @@ class ViTBlock(tnn.Module):
         q = self.norm1(x)
         attn_out, _ = self.attn(q, q, q)
         x = F.add(x, attn_out)
-        return F.add(x, self.mlp(self.norm2(x)))
+        # mlp = Linear, GELU, Dropout, Linear, Dropout (vit_backbone.py:31-37) with GELU+Dropout and
+        # Dropout+residual each fused into one kernel (same masks: the random stream is consumed in the same order)
+        lin1, act, drop1, lin2, drop2 = self.mlp[0], self.mlp[1], self.mlp[2], self.mlp[3], self.mlp[4]
+        h = F.act_dropout(lin1(self.norm2(x)), L.ACT_GELU, drop1.p, drop1.training)
+        return F.dropout_add(lin2(h), x, drop2.p, drop2.training)
 
 
 class ViTVAE(tnn.Module):

@@ -240,6 +240,11 @@ int cvae_add(const float* a, const float* b, float* out, int64_t n, cvae_stream_
  * gradient in backward (nn.Dropout(0.1); vit_backbone.py:35-37,104). */
 int cvae_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
                  const int64_t* counter, cvae_stream_t s);
+/* Fused forms with the SAME mask cvae_dropout draws for (seed, offset, counter), 0 < p < 1:
+ * mode 0: y = act(x) * mask/(1-p)  (nn.GELU -> nn.Dropout, vit_backbone.py:33-35);  mode 1 (its backward):
+ * y = aux * act'(x) * mask/(1-p), aux = dL/dy;  mode 2: y = aux + x * mask/(1-p)  (Dropout -> residual add). */
+int cvae_dropout_fused(const float* x, const float* aux, float* y, int64_t n, int mode, int act, float slope,
+                       float p, uint64_t seed, uint64_t offset, const int64_t* counter, cvae_stream_t s);
 /* y = clamp(x, lo, hi); dx = dy where lo <= x <= hi (torch.clamp; models.py:285-286,294) */
 int cvae_clamp_fwd(const float* x, float* y, int64_t n, float lo, float hi, cvae_stream_t s);
 int cvae_clamp_bwd(const float* dy, const float* x, float* dx, int64_t n, float lo, float hi,

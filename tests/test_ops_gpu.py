@@ -359,6 +359,37 @@ def test_dropout_statistics():
     assert torch.equal((x.grad != 0), (y != 0)), "backward must regenerate the same mask"
 
 
+def test_fused_dropout_forms_draw_the_same_mask():
+    """dropout(gelu(x)) and res + dropout(x) as single kernels: same values and gradients as the unfused
+    sequence at the same point of the random stream (fusing must change launches, not masks)."""
+    from causal_vae_b200 import _lib as L
+    from causal_vae_b200 import functional as F
+    x = gen(37, 65, 512, seed=50).cuda()
+    res = gen(37, 65, 512, seed=51).cuda()
+    gy = gen(37, 65, 512, seed=52).cuda()
+    cases = [(lambda a: F.act_dropout(a, L.ACT_GELU, 0.1, True), lambda a: F.dropout(F.activation(a, L.ACT_GELU), 0.1, True)),
+             (lambda a: F.dropout_add(a, res, 0.1, True), lambda a: F.add(res, F.dropout(a, 0.1, True)))]
+    for fused, plain in cases:
+        F.manual_seed(99)
+        a1 = x.clone().requires_grad_(True)
+        y1 = fused(a1)
+        y1.backward(gy)
+        F.manual_seed(99)
+        a2 = x.clone().requires_grad_(True)
+        y2 = plain(a2)
+        y2.backward(gy)
+        assert rel(y1, y2) <= 1e-6, rel(y1, y2)
+        assert rel(a1.grad, a2.grad) <= 1e-6, rel(a1.grad, a2.grad)
+    # odd length (vector tail) and p = 0 / eval fall back to the plain kernels
+    v = gen(1027, seed=53).cuda()
+    F.manual_seed(5)
+    t1 = F.act_dropout(v, L.ACT_GELU, 0.25, True)
+    F.manual_seed(5)
+    t2 = F.dropout(F.activation(v, L.ACT_GELU), 0.25, True)
+    assert rel(t1, t2) <= 1e-6
+    assert rel(F.act_dropout(v, L.ACT_GELU, 0.25, False), F.activation(v, L.ACT_GELU)) == 0.0
+
+
 @pytest.mark.parametrize("S,p", [(65, 0.0), (65, 0.3), (17, 0.1), (128, 0.2), (7, 0.0)])
 def test_attention_core_with_dropout(S, p):
     """softmax(QK^T/sqrt(d)) (dropout) V and its gradient against fp64 torch, using the very mask the
