@@ -60,33 +60,42 @@ class CounterfactualEngine:
     change in eval mode - call refresh() after loading new weights).  The eager sweep spends a third of
     its time in ~10^3 host-side enqueues per chunk; a replay is one launch.
 
+    `lanes` > 1 keeps that many independent (buffers, graph, stream) sets and rotates chunks over them, so
+    consecutive chunks overlap on the device (measured on B200 at chunk = 32: no gain - the image-sized
+    layers fill the GPU on their own - hence the default of 1).  sweep_all() drives a whole source set.
+
         eng = CounterfactualEngine(model, chunk=32, delta=5.0)
         for i in range(0, S, 32):
-            l2 = eng(m[i:i+32], z[i:i+32])        # [32, K]; valid until the next call
+            l2 = eng(m[i:i+32], z[i:i+32])        # [32, K]; valid until the lane is reused
+        l2_all = eng.sweep_all(m, z)              # [S, K]
     """
 
-    def __init__(self, model, chunk, delta=5.0, value=None):
+    def __init__(self, model, chunk, delta=5.0, value=None, lanes=1):
         self.model, self.chunk, self.delta, self.value = model, int(chunk), delta, value
         model.eval()
         p0 = next(model.parameters())
-        self.m = torch.zeros(self.chunk, model.m_dim, device=p0.device)
-        self.z = torch.zeros(self.chunk, model.my_z_dim, device=p0.device)
         self.plan = ops.PackPlan()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(2):
-                self._sweep()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
-            self.l2 = self._sweep()
+        self.lanes = []
+        self._next = 0
+        for _ in range(max(1, int(lanes))):
+            lane = {"m": torch.zeros(self.chunk, model.m_dim, device=p0.device),
+                    "z": torch.zeros(self.chunk, model.my_z_dim, device=p0.device),
+                    "stream": torch.cuda.Stream(), "done": torch.cuda.Event()}
+            lane["stream"].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(lane["stream"]), torch.no_grad():
+                for _ in range(2):
+                    self._sweep(lane)
+            torch.cuda.synchronize()
+            lane["graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(lane["graph"], stream=lane["stream"]), torch.no_grad():
+                lane["l2"] = self._sweep(lane)
+            self.lanes.append(lane)
+        torch.cuda.current_stream().wait_stream(self.lanes[-1]["stream"])
 
-    def _sweep(self):
+    def _sweep(self, lane):
         ops.set_pack_plan(self.plan)
         try:
-            l2, _, _ = counterfactual_sweep(self.model, self.m, self.z, delta=self.delta, value=self.value)
+            l2, _, _ = counterfactual_sweep(self.model, lane["m"], lane["z"], delta=self.delta, value=self.value)
         finally:
             ops.set_pack_plan(None)
         if self.plan.recording:
@@ -97,11 +106,42 @@ class CounterfactualEngine:
         """re-pack every weight layout from the model's current parameters (one launch)"""
         self.plan.run()
 
-    @torch.no_grad()
-    def __call__(self, m, z):
+    def _launch(self, m, z):
         if m.shape[0] != self.chunk:
             raise RuntimeError(f"CounterfactualEngine was captured for chunks of {self.chunk} sources, got {m.shape[0]}")
-        self.m.copy_(m, non_blocking=True)
-        self.z.copy_(z, non_blocking=True)
-        self.graph.replay()
-        return self.l2
+        lane = self.lanes[self._next]
+        self._next = (self._next + 1) % len(self.lanes)
+        st = lane["stream"]
+        st.wait_stream(torch.cuda.current_stream())       # inputs are ready; the lane's previous result was consumed
+        with torch.cuda.stream(st):
+            lane["m"].copy_(m, non_blocking=True)
+            lane["z"].copy_(z, non_blocking=True)
+            lane["graph"].replay()
+            lane["done"].record(st)
+        return lane
+
+    @torch.no_grad()
+    def __call__(self, m, z):
+        lane = self._launch(m, z)
+        torch.cuda.current_stream().wait_event(lane["done"])
+        return lane["l2"]
+
+    @torch.no_grad()
+    def sweep_all(self, m, z):
+        """[S, K] effect sizes of all sources; chunks rotate over the lanes so that they overlap on the device."""
+        S, K = m.shape
+        if S % self.chunk:
+            raise RuntimeError(f"number of sources ({S}) must be a multiple of the chunk size ({self.chunk})")
+        out = torch.empty(S, K, device=m.device)
+        cur = torch.cuda.current_stream()
+        pending = []
+        for i in range(0, S, self.chunk):
+            if len(pending) == len(self.lanes):            # the lane about to be reused: drain its result first
+                j, ln = pending.pop(0)
+                cur.wait_event(ln["done"])
+                out[j:j + self.chunk].copy_(ln["l2"], non_blocking=True)
+            pending.append((i, self._launch(m[i:i + self.chunk], z[i:i + self.chunk])))
+        for j, ln in pending:
+            cur.wait_event(ln["done"])
+            out[j:j + self.chunk].copy_(ln["l2"], non_blocking=True)
+        return out

@@ -63,13 +63,19 @@ def test_eval_forward_and_counterfactual(cfg):
         assert rel(l2[:, k], want) <= 1e-4
     assert rel(l2[:, 5], torch.tensor(gold["eval"]["cf_l2_per_sample"])) <= 1e-4
     # the graph-captured engine (static buffers, weight layouts packed once) gives the same effect sizes
-    eng = CF.CounterfactualEngine(model, B, delta=5.0)
+    eng = CF.CounterfactualEngine(model, B, delta=5.0, lanes=2)
     for _ in range(2):
         l2_g = eng(m.cuda(), z.cuda().float())
     assert rel(l2_g, l2) <= 1e-6, rel(l2_g, l2)
     l2_h = eng(m.cuda() * 0.5, z.cuda().float())          # different inputs through the same graph
     l2_e, _, _ = CF.counterfactual_sweep(model, m.cuda() * 0.5, z.cuda().float(), delta=5.0)
     assert rel(l2_h, l2_e) <= 1e-6
+    # a whole source set through the rotating lanes (3 chunks over 2 lanes)
+    m3 = torch.cat([m.cuda(), m.cuda() * 0.5, m.cuda() * 2.0])
+    z3 = torch.cat([z.cuda().float()] * 3)
+    l2_all = eng.sweep_all(m3, z3)
+    l2_2, _, _ = CF.counterfactual_sweep(model, m.cuda() * 2.0, z.cuda().float(), delta=5.0)
+    assert rel(l2_all[:B], l2) <= 1e-6 and rel(l2_all[B:2 * B], l2_e) <= 1e-6 and rel(l2_all[2 * B:], l2_2) <= 1e-6
 
 
 @pytest.mark.parametrize("cfg", [(64, 64, 4), (128, 96, 8), (256, 256, 8)])
