@@ -99,10 +99,14 @@ SIDE = {"stream": None, "keep": []}
 class side_wgrad:
     """with direct_grads(), side_wgrad(stream): loss.backward()"""
 
-    def __init__(self, stream):
-        self.stream = stream
+    def __init__(self, stream, join_first=False):
+        self.stream, self.join_first = stream, join_first
 
     def __enter__(self):
+        if self.stream is not None and self.join_first:
+            # work the trainer put on the side stream during forward (gradient zeroing, backward-only weight
+            # layouts) is complete before the first backward kernel
+            torch.cuda.current_stream().wait_stream(self.stream)
         SIDE["stream"], SIDE["keep"] = self.stream, []
 
     def __exit__(self, *exc):
@@ -357,7 +361,14 @@ class ChainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         gout = gout.contiguous()
-        dx, flat = chain_backward(ctx.chain, ctx.recs, ctx.final, gout, ctx.need_dx, ctx.grad_cols)
+        plan = ops._PLAN[0]
+        if plan is not None:
+            plan.phase = "bwd"
+        try:
+            dx, flat = chain_backward(ctx.chain, ctx.recs, ctx.final, gout, ctx.need_dx, ctx.grad_cols)
+        finally:
+            if plan is not None:
+                plan.phase = "fwd"
         ctx.recs = ctx.final = None
         if dx is not None and ctx.grad_cols is not None and ctx.grad_cols != ctx.x_cols:
             full = ops.zeros(*dx.shape[:-1], ctx.x_cols, like=dx)

@@ -105,7 +105,9 @@ class PackPlan:
 
     def __init__(self):
         self.entries, self.jobs, self.recording = {}, [], True
-        self.table, self.nblocks = None, 0
+        self.tables = {}            # phase ("fwd" | "bwd") -> (device job table, number of jobs, number of blocks)
+        self.phase = "fwd"          # set to "bwd" by the chain backward: layouts first needed there can be packed
+                                    # off the critical path (VesselTrainer runs them on its side stream)
 
     @staticmethod
     def key(w, A, A_pad, B, taps, src_bat, src_ld, tc):
@@ -114,22 +116,25 @@ class PackPlan:
     def finalize(self):
         import numpy as np
         self.recording = False
-        if not self.jobs:
-            return
         dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("A", "<i4"), ("A_pad", "<i4"), ("B", "<i4"), ("taps", "<i4"),
                        ("src_bat", "<i4"), ("src_ld", "<i4"), ("tc", "<i4"), ("block0", "<i4")])
-        arr = np.zeros(len(self.jobs), dtype=dt)
-        b0 = 0
-        for i, (w, out, (_, A, A_pad, B, taps, src_bat, src_ld, tc)) in enumerate(self.jobs):
-            arr[i] = (w.data_ptr(), out.data_ptr(), A, A_pad, B, taps, src_bat, src_ld, int(tc), b0)
-            b0 += int(L.lib.cvae_pack_batch_blocks(A_pad, B, taps, int(tc)))
-        self.nblocks = b0
-        dev = self.jobs[0][1].device
-        self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+        for phase in ("fwd", "bwd"):
+            jobs = [j for j in self.jobs if j[3] == phase]
+            if not jobs:
+                continue
+            arr = np.zeros(len(jobs), dtype=dt)
+            b0 = 0
+            for i, (w, out, (_, A, A_pad, B, taps, src_bat, src_ld, tc), _) in enumerate(jobs):
+                arr[i] = (w.data_ptr(), out.data_ptr(), A, A_pad, B, taps, src_bat, src_ld, int(tc), b0)
+                b0 += int(L.lib.cvae_pack_batch_blocks(A_pad, B, taps, int(tc)))
+            self.tables[phase] = (torch.from_numpy(arr.view(np.uint8).copy()).to(jobs[0][1].device), len(jobs), b0)
 
-    def run(self):
-        if self.table is not None:
-            L.check(L.lib.cvae_pack_batch(L.ptr(self.table), len(self.jobs), self.nblocks, L.stream()), "pack_batch")
+    def run(self, phase=None):
+        """re-pack the recorded layouts (all, or only those first requested in `phase`) on the current stream"""
+        for ph in (("fwd", "bwd") if phase is None else (phase,)):
+            if ph in self.tables:
+                table, njobs, nblocks = self.tables[ph]
+                L.check(L.lib.cvae_pack_batch(L.ptr(table), njobs, nblocks, L.stream()), "pack_batch")
 
 
 _PLAN = [None]
@@ -149,7 +154,7 @@ def pack_weight(w, A, A_pad, B, taps, src_bat, src_ld, tc=False):
         if plan.recording:
             out = _pack_weight_now(w, A, A_pad, B, taps, src_bat, src_ld, tc)
             plan.entries[k] = out
-            plan.jobs.append((w, out, k))
+            plan.jobs.append((w, out, k, plan.phase))
             return out
     return _pack_weight_now(w, A, A_pad, B, taps, src_bat, src_ld, tc)
 

@@ -1,5 +1,7 @@
 """Vessel training step — mirrors vessel_analysis/01_train/train.py:18-98 (loss_function,
 train_one_epoch's inner step) on the native kernels, plus a CUDA-graph-captured whole step."""
+import os
+
 import torch
 
 from .. import functional as F
@@ -48,18 +50,31 @@ class VesselTrainer:
         F.set_rng_counter(self.opt.step_count)
 
     def _fwd_bwd(self, x, m, t, eps):
-        self.opt.zero_grad()
         ops.arena_begin(self.flat.data.device)
         ops.set_pack_plan(self.pack_plan)
-        if not self.pack_plan.recording:
-            self.pack_plan.run()          # every weight layout of the step, one launch
+        packed = not self.pack_plan.recording
+        side_prep = self.side is not None and os.environ.get("CVAE_SIDE_PREP", "1") != "0"
+        if side_prep:
+            # off the critical path: the gradient buffer is zeroed and the weight layouts first needed in backward
+            # are packed on the side stream while the forward pass runs (joined when backward starts)
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                self.opt.zero_grad()
+                if packed:
+                    self.pack_plan.run("bwd")
+            if packed:
+                self.pack_plan.run("fwd")
+        else:
+            self.opt.zero_grad()
+            if packed:
+                self.pack_plan.run()      # every weight layout of the step, one launch
         try:
             out = self.model(x, m, t, eps)
             recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
             loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
             # zero_grad() above zeroed the flat buffer and every parameter is used once: gradients are written
             # in place, the weight-gradient kernels on a side stream (joined on exit, before the optimizer)
-            with direct_grads(), side_wgrad(self.side):
+            with direct_grads(), side_wgrad(self.side, join_first=side_prep):
                 loss.backward()
         finally:
             ops.arena_end()

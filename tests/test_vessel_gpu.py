@@ -150,31 +150,30 @@ def test_graph_replay_equals_eager():
     from causal_vae_b200.vessel import train
     H = W = 64
     B = 4
+    lr = 1e-4
     x, m, t, eps = (a.cuda() for a in O.vessel_inputs(B, H, W, seed=0))
     model_a, _ = build(H, W)
-    ta = train.VesselTrainer(model_a, lr=1e-3)
+    ta = train.VesselTrainer(model_a, lr=lr)
     la = [float(ta.step(x, m, t, eps)[0]) for _ in range(3)]
     model_b, _ = build(H, W)
-    tb = train.VesselTrainer(model_b, lr=1e-3).capture(B, H, W)
+    tb = train.VesselTrainer(model_b, lr=lr).capture(B, H, W)
     lb = []
     for _ in range(3):
         tb.load_batch(x, m, t, eps)
         lb.append(float(tb.replay()[0]))
-    # step 1 is the same computation (only atomic ordering differs).  Later steps diverge by chaotic
-    # amplification, not by a replay defect: Adam at lr 1e-3 moves every parameter by ~lr * sign(g)
-    # in its first steps, and the sign of rounding-noise gradients (e.g. biases feeding a BatchNorm,
-    # whose true gradient is 0) differs run to run -- two EAGER runs differ by the same amount
-    # (scripts/diag_determinism.py).
-    assert abs(la[0] - lb[0]) <= 1e-6 * abs(la[0]), (la, lb)
-    for a, b in zip(la, lb):
-        assert abs(a - b) <= 1e-3 * abs(a), (la, lb)
-    assert la[2] < la[0]
-    # Adam's g/sqrt(v) amplifies last-bit (atomic-order) differences of tiny gradients: loose bound
+    # Step 1 is the same computation (only atomic ordering differs).  Later steps diverge by chaotic
+    # amplification, not by a replay defect: Adam's first steps move every parameter by ~lr * sign(g), the sign
+    # of rounding-noise gradients (a bias feeding a BatchNorm, whose true gradient is 0) differs run to run, and
+    # last-bit differences in the BatchNorm statistics flip LeakyReLU derivatives -- two EAGER runs differ by the
+    # same amount (scripts/diag_determinism.py: 1e-5..1e-4 of max |g| per tensor between identical runs).
+    tol = [1e-6, 3e-4, 3e-3]
+    for a, b, tl in zip(la, lb, tol):
+        assert abs(a - b) <= tl * abs(a), (la, lb)
+    assert la[2] < la[0] and lb[2] < lb[0]
     for (k, pa), (_, pb) in zip(model_a.state_dict().items(), model_b.state_dict().items()):
-        # (parameters whose true gradient is 0 - a bias feeding a BatchNorm - random-walk by +-lr per step
-        # on the sign of rounding noise: bounded by Adam's maximum displacement, 3 steps x lr x 2)
+        # bounded by Adam's maximum displacement: 3 steps x lr x 2 (opposite signs)
         d = float((pb.float() - pa.float()).abs().max())
-        assert rel(pb.float(), pa.float()) <= 2e-2 or float(pa.float().abs().max()) == 0 or d <= 6.5e-3, (k, d)
+        assert rel(pb.float(), pa.float()) <= 2e-2 or float(pa.float().abs().max()) == 0 or d <= 6.5 * lr, (k, d)
 
 
 def test_training_with_dropout_runs_and_is_reproducible():
@@ -189,7 +188,10 @@ def test_training_with_dropout_runs_and_is_reproducible():
         F.manual_seed(7)
         tr = train.VesselTrainer(model, lr=1e-4)
         out.append([float(tr.step(x, m, t, eps)[0]) for _ in range(2)])
-    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(out[0], out[1])), out
+    # same seed -> same dropout masks: step 1 agrees to atomic-ordering noise; step 2 inherits the run-to-run
+    # chaos of the first Adam update (see test_graph_replay_equals_eager), far below the ~1e-2 a different mask costs
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0]), out
+    assert abs(out[0][1] - out[1][1]) <= 2e-4 * abs(out[0][1]), out
     model0, _ = build(H, W, p_drop=0.0)
     l0 = float(train.VesselTrainer(model0, lr=1e-4).step(x, m, t, eps)[0])
     assert abs(out[0][0] - l0) / l0 < 0.2 and out[0][0] != l0
