@@ -22,6 +22,7 @@
 //     TMA ring, one (tap, k-block) per stage;
 //   * epilogue as in conv_tc.cu (TMEM -> registers -> padded smem -> coalesced 128-bit stores with
 //     fused bias / BatchNorm statistics / activation-derivative + BN-backward sums).
+#include <cstdlib>
 #include "common.cuh"
 #include "conv_args.cuh"
 #include "tc_common.cuh"
@@ -34,7 +35,8 @@ constexpr int kHTH = 16, kHTW = 8;                 // q-space tile: 16 rows x 8 
 constexpr int kHMaxSlots = 184;                    // (16+2)*(8+2) = 180, rounded so a half is 23 KiB
 constexpr int kHHalf = kHMaxSlots * 128;           // bytes of one tf32 plane (hi or lo) of an A stage
 constexpr int kHAStage = 2 * kHHalf;
-constexpr int kHNA = 2;                            // A ring depth
+constexpr int kHNA = 2;                            // A ring depth (shared memory)
+constexpr int kHNAT = 4;                           // A ring depth in tensor-memory mode (64 columns per stage)
 constexpr int kHProdWarps = 8;
 constexpr int kHThreads = (kHProdWarps + 2 + 4) * 32;   // + MMA warp + weight-loader warp + 4 epilogue warps
 constexpr int kHItems = (kHMaxSlots * 8 + kHProdWarps * 32 - 1) / (kHProdWarps * 32);   // 16-byte vectors per producer thread
@@ -54,6 +56,7 @@ struct HaloPlan {
   int ph[4], pw[4];           // output offset of each phase
   int pos[4];                 // accumulator position (TMEM column block) of each phase
   int bslot_bytes;            // weight ring slot: 256 * BN * (largest group)
+  int a_tmem;                 // 1: Linear / 1x1 mode with the A operand staged in tensor memory (see the producer)
   HaloPlane plane[4];
 };
 
@@ -85,7 +88,7 @@ __device__ __forceinline__ HTile h_decode(const HaloPlan& p, int t) {
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ HaloPlan p, const int total) {
   extern __shared__ uint8_t dsm_raw[];
-  __shared__ __align__(8) uint64_t s_afull[kHNA], s_aempty[kHNA];
+  __shared__ __align__(8) uint64_t s_afull[kHNAT], s_aempty[kHNAT];
   __shared__ __align__(8) uint64_t s_bfull[4], s_bempty[4];
   __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
@@ -97,8 +100,10 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   const int KB = (a.Cs + 31) >> 5;
   const uint32_t bstage = (uint32_t)p.bslot_bytes;
   const uint32_t acc_cols = (uint32_t)(a.nphase * BN);
+  const uint32_t a_cols = p.a_tmem ? (uint32_t)(kHNAT * 64) : 0u;     // A ring in tensor memory: hi | lo, 32 columns each
+  const int na = p.a_tmem ? kHNAT : kHNA;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
+  while (tmem_cols < 2u * acc_cols + a_cols) tmem_cols <<= 1;
   uint8_t* dsm_gen = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
   const uint32_t dsm = smem_u32(dsm_gen);
   const uint32_t b_base = dsm + kHNA * kHAStage;
@@ -107,7 +112,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   for (int i = tid; i < 512; i += kHThreads) s_stat[i] = 0.0;
   if (warp == kHProdWarps) {
     if (lane == 0) {
-      for (int i = 0; i < kHNA; ++i) { mbar_init(smem_u32(&s_afull[i]), kHProdWarps); mbar_init(smem_u32(&s_aempty[i]), 1); }
+      for (int i = 0; i < kHNAT; ++i) { mbar_init(smem_u32(&s_afull[i]), kHProdWarps); mbar_init(smem_u32(&s_aempty[i]), 1); }
       for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&s_bfull[i]), 1); mbar_init(smem_u32(&s_bempty[i]), 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), 4); }
       mbar_fence_init();
@@ -120,7 +125,70 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  if (warp < kHProdWarps) {
+  if (warp < kHProdWarps && p.a_tmem) {
+    // ============================== A producers, Linear / 1x1 mode: rows -> tensor memory ==============================
+    // With both operands in shared memory a kind::tf32 MMA costs ~96 clk for N <= 128 (operand fetch), with A
+    // in tensor memory 64 clk (scripts/umma_rate.cu) - and a Linear layer has no halo to share between taps,
+    // so nothing is lost by leaving shared memory out: thread = one row of the 128-row tile (TMEM lane), warps
+    // w and w + 4 take channels 0-15 / 16-31 of the k-block, hi and lo planes go to columns [0,32) / [32,64)
+    // of the stage with tcgen05.st.
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_a = tmem + 2u * acc_cols + ((uint32_t)(q * 32) << 16);
+    uint32_t it = 0;
+    T_DECL
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const HTile tl = h_decode(p, t);
+      const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
+      const bool rok = qh < a.Hs && qw < a.Ws;
+      const float* rp = a.src + (((size_t)tl.n * a.Hs + (rok ? qh : 0)) * a.Ws + (rok ? qw : 0)) * a.Cs;
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int c0 = kb * 32 + half * 16;
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rok && c0 + 4 * j < a.Cs) v[j] = __ldg(reinterpret_cast<const float4*>(rp + c0 + 4 * j));
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 x = v[j];
+          const int c = c0 + 4 * j;
+          if (rok && c < a.Cs) {   // padding stays exactly 0
+            if (a.in_affine) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c));
+              float4 ce = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c));
+              x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
+              x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+            }
+            if (a.in_act) {
+              x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope);
+              x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope);
+            }
+          }
+          float4 h4, l4;
+          split4(x, h4, l4);
+          hi[4 * j] = __float_as_uint(h4.x); hi[4 * j + 1] = __float_as_uint(h4.y);
+          hi[4 * j + 2] = __float_as_uint(h4.z); hi[4 * j + 3] = __float_as_uint(h4.w);
+          lo[4 * j] = __float_as_uint(l4.x); lo[4 * j + 1] = __float_as_uint(l4.y);
+          lo[4 * j + 2] = __float_as_uint(l4.z); lo[4 * j + 3] = __float_as_uint(l4.w);
+        }
+        const int slot = it % kHNAT;
+        T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / kHNAT) & 1u) ^ 1u))
+        tc_fence_after();
+        tmem_st16(t_a + (uint32_t)(slot * 64 + half * 16), hi);
+        tmem_st16(t_a + (uint32_t)(slot * 64 + 32 + half * 16), lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_afull[slot]));
+      }
+    }
+    if (tid == 0) T_FLUSH(0, 1)
+  } else if (warp < kHProdWarps) {
     // ============================== A producers: halo tile -> swizzled hi / lo planes ==============================
     const int chunk = tid & 7;
     const int nslots = p.R * p.C;
@@ -208,10 +276,34 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
           const int ksteps = min(32, a.Cs - kb * 32) >> 3;
           for (int pl = 0; pl < p.nplanes; ++pl, ++ita) {
             const HaloPlane& P = p.plane[pl];
-            const int aslot = ita % kHNA;
-            T_WAIT(1, mbar_wait(smem_u32(&s_afull[aslot]), (ita / kHNA) & 1u))
+            const int aslot = ita % na;
+            T_WAIT(1, mbar_wait(smem_u32(&s_afull[aslot]), (ita / na) & 1u))
             tc_fence_after();
             const uint32_t a_hi0 = dsm + (uint32_t)aslot * kHAStage;
+            if (p.a_tmem) {          // one tap, A operand in tensor memory (columns: hi [0,32), lo [32,64) of the stage)
+              const int bslot = itb % NB;
+              T_WAIT(2, mbar_wait(smem_u32(&s_bfull[bslot]), (itb / NB) & 1u))
+              tc_fence_after();
+              const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+              const uint32_t b_hi = b_base + (uint32_t)bslot * bstage;
+              uint64_t dbh = b_desc_hi | (uint64_t)((b_hi & 0x3FFFFu) >> 4);
+              uint64_t dbl = b_desc_hi | (uint64_t)(((b_hi + 128u * (uint32_t)BN) & 0x3FFFFu) >> 4);
+              uint32_t ta_hi = tmem + 2u * acc_cols + (uint32_t)(aslot * 64), ta_lo = ta_hi + 32u;
+              uint32_t accum = started ? 1u : 0u;
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {
+                mma_tf32_ts(d_base, ta_lo, dbh, idesc, accum);
+                mma_tf32_ts(d_base, ta_hi, dbl, idesc, 1u);
+                mma_tf32_ts(d_base, ta_hi, dbh, idesc, 1u);
+                accum = 1u;
+                ta_hi += 8; ta_lo += 8; dbh += 2; dbl += 2;
+              }
+              started = 1u;
+              mma_commit(smem_u32(&s_bempty[bslot]));
+              ++itb;
+              mma_commit(smem_u32(&s_aempty[aslot]));
+              continue;
+            }
             for (int tp = 0; tp < P.ntaps; ++tp, ++itb) {
               const HaloTap tap = P.taps[tp];
               const int bslot = itb % NB;
@@ -569,6 +661,11 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   for (int i = 1; i < g.nphase; ++i)
     if (g.phase[i].Hq != hp.Hq || g.phase[i].Wq != hp.Wq) return 1;
   hp.BN = bn;
+  {  // Linear / 1x1 layers: A operand through tensor memory (CVAE_LIN_TMEM=0 keeps it in shared memory)
+    static const bool lin_tmem = [] { const char* e = getenv("CVAE_LIN_TMEM"); return !(e && e[0] == '0'); }();
+    hp.a_tmem = (lin_tmem && g.wtaps < 2 && hp.nplanes == 1 && g.nphase == 1 && hp.plane[0].ntaps == 1 &&
+                 2 * bn + kHNAT * 64 <= 512) ? 1 : 0;
+  }
   hp.bslot_bytes *= 256 * bn;
   hp.NB = hp.bslot_bytes >= 32768 ? (bn >= 128 ? 3 : 2) : 4;
   if (hp.bslot_bytes == 32768 && bn < 128) hp.NB = 2;
