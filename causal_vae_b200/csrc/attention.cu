@@ -78,23 +78,36 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const float* __restr
   const int lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   float* pg = probs + (size_t)blockIdx.x * S * S;
+  // A lane owns keys 4*lane .. 4*lane + 3 of the row (S <= 128): one Philox4x32 call yields the four
+  // keep decisions (the per-element form spent ~100 instructions of generator per probability: 25 % of
+  // the kernel's instructions in profiles/).
   for (int r = w; r < S; r += nw) {
+    float e[4];
     float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, P[r * lp + j]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * lane + u;
+      e[u] = j < S ? P[r * lp + j] : -INFINITY;
+      mx = fmaxf(mx, e[u]);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int j = lane; j < S; j += 32) { const float e = expf(P[r * lp + j] - mx); P[r * lp + j] = e; sum += e; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { e[u] = (4 * lane + u < S) ? expf(e[u] - mx) : 0.f; sum += e[u]; }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int j = lane; j < S; j += 32) {
-      const float pv = P[r * lp + j] * inv;
-      bool keep = true;
-      if (p_drop > 0.f) {
-        const uint64_t idx = ((uint64_t)blockIdx.x * S + r) * S + j;
-        keep = dropout_keep(seed, offset, idx, p_drop);
+    uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (p_drop > 0.f) rnd = philox4x32(seed, ((uint64_t)blockIdx.x * S + r) * 32 + lane, offset);
+    const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * lane + u;
+      if (j < S) {
+        const float pv = e[u] * inv;
+        const bool keep = p_drop > 0.f ? (float)(rw[u] >> 8) * (1.0f / 16777216.0f) >= p_drop : true;
+        pg[r * S + j] = keep ? pv : -pv;          // sign bit = dropped
+        P[r * lp + j] = keep ? pv * keep_scale : 0.f;
       }
-      pg[r * S + j] = keep ? pv : -pv;          // sign bit = dropped
-      P[r * lp + j] = keep ? pv * keep_scale : 0.f;
     }
   }
   __syncthreads();
