@@ -73,6 +73,8 @@ _SIGS = {
     "cvae_dact_stats": [vp, vp, Xform, vp, vp, i64, i32, vp],
     "cvae_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, f32, vp],
     "cvae_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i32, vp],
+    "cvae_add_layernorm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, vp],
+    "cvae_layernorm_bwd_add": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "cvae_attention_fwd": [vp, vp, vp, i32, i32, i32, i32, f32, u64, u64, vp, vp],
     "cvae_attention_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, u64, vp, vp],
     "cvae_act_fwd": [vp, vp, i64, i32, f32, vp],
@@ -102,6 +104,8 @@ _SIGS = {
     "cvae_bce_fwd": [vp, vp, i64, vp, vp],
     "cvae_bce_bwd": [vp, vp, i64, vp, f32, vp, vp],
     "cvae_finish_scalar": [vp, f32, vp, vp],
+    "cvae_scalar_combine": [vp, vp, vp, vp, f32, f32, f32, f32, vp, vp],
+    "cvae_scalar_scale4": [vp, f32, f32, f32, f32, vp, vp],
     "cvae_argmax_rows": [vp, i64, i32, vp, vp],
     "cvae_one_hot": [vp, i64, i32, vp, vp],
     "cvae_softmax_ce_fwd": [vp, vp, i64, i32, vp, vp],

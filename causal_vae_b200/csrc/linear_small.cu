@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int m = warp * R + r;
-    if (m < M) atomicAdd(a.dst + (size_t)m * a.Cd + n, acc[r] + b);
+    if (m < M) {
+      if (gridDim.y == 1) a.dst[(size_t)m * a.Cd + n] = acc[r] + b;      // single K chunk: plain store, no pre-zeroing
+      else atomicAdd(a.dst + (size_t)m * a.Cd + n, acc[r] + b);
+    }
   }
 }
 
@@ -118,8 +121,8 @@ int launch_linear_small(const GatherArgs& g, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(g.src) & 15) != 0) return 0;
   if (g.in_affine && (((reinterpret_cast<uintptr_t>(g.in_scale) | reinterpret_cast<uintptr_t>(g.in_shift)) & 15) != 0 ||
                       (g.in_center && (reinterpret_cast<uintptr_t>(g.in_center) & 15) != 0))) return 0;
-  if (cudaMemsetAsync(g.dst, 0, sizeof(float) * (size_t)M * g.Cd, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
   const dim3 grid((g.Cd + 31) / 32, (g.Cs + kLsKC - 1) / kLsKC);
+  if (grid.y > 1 && cudaMemsetAsync(g.dst, 0, sizeof(float) * (size_t)M * g.Cd, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
   if (M <= 16) linear_small_kernel<4><<<grid, 128, 0, st>>>(g, (int)M);
   else if (M <= 32) linear_small_kernel<8><<<grid, 128, 0, st>>>(g, (int)M);
   else if (M <= 64) linear_small_kernel<16><<<grid, 128, 0, st>>>(g, (int)M);

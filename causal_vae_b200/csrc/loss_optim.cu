@@ -119,6 +119,21 @@ __global__ void pair_loss_bwd_kernel(const float* __restrict__ a, const float* _
 
 __global__ void finish_scalar_kernel(const double* acc, float mul, float* out) { *out = (float)(*acc * (double)mul); }
 
+// out = sum_i w[i] * x_i for up to 4 device scalars (total loss = recon + beta*kld + lambda*morph + 0.3*sparsity,
+// vessel_analysis/01_train/train.py:82) and its backward g -> (w[i] * g): two launches instead of ~12 ATen ones
+__global__ void scalar_combine_kernel(const float* a, const float* b, const float* c, const float* d, float wa, float wb,
+                                      float wc, float wd, float* out) {
+  float v = wa * *a;
+  if (b) v += wb * *b;
+  if (c) v += wc * *c;
+  if (d) v += wd * *d;
+  *out = v;
+}
+__global__ void scalar_scale4_kernel(const float* g, float wa, float wb, float wc, float wd, float* out4) {
+  const float gv = *g;
+  out4[0] = wa * gv; out4[1] = wb * gv; out4[2] = wc * gv; out4[3] = wd * gv;
+}
+
 // ---- optimizer ---------------------------------------------------------------------------------
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* acc) {
   __shared__ double red[32];
@@ -219,6 +234,19 @@ extern "C" int cvae_bce_bwd(const float* p, const float* y, int64_t n, const flo
 extern "C" int cvae_finish_scalar(const double* acc, float mul, float* out, cvae_stream_t s) {
   if (!acc || !out) return CVAE_ERR_BAD_ARG;
   finish_scalar_kernel<<<1, 1, 0, ST>>>(acc, mul, out);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+extern "C" int cvae_scalar_combine(const float* a, const float* b, const float* c, const float* d, float wa, float wb,
+                                   float wc, float wd, float* out, cvae_stream_t s) {
+  if (!a || !out) return CVAE_ERR_BAD_ARG;
+  scalar_combine_kernel<<<1, 1, 0, ST>>>(a, b, c, d, wa, wb, wc, wd, out);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+extern "C" int cvae_scalar_scale4(const float* g, float wa, float wb, float wc, float wd, float* out4, cvae_stream_t s) {
+  if (!g || !out4) return CVAE_ERR_BAD_ARG;
+  scalar_scale4_kernel<<<1, 1, 0, ST>>>(g, wa, wb, wc, wd, out4);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

@@ -175,6 +175,39 @@ __global__ void col_reduce_kernel(const float* __restrict__ p0, const float* __r
 }
 
 // ---- LayerNorm: one warp per row --------------------------------------------------------------
+// s = a + b (written out) and y = LayerNorm(s) in one pass: the residual add in front of norm2 of a ViT block
+// (vit_backbone.py:44-46).  D <= 1024, contiguous rows.
+__global__ void add_layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ sum, float* __restrict__ y, float* __restrict__ mean,
+                                         float* __restrict__ rstd, int64_t rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* ar = a + row * D;
+  const float* br = b + row * D;
+  float* sr = sum + row * D;
+  float v[32];                                     // D <= 1024
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < D ? ar[i] + br[i] : 0.f;
+    s += v[k];
+  }
+  const float mu = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { const float d = (lane + 32 * k < D) ? v[k] - mu : 0.f; q = fmaf(d, d, q); }
+  const float rs = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int i = lane + 32 * k;
+    if (i < D) { sr[i] = v[k]; y[row * D + i] = (v[k] - mu) * rs * gamma[i] + beta[i]; }
+  }
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+}
+
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean,
                                      float* __restrict__ rstd, int64_t rows, int D, int64_t xs, float eps) {
@@ -240,7 +273,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const float* __r
                                                                 const float* __restrict__ rstd, float* __restrict__ dx,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                 int64_t rows, int D, int64_t xs, int64_t dxs,
-                                                                int accumulate_dx) {
+                                                                int accumulate_dx, const float* __restrict__ dadd = nullptr) {
   extern __shared__ float sm[];  // [2][D]
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
@@ -266,7 +299,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reg_kernel(const float* __r
 #pragma unroll
     for (int k = 0; k < NPL; ++k) {
       if (k < n) {
-        const float v = rs * (d[k] * ga[k] - s1 - xh[k] * s2);
+        float v = rs * (d[k] * ga[k] - s1 - xh[k] * s2);
+        if (dadd != nullptr) v += dadd[row * D + lane + 32 * k];     // gradient arriving at the same tensor by the residual path
         float* o = dx + row * dxs + lane + 32 * k;
         *o = accumulate_dx ? *o + v : v;
         pg[k] = fmaf(d[k], xh[k], pg[k]); pb[k] += d[k];
@@ -426,6 +460,29 @@ extern "C" int cvae_layernorm_fwd(const float* x, const float* gamma, const floa
   if (!x || !gamma || !beta || !y || rows <= 0 || D <= 0) return CVAE_ERR_BAD_ARG;
   const int64_t blocks = (rows + 7) / 8;
   layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(s)>>>(x, gamma, beta, y, mean, rstd, rows, D, xs, eps);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+
+extern "C" int cvae_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* sum,
+                                      float* y, float* mean, float* rstd, int64_t rows, int D, float eps, cvae_stream_t s) {
+  if (!a || !b || !gamma || !beta || !sum || !y || !mean || !rstd || rows <= 0 || D <= 0) return CVAE_ERR_BAD_ARG;
+  if (D > 1024) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  add_layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(s)>>>(a, b, gamma, beta, sum, y, mean, rstd, rows, D, eps);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+
+// dx = LayerNorm-backward(dy) + dadd  (dadd: the gradient reaching the same tensor through the residual connection)
+extern "C" int cvae_layernorm_bwd_add(const float* dy, const float* x, const float* gamma, const float* mean,
+                                      const float* rstd, const float* dadd, float* dx, float* dgamma, float* dbeta,
+                                      int64_t rows, int D, cvae_stream_t s) {
+  if (!dy || !x || !gamma || !mean || !rstd || !dadd || !dx || !dgamma || !dbeta || rows <= 0 || D <= 0) return CVAE_ERR_BAD_ARG;
+  if (D % 32 != 0 || D > 256) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  int64_t blocks = (rows + 15) / 16;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  layernorm_bwd_reg_kernel<8><<<(unsigned)blocks, 256, 2 * D * sizeof(float), as_stream(s)>>>(
+      dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, D, D, D, 0, dadd);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

@@ -297,6 +297,53 @@ def layer_norm(x, gamma, beta, eps):
     return _LayerNorm.apply(x, gamma, beta, float(eps))
 
 
+class _AddLayerNorm(torch.autograd.Function):
+    """(s, y) = (a + b, LayerNorm(a + b)): the residual add in front of a LayerNorm as one kernel; backward adds the
+    gradient reaching `s` through its other consumer inside the LayerNorm-backward kernel (no accumulate launch)."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps):
+        D = a.shape[-1]
+        ac, bc = a.contiguous(), b.contiguous()
+        rows = ac.numel() // D
+        s, y = torch.empty_like(ac), torch.empty_like(ac)
+        mean, rstd = ops.empty(rows, like=ac), ops.empty(rows, like=ac)
+        L.check(L.lib.cvae_add_layernorm_fwd(L.ptr(ac), L.ptr(bc), L.ptr(gamma), L.ptr(beta), L.ptr(s), L.ptr(y),
+                                             L.ptr(mean), L.ptr(rstd), rows, D, float(eps), L.stream()), "add_layernorm_fwd")
+        ctx.save_for_backward(s, gamma, mean, rstd)
+        ctx.params = (gamma, beta)
+        ctx.geom = (rows, D)
+        return s, y
+
+    @staticmethod
+    def backward(ctx, gs, gy):
+        from .chain import direct_ok
+        s, gamma, mean, rstd = ctx.saved_tensors
+        rows, D = ctx.geom
+        pg, pb = ctx.params
+        direct = direct_ok(pg) and direct_ok(pb)
+        dgamma, dbeta = (pg.grad, pb.grad) if direct else (ops.zeros(D, like=s), ops.zeros(D, like=s))
+        if gy is None:
+            return gs, gs, None, None, None
+        gy = gy.contiguous()
+        dx = torch.empty_like(s)
+        if gs is not None and D % 32 == 0 and D <= 256:
+            L.check(L.lib.cvae_layernorm_bwd_add(L.ptr(gy), L.ptr(s), L.ptr(gamma), L.ptr(mean), L.ptr(rstd),
+                                                 L.ptr(gs.contiguous()), L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), rows, D,
+                                                 L.stream()), "layernorm_bwd_add")
+        else:
+            ops.layernorm_bwd(gy, s, gamma, mean, rstd, rows, D, D, dx, D, False, dgamma, dbeta)
+            if gs is not None:
+                dx = ops.add(dx, gs.contiguous())
+        dx = dx.view(s.shape)
+        return dx, dx, (None if direct else dgamma), (None if direct else dbeta), None
+
+
+def add_layer_norm(a, b, gamma, beta, eps):
+    """(a + b, layer_norm(a + b))"""
+    return _AddLayerNorm.apply(a, b, gamma, beta, float(eps))
+
+
 # ---- attention core --------------------------------------------------------------------------------
 class _AttnCore(torch.autograd.Function):
     """qkv [B,S,3D] -> softmax(QK^T/sqrt(d)) V merged over heads [B,S,D] (vit_backbone.py:28-30,43)."""
@@ -548,6 +595,31 @@ def mse_mean(a, b):
 def kld_mean(mu, logvar):
     """-0.5 * mean(1 + logvar - mu^2 - exp(logvar)) (latent_translator/engine.py:26)."""
     return _Kld.apply(mu, logvar, 1.0 / mu.numel())
+
+
+class _WeightedSum(torch.autograd.Function):
+    """sum_i w_i * x_i over up to four 0-dim loss tensors, one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, w, *xs):
+        ctx.w = tuple(float(v) for v in w) + (0.0,) * (4 - len(w))
+        ctx.n = len(xs)
+        ps = [L.ptr(x.contiguous()) for x in xs] + [None] * (4 - len(xs))
+        out = torch.empty((), dtype=torch.float32, device=xs[0].device)
+        L.check(L.lib.cvae_scalar_combine(ps[0], ps[1], ps[2], ps[3], *ctx.w, L.ptr(out), L.stream()), "scalar_combine")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out4 = torch.empty(4, dtype=torch.float32, device=g.device)
+        L.check(L.lib.cvae_scalar_scale4(L.ptr(g.contiguous()), *ctx.w, L.ptr(out4), L.stream()), "scalar_scale4")
+        return (None, *[out4[i] for i in range(ctx.n)])
+
+
+def weighted_sum(xs, ws):
+    """sum_i ws[i] * xs[i] for 0-dim CUDA tensors (at most four)."""
+    assert 1 <= len(xs) <= 4 and len(xs) == len(ws)
+    return _WeightedSum.apply(tuple(ws), *xs)
 
 
 # ---- treatment labels -------------------------------------------------------------------------------

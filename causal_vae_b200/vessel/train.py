@@ -25,6 +25,8 @@ def loss_function(recon_x, x, m_hat, m, mu, logvar, m_mu, m_logvar):
 def total_loss(recon, kld, morph, sparsity, beta=None, lambda_morph=1.0):
     """train.py:82 (lambda_morph = 1) / train_kfold.py:71 (lambda_morph = CONFIG['LAMBDA_MORPH'])."""
     beta = CONFIG["BETA"] if beta is None else beta
+    if all(torch.is_tensor(v) and v.is_cuda and v.dim() == 0 for v in (recon, kld, morph, sparsity)):
+        return F.weighted_sum((recon, kld, morph, sparsity), (1.0, beta, lambda_morph, 0.3))   # one kernel each way
     return recon + beta * kld + lambda_morph * morph + 0.3 * sparsity
 
 

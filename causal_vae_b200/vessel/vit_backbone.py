@@ -30,11 +30,11 @@ class ViTBlock(tnn.Module):
     def forward(self, x):
         q = self.norm1(x)
         attn_out, _ = self.attn(q, q, q)
-        x = F.add(x, attn_out)
+        x, n2 = F.add_layer_norm(x, attn_out, self.norm2.weight, self.norm2.bias, self.norm2.eps)   # residual + norm2
         # mlp = Linear, GELU, Dropout, Linear, Dropout (vit_backbone.py:31-37) with GELU+Dropout and
         # Dropout+residual each fused into one kernel (same masks: the random stream is consumed in the same order)
         lin1, act, drop1, lin2, drop2 = self.mlp[0], self.mlp[1], self.mlp[2], self.mlp[3], self.mlp[4]
-        h = F.act_dropout(lin1(self.norm2(x)), L.ACT_GELU, drop1.p, drop1.training)
+        h = F.act_dropout(lin1(n2), L.ACT_GELU, drop1.p, drop1.training)
         return F.dropout_add(lin2(h), x, drop2.p, drop2.training)
 
 

@@ -216,6 +216,14 @@ int cvae_layernorm_bwd(const float* dy, const float* x, const float* gamma, cons
                        const float* rstd, float* dx, float* dgamma, float* dbeta, int64_t rows, int D,
                        int64_t x_row_stride, int64_t dx_row_stride, int accumulate_dx,
                        cvae_stream_t s);
+/* Residual add fused with the LayerNorm that follows it (x = x + attn(...); mlp(norm2(x)), vit_backbone.py:44-46):
+ * sum = a + b, y = LayerNorm(sum); backward: dx = LayerNorm-backward(dy) + dadd (dadd = gradient of `sum` from its
+ * other consumer), dgamma / dbeta accumulated.  D % 32 == 0, D <= 256 for the backward form. */
+int cvae_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* sum,
+                           float* y, float* mean, float* rstd, int64_t rows, int D, float eps, cvae_stream_t s);
+int cvae_layernorm_bwd_add(const float* dy, const float* x, const float* gamma, const float* mean,
+                           const float* rstd, const float* dadd, float* dx, float* dgamma, float* dbeta,
+                           int64_t rows, int D, cvae_stream_t s);
 
 /* ---- multi-head self-attention core (nn.MultiheadAttention; vit_backbone.py:28-30,43) --------
  * qkv: [B, S, 3*D] packed projections; out: [B, S, D]; probs: [B, H, S, S] saved softmax.
@@ -307,6 +315,11 @@ int cvae_bce_bwd(const float* p, const float* y, int64_t n, const float* g, floa
                  cvae_stream_t s);
 /* double accumulator -> float scalar (optionally scaled) */
 int cvae_finish_scalar(const double* acc, float mul, float* out, cvae_stream_t s);
+/* out = wa*a + wb*b + wc*c + wd*d over device scalars (b, c, d may be NULL): the weighted total loss
+ * (train.py:82); scale4: out4[i] = w_i * g, its backward. */
+int cvae_scalar_combine(const float* a, const float* b, const float* c, const float* d, float wa, float wb,
+                        float wc, float wd, float* out, cvae_stream_t s);
+int cvae_scalar_scale4(const float* g, float wa, float wb, float wc, float wd, float* out4, cvae_stream_t s);
 
 /* ---- treatment labels: argmax / one-hot (integer, bit-exact) and softmax losses on [rows, T] logits -----
  * torch.argmax(t, dim=1) (first maximum; mnist_test/01_baseline_causal_vae/train.py:38),
