@@ -70,6 +70,8 @@ _SIGS = {
     "cvae_bn_bwd_finalize": [vp, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "cvae_affine_act": [vp, Xform, vp, Xform, vp, i64, i32, vp],
     "cvae_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
+    "cvae_bn_bwd_fused_ok": [i32],
+    "cvae_bn_bwd": [vp, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "cvae_dact_stats": [vp, vp, Xform, vp, vp, i64, i32, vp],
     "cvae_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, f32, vp],
     "cvae_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i32, vp],

@@ -219,11 +219,9 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
         if rec.mean is None:
             raise NotImplementedError("backward through eval-mode BatchNorm is not supported")
         outs = tuple(p.grad if direct_ok(p) else None for p in (u.bn.weight, u.bn.bias, u.mod.bias))
-        ca, cb, cc, dgamma, dbeta, dbias = ops.bn_bwd_finalize(stats, Cd, N * Hd * Wd, u.bn.weight, rec.mean,
-                                                               rec.rstd, has_bias, outs)
+        dy, dgamma, dbeta, dbias = ops.bn_bwd(dz, y, stats, N * Hd * Wd, u.bn.weight, rec.mean, rec.rstd, has_bias, outs)
         dgamma, dbeta = (None if o is not None else g for o, g in zip(outs[:2], (dgamma, dbeta)))
         dbias = None if outs[2] is not None else dbias
-        dy = ops.bn_bwd_apply(dz, y, ca, cb, cc, rec.mean)
     else:
         dy = dz
         dgamma = dbeta = None

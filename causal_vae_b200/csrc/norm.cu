@@ -129,6 +129,43 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
   }
 }
 
+// bn_bwd_finalize + bn_bwd_apply in one launch (C <= 512, C % 4 == 0): every block derives the per-channel
+// coefficients from the statistics into shared memory (2 C doubles from L2), block 0 also writes
+// dgamma / dbeta / dbias; then the stream pass.  One launch less per BatchNorm on the backward critical path.
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+                                                           const double* __restrict__ stats, double count,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, float* __restrict__ out,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ dbias_pre, int64_t total, int C) {
+  __shared__ __align__(16) float sA[512], sB[512], sC[512], sM[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double sdz = stats[c], sdzc = stats[C + c];
+    const double rs = rstd[c], g = gamma ? (double)gamma[c] : 1.0;
+    const double sdzxh = rs * sdzc;
+    const double k1 = sdz / count, k2 = sdzxh / count;
+    sA[c] = (float)(g * rs); sB[c] = (float)(-g * rs * rs * k2); sC[c] = (float)(-g * rs * k1); sM[c] = mean[c];
+    if (blockIdx.x == 0) {
+      if (dgamma) dgamma[c] = (float)sdzxh;
+      if (dbeta) dbeta[c] = (float)sdz;
+      if (dbias_pre) dbias_pre[c] = 0.f;     // a bias feeding a training-mode BatchNorm has an exactly zero gradient
+    }
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, n4 = total >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = (int)((i << 2) % C);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dz) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);
+    const float4 A = *reinterpret_cast<const float4*>(sA + c), B = *reinterpret_cast<const float4*>(sB + c);
+    const float4 Cc = *reinterpret_cast<const float4*>(sC + c), Mu = *reinterpret_cast<const float4*>(sM + c);
+    float4 o;
+    o.x = fmaf(A.x, d.x, fmaf(B.x, v.x - Mu.x, Cc.x)); o.y = fmaf(A.y, d.y, fmaf(B.y, v.y - Mu.y, Cc.y));
+    o.z = fmaf(A.z, d.z, fmaf(B.z, v.z - Mu.z, Cc.z)); o.w = fmaf(A.w, d.w, fmaf(B.w, v.w - Mu.w, Cc.w));
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
 // column statistics of a [rows, C] matrix.  Block (32 x 8): threadIdx.x -> column, threadIdx.y
 // strides rows; MODE 0: (sum y, sum y^2); MODE 1: dz = g*act'(xform(ref)) written out, (sum dz, sum dz*ref);
 // MODE 2: plain column sum into a float output.
@@ -404,6 +441,21 @@ extern "C" int cvae_bn_bwd_apply(const float* dz, const float* y, const float* c
   const int64_t total = rows * C;
   bn_bwd_apply_kernel<<<stream_blocks((C & 3) == 0 ? total / 4 : total), 256, 0, as_stream(s)>>>(dz, y, ca, cb, cc,
                                                                                                  mean, out, total, C);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+
+// 1 when cvae_bn_bwd covers the shape (otherwise use cvae_bn_bwd_finalize + cvae_bn_bwd_apply)
+extern "C" int cvae_bn_bwd_fused_ok(int C) { return (C <= 512 && (C & 3) == 0) ? 1 : 0; }
+
+extern "C" int cvae_bn_bwd(const float* dz, const float* y, const double* stats, double count, const float* gamma,
+                           const float* mean, const float* rstd, float* out, float* dgamma, float* dbeta,
+                           float* dbias_pre, int64_t rows, int C, cvae_stream_t s) {
+  if (!dz || !y || !stats || !mean || !rstd || !out || rows <= 0 || count <= 0) return CVAE_ERR_BAD_ARG;
+  if (!cvae_bn_bwd_fused_ok(C)) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  const int64_t total = rows * C;
+  bn_bwd_fused_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(s)>>>(dz, y, stats, count, gamma, mean, rstd, out,
+                                                                           dgamma, dbeta, dbias_pre, total, C);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

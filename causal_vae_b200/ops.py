@@ -263,6 +263,25 @@ def bn_bwd_finalize(stats, C, count, gamma, mean, rstd, want_dbias, outs=(None, 
     return ca, cb, cc, dg, db, dbias
 
 
+def bn_bwd(dz, y, stats, count, gamma, mean, rstd, want_dbias, outs=(None, None, None)):
+    """BatchNorm backward in one launch: returns (dy, dgamma, dbeta, dbias); falls back to finalize + apply for
+    shapes the fused kernel does not cover.  outs as in bn_bwd_finalize."""
+    C = y.shape[-1]
+    if not L.lib.cvae_bn_bwd_fused_ok(int(C)):
+        ca, cb, cc, dg, db, dbias = bn_bwd_finalize(stats, C, count, gamma, mean, rstd, want_dbias, outs)
+        return bn_bwd_apply(dz, y, ca, cb, cc, mean), dg, db, dbias
+    dg = outs[0] if outs[0] is not None else empty(C, like=mean)
+    db = outs[1] if outs[1] is not None else empty(C, like=mean)
+    dbias = None
+    if want_dbias:
+        dbias = outs[2] if outs[2] is not None else empty(C, like=mean)
+    out = torch.empty_like(y)
+    rows = y.numel() // C
+    L.check(L.lib.cvae_bn_bwd(L.ptr(dz), L.ptr(y), L.ptr(stats), float(count), L.ptr(gamma), L.ptr(mean), L.ptr(rstd),
+                              L.ptr(out), L.ptr(dg), L.ptr(db), L.ptr(dbias), rows, C, L.stream()), "bn_bwd")
+    return out, dg, db, dbias
+
+
 def affine_act(a, xa, b=None, xb=IDENT, out=None):
     C = a.shape[-1]
     rows = a.numel() // C

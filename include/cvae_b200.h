@@ -201,6 +201,12 @@ int cvae_affine_act(const float* a, cvae_xform_t xa, const float* b, cvae_xform_
 int cvae_bn_bwd_apply(const float* dz, const float* y, const float* ca, const float* cb,
                       const float* cc, const float* mean, float* out, int64_t rows, int C,
                       cvae_stream_t s);
+/* cvae_bn_bwd_finalize + cvae_bn_bwd_apply as one launch (C <= 512, C % 4 == 0): out = BatchNorm-backward of dz
+ * given the producer's raw output y and the sums in `stats`; dgamma / dbeta / dbias_pre [C] may be NULL. */
+int cvae_bn_bwd_fused_ok(int C);
+int cvae_bn_bwd(const float* dz, const float* y, const double* stats, double count, const float* gamma,
+                const float* mean, const float* rstd, float* out, float* dgamma, float* dbeta,
+                float* dbias_pre, int64_t rows, int C, cvae_stream_t s);
 /* dz = g * act'(xform(ref)); stats += (sum dz, sum dz*ref)  — the CVAE_EPI_DACT epilogue as a
  * standalone pass. */
 int cvae_dact_stats(const float* g, const float* ref, cvae_xform_t x, float* dz, double* stats,
