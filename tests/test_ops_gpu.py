@@ -359,6 +359,59 @@ def test_dropout_statistics():
     assert torch.equal((x.grad != 0), (y != 0)), "backward must regenerate the same mask"
 
 
+def test_head_backward_fused_vs_separate_kernels_and_fp64():
+    """cvae_head_bwd (weight + input gradient of the Conv 16->1 image head in one pass) against fp64 torch and
+    against the separate weight-gradient / input-gradient kernels it replaces."""
+    from causal_vae_b200 import _lib as L
+    from causal_vae_b200 import ops
+    N, H, W, C = 5, 120, 112, 16                       # ragged 8 x 32 patches
+    assert ops.head_bwd_eligible(N, H, W, C)
+    y = gen(N, H, W, C, seed=60)
+    g = gen(N, H, W, 1, seed=61)
+    w = gen(1, C, 3, 3, seed=62) * 0.2
+    scale, shift, center = gen(C, seed=63).abs() + 0.5, gen(C, seed=64), gen(C, seed=65)
+    xf = ops.XF(scale.cuda(), shift.cuda(), 0.01, center.cuda())
+    stats = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    dw = torch.empty(1, C, 3, 3, device="cuda")
+    dz = ops.head_bwd(g.cuda(), y.cuda(), xf, w.cuda(), dw, stats)
+    # fp64 reference
+    yr = y.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    z = (yr - center.double().view(1, C, 1, 1)) * scale.double().view(1, C, 1, 1) + shift.double().view(1, C, 1, 1)
+    a = torch.where(z > 0, z, z * 0.01)
+    out = torch.nn.functional.conv2d(a, wr, None, 1, 1)
+    out.backward(g.double().permute(0, 3, 1, 2))
+    # dz is the gradient w.r.t. the pre-activation z (the BatchNorm-backward factor `scale` is applied later)
+    want_dz = (yr.grad / scale.double().view(1, C, 1, 1)).permute(0, 2, 3, 1)
+    assert_close(dz, want_dz, GRAD_TOL, "head dz")
+    assert_close(dw, wr.grad, GRAD_TOL, "head dW")
+    refc = (y.double() - center.double())
+    want_st = torch.cat([want_dz.sum((0, 1, 2)), (want_dz * refc).sum((0, 1, 2))])
+    assert rel(stats, want_st) <= 1e-5, rel(stats, want_st)
+
+
+def test_batched_weight_packing_equals_per_use_packing():
+    """ops.PackPlan: the one-launch re-pack reproduces every per-use layout bit for bit after the weights change."""
+    from causal_vae_b200 import ops
+    ws = [gen(64, 32, 9, seed=70).cuda(), gen(48, 16, 1, seed=71).cuda(), gen(16, 16, 9, seed=72).cuda()]
+    args = [(32, 32, 64, 9, True, 32, True), (48, 48, 16, 1, False, 16, True), (16, 16, 16, 9, False, 16, False)]
+    plan = ops.PackPlan()
+    ops.set_pack_plan(plan)
+    try:
+        first = [ops.pack_weight(w, *a[:6], tc=a[6]) for w, a in zip(ws, args)]
+        plan.finalize()
+        for w in ws:
+            w.mul_(1.7).add_(0.3)                       # "optimizer step"
+        plan.run()
+        cached = [ops.pack_weight(w, *a[:6], tc=a[6]) for w, a in zip(ws, args)]
+    finally:
+        ops.set_pack_plan(None)
+    fresh = [ops.pack_weight(w, *a[:6], tc=a[6]) for w, a in zip(ws, args)]
+    for c, f, o in zip(cached, fresh, first):
+        assert c.data_ptr() == o.data_ptr()             # the plan's own buffer, re-packed in place
+        assert torch.equal(c, f)
+
+
 def test_fused_dropout_forms_draw_the_same_mask():
     """dropout(gelu(x)) and res + dropout(x) as single kernels: same values and gradients as the unfused
     sequence at the same point of the random stream (fusing must change launches, not masks)."""
