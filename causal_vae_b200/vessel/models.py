@@ -63,7 +63,11 @@ class CausalViTVAE(tnn.Module):
 
     def decode(self, m, z):
         """backbone.decode(dec_adapter(cat[m, z])) — m first (models.py:299-305)."""
-        return self.backbone.decode(self.dec_adapter(F.cat_pad([m, z])))
+        h = self.dec_adapter(F.cat_pad([m, z]))
+        hook = getattr(self, "_decoder_grad_hook", None)
+        if hook is not None and h.requires_grad:
+            h.register_hook(hook)      # fires when the whole decoder's backward has been enqueued (data-parallel overlap)
+        return self.backbone.decode(h)
 
     def forward(self, x, m, t, eps=None):
         mu, logvar, z = self.encode(x, m, t, eps)

@@ -1,0 +1,39 @@
+"""torchrun --nproc-per-node 2 scripts/check_dp_overlap.py: the flat gradient after one data-parallel step with the
+overlapped (decoder-first) all-reduce equals the single-collective result, and both equal the sum of the two ranks'
+local gradients."""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import cvae_oracle as O
+from causal_vae_b200.vessel import models, train
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+H = W = 64; B = 4
+models.CONFIG["IMG_HEIGHT"], models.CONFIG["IMG_WIDTH"] = H, W
+sd = O.fill_state_dict(O.vessel_shapes(H, W), seed=0)
+x, m, t, eps = (a.cuda() for a in O.vessel_inputs(B, H, W, seed=rank))
+res = {}
+for mode in ("local", "single", "overlap"):
+    os.environ["CVAE_DP_OVERLAP"] = "1" if mode == "overlap" else "0"
+    model = models.CausalViTVAE(); model.load_state_dict(sd); model = model.cuda()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout): mod.p = 0.0
+        if hasattr(mod, "in_proj_weight"): mod.dropout = 0.0
+    tr = train.VesselTrainer(model, lr=1e-4, distributed=(mode != "local"))
+    tr.model.train()
+    tr._fwd_bwd(x, m, t, eps)
+    tr._allreduce()
+    torch.cuda.synchronize()
+    res[mode] = tr.flat.grad.clone()
+    assert (mode == "overlap") == (tr.comm is not None), (mode, tr.comm)
+summed = res["local"].clone()
+dist.all_reduce(summed)
+mx = summed.abs().max().item()
+e1 = (res["single"] - summed).abs().max().item() / mx
+e2 = (res["overlap"] - summed).abs().max().item() / mx
+e3 = (res["overlap"] - res["single"]).abs().max().item() / mx
+print(f"rank {rank}: single vs sum {e1:.2e}  overlap vs sum {e2:.2e}  overlap vs single {e3:.2e}", flush=True)
+# three separate forward/backward runs: run-to-run chaos of identical runs reaches ~1e-4 of max |g| (diag_determinism.py)
+assert e1 < 1e-3 and e2 < 1e-3, (e1, e2)
+dist.barrier()
+os._exit(0)
