@@ -455,6 +455,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             esh = __ldg(reinterpret_cast<const float4*>(a.e_shift + col));
             if (a.e_center != nullptr) ece = __ldg(reinterpret_cast<const float4*>(a.e_center + col));
           }
+          float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};   // fp32 partial sums of this chunk's <= 8 rows
           for (int p0 = 0; p0 < cgs; p0 += 4) {     // 4 rows per batch: their global loads overlap
             int o[4];
             float4 r4[4], d4[4];
@@ -475,7 +476,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
               float x[4] = {t4.x + bias.x, t4.y + bias.y, t4.z + bias.z, t4.w + bias.w};
               if (a.epi == CVAE_EPI_STATS) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { s1[j] += (double)x[j]; s2[j] += (double)x[j] * (double)x[j]; }
+                for (int j = 0; j < 4; ++j) { f1[j] += x[j]; f2[j] = fmaf(x[j], x[j], f2[j]); }
               } else if (a.epi == CVAE_EPI_DACT) {
                 const float refc[4] = {r4[u].x - ece.x, r4[u].y - ece.y, r4[u].z - ece.z, r4[u].w - ece.w};
                 x[0] += d4[u].x; x[1] += d4[u].y; x[2] += d4[u].z; x[3] += d4[u].w;
@@ -484,11 +485,15 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   x[j] = z[j] > 0.f ? x[j] : x[j] * a.e_slope;
-                  s1[j] += (double)x[j]; s2[j] += (double)x[j] * (double)refc[j];
+                  f1[j] += x[j]; f2[j] = fmaf(x[j], refc[j], f2[j]);
                 }
               }
               *reinterpret_cast<float4*>(a.dst + (size_t)o[u] * a.Cd + col) = make_float4(x[0], x[1], x[2], x[3]);
             }
+          }
+          if (want_stats) {                         // fold the chunk's fp32 partials into the fp64 running sums
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1[j] += (double)f1[j]; s2[j] += (double)f2[j]; }
           }
           if (want_stats && !reg_stats) reduce_stats(tl.n0 + ch * 32);   // its barriers also free the staging tile
           else if (nbuf == 1) hbar_sync(1, 128);                         // single staging tile: free it for reuse
