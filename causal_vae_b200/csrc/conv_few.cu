@@ -135,19 +135,37 @@ convt16_up_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ 
       sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + s4 * 4));
       if (a.in_center) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + s4 * 4));
     }
-    for (int idx = tid; idx < kUpPix * 4; idx += kFewThreads) {
-      const int pix = idx >> 2, gi = pix / kUpGC, gj = pix - gi * kUpGC, ih = h0 + gi, iw = w0 + gj;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ih < a.Hs && iw < a.Ws) {
-        v = __ldg(reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * 16 + s4 * 4));
-        if (a.in_affine) {
-          v.x = fmaf(v.x - ce.x, sc.x, sh.x); v.y = fmaf(v.y - ce.y, sc.y, sh.y);
-          v.z = fmaf(v.z - ce.z, sc.z, sh.z); v.w = fmaf(v.w - ce.w, sc.w, sh.w);
+    {   // 297 x 4 vectors = at most 5 per thread: all loads issued before the first store
+      float4 v[5];
+      int pixs[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int idx = tid + u * kFewThreads;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pixs[u] = -1;
+        if (idx < kUpPix * 4) {
+          const int pix = idx >> 2, gi = pix / kUpGC, gj = pix - gi * kUpGC, ih = h0 + gi, iw = w0 + gj;
+          pixs[u] = pix;
+          if (ih < a.Hs && iw < a.Ws) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * 16 + s4 * 4));
+            pixs[u] |= 1 << 30;                       // valid pixel: the transform applies (padding stays exactly 0)
+          }
         }
-        if (a.in_act) { v.x = lrelu(v.x, a.in_slope); v.y = lrelu(v.y, a.in_slope); v.z = lrelu(v.z, a.in_slope); v.w = lrelu(v.w, a.in_slope); }
       }
-      float* d = sX + (s4 * 4) * kUpPlane + pix;
-      d[0] = v.x; d[kUpPlane] = v.y; d[2 * kUpPlane] = v.z; d[3 * kUpPlane] = v.w;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        if (pixs[u] < 0) continue;
+        float4 x = v[u];
+        if (pixs[u] & (1 << 30)) {
+          if (a.in_affine) {
+            x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
+            x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+          }
+          if (a.in_act) { x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope); x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope); }
+        }
+        float* d = sX + (s4 * 4) * kUpPlane + (pixs[u] & ~(1 << 30));
+        d[0] = x.x; d[kUpPlane] = x.y; d[2 * kUpPlane] = x.z; d[3 * kUpPlane] = x.w;
+      }
     }
     __syncthreads();
     float acc[4][4][4];
@@ -264,29 +282,48 @@ conv16_dn_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ D
         for (int c = 0; c < 4; ++c) acc[r][p][c] = 0.f;
     for (int hc = 0; hc < 2; ++hc) {
       __syncthreads();                               // previous pass's readers are done (also orders the sW fill)
-      for (int idx = tid; idx < kDnGR * kDnGC; idx += kFewThreads) {
-        const int gi = idx / kDnGC, gj = idx - gi * kDnGC, ih = 2 * h0 - 1 + gi, iw = 2 * w0 - 1 + gj;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if ((unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws) {
-          const float4* sp = reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * 16 + hc * 8);
-          const float4 v0 = __ldg(sp), v1 = __ldg(sp + 1);
-          v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-          if (a.in_affine) {
+      // Batches of 4 pixels per thread with all 8 loads issued before the first store: the one-pixel-at-a-time
+      // loop paid a full global round trip per iteration (26 % of the stall samples in profiles/r1_ncu_few_raw.txt).
+      for (int idx0 = tid; idx0 < kDnGR * kDnGC; idx0 += 4 * kFewThreads) {
+        float4 v0[4], v1[4];
+        int dofs[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int c = hc * 8 + k;
-              const float cen = a.in_center ? __ldg(a.in_center + c) : 0.f;
-              v[k] = fmaf(v[k] - cen, __ldg(a.in_scale + c), __ldg(a.in_shift + c));
+        for (int u = 0; u < 4; ++u) {
+          const int idx = idx0 + u * kFewThreads;
+          v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
+          dofs[u] = -1;
+          if (idx < kDnGR * kDnGC) {
+            const int gi = idx / kDnGC, gj = idx - gi * kDnGC, ih = 2 * h0 - 1 + gi, iw = 2 * w0 - 1 + gj;
+            dofs[u] = gi * kDnPitch + dn_col(gj);
+            if ((unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws) {
+              const float4* sp = reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * 16 + hc * 8);
+              v0[u] = __ldg(sp); v1[u] = __ldg(sp + 1);
+              dofs[u] |= 1 << 30;                     // valid pixel: the transform applies (padding stays exactly 0)
             }
           }
-          if (a.in_act) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = lrelu(v[k], a.in_slope);
-          }
         }
-        float* d = sX + gi * kDnPitch + dn_col(gj);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[k * kDnPlane] = v[k];
+        for (int u = 0; u < 4; ++u) {
+          if (dofs[u] < 0) continue;
+          float v[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+          if (dofs[u] & (1 << 30)) {
+            if (a.in_affine) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int c = hc * 8 + k;
+                const float cen = a.in_center ? __ldg(a.in_center + c) : 0.f;
+                v[k] = fmaf(v[k] - cen, __ldg(a.in_scale + c), __ldg(a.in_shift + c));
+              }
+            }
+            if (a.in_act) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = lrelu(v[k], a.in_slope);
+            }
+          }
+          float* d = sX + (dofs[u] & ~(1 << 30));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k * kDnPlane] = v[k];
+        }
       }
       __syncthreads();
 #pragma unroll 1
