@@ -53,6 +53,42 @@ def counterfactual_sweep(model, m, z, delta=5.0, value=None, return_images=False
     return l2, (x_cf if return_images else None), base
 
 
+@torch.no_grad()
+def feature_importance(model, m, z, delta=1.0):
+    """Visual sensitivity of every concept: mean over samples of ||decode(m + delta*e_k, z) - decode(m, z)||_2
+    (vessel_analysis/03_evaluate_vessel/analyze_vessel.py:68-115, which perturbs by +1 sigma on random (m, z)).
+    One batched sweep instead of K decodes; returns [K]."""
+    l2, _, _ = counterfactual_sweep(model, m, z, delta=delta)
+    return l2.mean(dim=0)
+
+
+@torch.no_grad()
+def mediation_decomposition(model, m_a, z_a, m_b, z_b):
+    """How much of the visual difference between (m_a, z_a) and (m_b, z_b) is carried by the measured concepts M, by
+    the unmeasured style Z, and by each single concept (mnist_test/05_feature_analysis/analyze_mediation.py:128-173,
+    batched over S pairs and written for any model with .decode(m, z)):
+
+        total   = ||dec(m_b, z_b) - dec(m_a, z_a)||
+        m_pct   = 100 * ||dec(m_b, z_a) - base|| / total          (all of M swapped, Z held)
+        z_pct   = 100 * ||dec(m_a, z_b) - base|| / total          (Z swapped, M held)
+        k_pct_k = 100 * ||dec(m_a with m_a[k] := m_b[k], z_a) - base|| / total
+
+    All (K + 3) * S counterfactual rows go through ONE decode; the norms are reduced on device.
+    Returns dict(total [S], m_pct [S], z_pct [S], feature_pct [S, K])."""
+    S, K = m_a.shape
+    eye = torch.eye(K, device=m_a.device, dtype=torch.bool)
+    m_feat = torch.where(eye.unsqueeze(0), m_b.unsqueeze(1), m_a.unsqueeze(1))            # [S, K, K]: row k swaps concept k
+    m_rows = torch.cat([m_b.unsqueeze(1), m_b.unsqueeze(1), m_a.unsqueeze(1), m_feat], dim=1)   # target, M-swap, Z-swap, K swaps
+    z_rows = torch.cat([z_b.unsqueeze(1), z_a.unsqueeze(1), z_b.unsqueeze(1), z_a.unsqueeze(1).expand(S, K, -1)], dim=1)
+    G = K + 3
+    base = model.decode(m_a.contiguous(), z_a.contiguous())
+    x = model.decode(m_rows.reshape(S * G, K).contiguous(), z_rows.reshape(S * G, -1).contiguous())
+    d = rowdiff_l2(x, base, G).view(S, G)
+    total = d[:, 0] + 1e-9
+    return {"total": d[:, 0], "m_pct": 100.0 * d[:, 1] / total, "z_pct": 100.0 * d[:, 2] / total,
+            "feature_pct": 100.0 * d[:, 3:] / total.unsqueeze(1)}
+
+
 class CounterfactualEngine:
     """High-throughput form of counterfactual_sweep for a frozen model: the whole sweep of one chunk of
     sources (base decode, do() scatter, decode of chunk*K rows, per-image L2) is captured once in a CUDA
