@@ -223,3 +223,40 @@ class VesselTrainer:
     def replay(self):
         self.graph.replay()
         return self.static_losses
+
+
+# ---- epoch loops with the reference's names (vessel_analysis/01_train/train.py:62-133) ------------------------------
+def train_one_epoch(vae, train_loader, optimizer, epoch=0, device=None):
+    """train.py:62-98.  `optimizer` is a VesselTrainer (fused step); returns the epoch loss per sample.  Unlike the
+    reference the running totals stay on the device: one host synchronisation per epoch, not one per batch."""
+    trainer = optimizer
+    if not isinstance(trainer, VesselTrainer):
+        raise RuntimeError("train_one_epoch needs a VesselTrainer (fused clip + Adam); wrap the model with VesselTrainer(vae)")
+    dev = trainer.flat.data.device if device is None else device
+    total = torch.zeros((), device=dev)
+    n = 0
+    for x, m, t in train_loader:
+        losses = trainer.step(x.to(dev, non_blocking=True), m.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
+        total += losses[0].detach()
+        n += x.shape[0]
+    return float(total) / max(n, 1)
+
+
+@torch.no_grad()
+def validate(vae, val_loader, device=None):
+    """train.py:100-133: eval-mode forward + the four loss terms over a loader; returns the validation loss per
+    sample (recon + BETA * kld + morph + 0.3 * sparsity).  validate.breakdown holds the per-sample recon / kld /
+    morph averages the reference prints."""
+    vae.eval()
+    dev = next(vae.parameters()).device if device is None else device
+    tot = torch.zeros(4, device=dev)
+    n = 0
+    for x, m, t in val_loader:
+        x, m, t = (a.to(dev, non_blocking=True) for a in (x, m, t))
+        out = vae(x, m, t)
+        recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
+        tot += torch.stack([total_loss(recon, kld, morph, sp), recon, kld, morph])
+        n += x.shape[0]
+    vals = (tot / max(n, 1)).tolist()
+    validate.breakdown = {"recon": vals[1], "kld": vals[2], "morph": vals[3]}
+    return vals[0]
