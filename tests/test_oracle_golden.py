@@ -141,3 +141,36 @@ def test_mnist_oracle(tag):
     close(ld, g["loss_d"])
     for k, s in g["disc_grads"].items():
         check_summary(D[k].grad, s, rtol=1e-4, what="dgrad." + k)
+
+
+def test_ridge_loocv_translator_matches_live_reference():
+    """latent_translator/analysis.py::fit_translator_ridge (sklearn Ridge + LeaveOneOut) replayed by the batched
+    closed-form solve, against outputs of the live reference (tests/golden/make_ridge_golden.py).  The module is
+    loaded by path: it is pure torch and needs no CUDA library."""
+    import importlib.util
+    import json
+    import os
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "ridge_loocv.json")) as f:
+        gold = json.load(f)
+    spec = importlib.util.spec_from_file_location(
+        "lt_analysis", os.path.join(here, "..", "causal_vae_b200", "latent_translator", "analysis.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(gold["seed"])
+    N, D, Fm = gold["N"], gold["D"], gold["F"]
+    Z = rng.standard_normal((N, D)).astype(np.float32)
+    Wtrue = rng.standard_normal((D, Fm)) * 0.05
+    M = (Z @ Wtrue + 0.1 * rng.standard_normal((N, Fm)) + np.array([1.0, -2.0, 0.5, 0.0, 3.0, -1.0])).astype(np.float32)
+    names = [f"f{j}" for j in range(Fm)]
+    model, metrics, Mhat, W = mod.fit_translator_ridge(Z, M, feature_names=names, alpha=gold["alpha"])
+    want = {r["feature"]: r for r in gold["metrics"]}
+    for r in metrics.to_dict(orient="records"):
+        assert abs(r["r2"] - want[r["feature"]]["r2"]) <= 1e-4, r
+        assert abs(r["corr"] - want[r["feature"]]["corr"]) <= 1e-4, r
+    assert list(metrics["feature"]) == [r["feature"] for r in gold["metrics"]]          # same ranking
+    assert np.abs(Mhat - np.array(gold["Mhat"])).max() <= 1e-4 * np.abs(np.array(gold["Mhat"])).max()
+    assert np.abs(W[:, ::37] - np.array(gold["W_sample"])).max() <= 1e-4 * gold["W_absmax"]
+    assert np.abs(model.intercept_ - np.array(gold["intercept"])).max() <= 1e-4
+    assert np.abs(model.predict(Z) - Mhat).max() <= 1e-9
