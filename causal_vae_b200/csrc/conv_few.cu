@@ -376,6 +376,126 @@ conv16_dn_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ D
   few_epi_flush(E, a, reinterpret_cast<double*>(dsm));
 }
 
+// ============================== Conv2d 16 -> 1, k3 s1 p1 (image head forward), plain epilogue ==============================
+// Output tile 32 x 32; the 34 x 34 x 16 input window is staged channel-planar (BatchNorm + LeakyReLU applied while
+// staging).  thread = 4 vertically adjacent outputs of one column: the 32 lanes of a warp read 32 consecutive words
+// of a plane (conflict-free, one wavefront per load), a 6 x 3 window per channel feeds 36 FMAs, and the 9 weights of
+// the channel come as three 128-bit broadcasts.  The previous kernel (skinny.cu conv_cd1_tile) read the window as
+// 128-bit vectors, four wavefronts each: 168 shared-memory wavefronts per output against 84 here.
+constexpr int kHdT = 32, kHdG = kHdT + 2, kHdPix = kHdG * kHdG;     // 1156 staged pixels
+constexpr int kHdPlane = 1162;                                       // 4 * plane % 32 == 8 (conflict-free staging stores)
+constexpr int kHdSmem = (16 * kHdPlane + 16 * 12) * 4;
+
+__global__ void __launch_bounds__(kFewThreads, 3)
+conv16_head_fwd_kernel(const __grid_constant__ GatherArgs a, const int tiles_h, const int tiles_w, const int total) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sX = dsm;                                                   // [16][34 x 34]
+  float4* sW = reinterpret_cast<float4*>(dsm + 16 * kHdPlane);       // [ci][3]: taps (kh, kw) row-major, padded to 12
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PhaseGeom& P = a.phase[0];
+  if (tid < 16 * 12) {
+    const int ci = tid / 12, t = tid % 12;
+    float w = 0.f;
+    if (t < 9)
+      for (int u = 0; u < 9; ++u)
+        if ((P.taps[u].dh + 1) * 3 + P.taps[u].dw + 1 == t) w = __ldg(a.wt + P.taps[u].widx * 16 + ci);
+    reinterpret_cast<float*>(sW)[tid] = w;
+  }
+  const int s4 = tid & 3;
+  const float bias = a.bias ? __ldg(a.bias) : 0.f;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tw = tile % tiles_w, tt = tile / tiles_w, th = tt % tiles_h, n = tt / tiles_h;
+    const int h0 = th * kHdT, w0 = tw * kHdT;
+    __syncthreads();
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), ce = sh;
+    if (a.in_affine) {
+      sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + s4 * 4));
+      sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + s4 * 4));
+      if (a.in_center) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + s4 * 4));
+    }
+    for (int base = 0; base < kHdPix * 4; base += 6 * kFewThreads) {   // 4624 vectors: batches of 6 loads per thread
+      float4 v[6];
+      int pixs[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int idx = base + tid + u * kFewThreads;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pixs[u] = -1;
+        if (idx < kHdPix * 4) {
+          const int pix = idx >> 2, gi = pix / kHdG, gj = pix - gi * kHdG, ih = h0 - 1 + gi, iw = w0 - 1 + gj;
+          pixs[u] = pix;
+          if ((unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * 16 + s4 * 4));
+            pixs[u] |= 1 << 30;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        if (pixs[u] < 0) continue;
+        float4 x = v[u];
+        if (pixs[u] & (1 << 30)) {
+          if (a.in_affine) {
+            x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
+            x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+          }
+          if (a.in_act) { x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope); x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope); }
+        }
+        float* d = sX + (s4 * 4) * kHdPlane + (pixs[u] & ~(1 << 30));
+        d[0] = x.x; d[kHdPlane] = x.y; d[2 * kHdPlane] = x.z; d[3 * kHdPlane] = x.w;
+      }
+    }
+    __syncthreads();
+    float acc[4] = {bias, bias, bias, bias};
+    const float* xp0 = sX + (4 * warp) * kHdG + lane;                // window rows 4 warp .. 4 warp + 5, columns lane .. lane + 2
+#pragma unroll 4
+    for (int ci = 0; ci < 16; ++ci) {
+      const float* xp = xp0 + ci * kHdPlane;
+      const float4 wa = sW[ci * 3], wb = sW[ci * 3 + 1], wc = sW[ci * 3 + 2];
+      const float w[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
+      float x[6][3];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[r][c] = xp[r * kHdG + c];
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) acc[o] = fmaf(x[o + kh][kw], w[kh * 3 + kw], acc[o]);
+    }
+    const int qw = w0 + lane;
+    if (qw < a.Wd) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int qh = h0 + 4 * warp + o;
+        if (qh < a.Hd) a.dst[((size_t)n * a.Hd + qh) * a.Wd + qw] = acc[o];
+      }
+    }
+  }
+}
+
+// 1: launched, 0: not covered
+int launch_conv16_head_fwd(const GatherArgs& g, cudaStream_t st) {
+  if (g.Cs != 16 || g.Cd != 1 || g.nphase != 1 || g.is != 1 || g.os != 1 || g.phase[0].ntaps != 9 || g.epi != CVAE_EPI_PLAIN) return 0;
+  if (g.Hs != g.Hd || g.Ws != g.Wd || (long long)g.N * g.Hd * g.Wd < 65536) return 0;
+  for (int t = 0; t < 9; ++t) {
+    const TapEntry& e = g.phase[0].taps[t];
+    if (e.dh < -1 || e.dh > 1 || e.dw < -1 || e.dw > 1) return 0;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv16_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHdSmem) != cudaSuccess) return CVAE_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int tiles_h = (g.Hd + kHdT - 1) / kHdT, tiles_w = (g.Wd + kHdT - 1) / kHdT;
+  const long long total = (long long)g.N * tiles_h * tiles_w;
+  if (total >= (1ll << 31)) return 0;
+  conv16_head_fwd_kernel<<<(int)min(total, (long long)kNumSMs * 3), kFewThreads, kHdSmem, st>>>(g, tiles_h, tiles_w, (int)total);
+  return 1;
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 static bool few_shape(int Cs, int Cd, int kh, int kw, int stride, int pad, int mode, int N, int Hs, int Ws, int Hd,
                       int Wd, int epi) {

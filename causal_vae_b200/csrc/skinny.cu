@@ -6,6 +6,7 @@
 // 256x256 activation).  Here a group of TP = C/4 threads owns one pixel, every thread moves one
 // 128-bit vector per tap, weights live in shared memory as float4 rows, and all per-channel sums stay
 // in registers across the grid-stride loop.
+#include <cstdlib>
 #include "conv_args.cuh"
 
 namespace cvae {
@@ -436,6 +437,10 @@ bool launch_conv_cd1(const GatherArgs& g, int maxM, cudaStream_t st) {
   if (g.Cd != 1 || (g.Cs & 3) || g.Cs > 64 || g.Cs < 4 || g.wtaps > 16 || g.epi != CVAE_EPI_PLAIN) return false;
   const int tp = g.Cs / 4;
   if (tp & (tp - 1)) return false;                      // power of two: shuffle reduction inside a warp
+  {
+    static const bool on = [] { const char* e = getenv("CVAE_HEAD_FWD_NEW"); return !(e && e[0] == '0'); }();
+    if (on && launch_conv16_head_fwd(g, st) == 1) return true;
+  }
   if (window3x3(g) && g.is == 1 && maxM >= 65536 && g.Cs == 16) {
     const PhaseGeom& P = g.phase[0];
     const int tiles_h = (P.Hq + 15) / 16, tiles_w = (P.Wq + 31) / 32;
