@@ -154,7 +154,16 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
   const float* pg = probs + (size_t)blockIdx.x * S * S;
   for (int i = tid; i < Sp * lp; i += blockDim.x) Ps[i] = 0.f;
   __syncthreads();
-  for (int i = tid; i < S * S; i += blockDim.x) { const int r = i / S; Ps[r * lp + (i - r * S)] = __ldg(pg + i); }
+  for (int i0 = tid; i0 < S * S; i0 += 6 * blockDim.x) {       // batches of 6 loads per thread before the first store
+    float pv[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) { const int i = i0 + u * blockDim.x; pv[u] = i < S * S ? __ldg(pg + i) : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < S * S) { const int r = i / S; Ps[r * lp + (i - r * S)] = pv[u]; }
+    }
+  }
   __syncthreads();
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   // dP = mask * (dO V^T)
