@@ -38,6 +38,12 @@ class WgradParams(C.Structure):
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32)]
 
 
+class PreprocParams(C.Structure):
+    _fields_ = [("raw", vp), ("resized", vp), ("stats", vp), ("mask", vp), ("thr", vp), ("aug_mode", vp),
+                ("xmin", vp), ("xsize", vp), ("xw", vp), ("ymin", vp), ("ysize", vp), ("yw", vp),
+                ("B", i32), ("Hin", i32), ("Win", i32), ("H", i32), ("W", i32)]
+
+
 EPI_PLAIN, EPI_STATS, EPI_DACT = 0, 1, 2
 MODE_GATHER, MODE_SCATTER = 0, 1
 ACT_LRELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2
@@ -119,6 +125,10 @@ _SIGS = {
     "cvae_rowdiff_l2": [vp, vp, vp, i64, i64, i32, vp],
     "cvae_sumsq": [vp, i64, vp, vp],
     "cvae_clip_adam": [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp, vp],
+    "cvae_aa_max_interp": [i32, i32],
+    "cvae_aa_weights": [i32, i32, vp, vp, vp, vp],
+    "cvae_vessel_preprocess": [C.POINTER(PreprocParams), vp],
+    "cvae_scaler_transform": [vp, vp, vp, vp, i64, i32, vp],
 }
 EXPORTS = tuple(_SIGS)
 

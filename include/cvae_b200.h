@@ -362,6 +362,35 @@ int cvae_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float max_norm, float lr, float beta1, float beta2, float eps, float grad_scale,
                    int64_t* step_count, cvae_stream_t s);
 
+/* ---- vessel input pipeline on the device ---------------------------------------
+ * What VesselDataset.__getitem__ does per raw image on DataLoader worker CPUs
+ * (vessel_analysis/00_core/dataset.py:186,216-237): transforms.Resize((H, W), antialias=True) (ATen's separable
+ * antialiased bilinear kernel, width pass first, fp32), hflip / vflip / both by aug_mode = idx % 4
+ * (dataset.py:219-226), per-image min-max to [0,1] (all zeros when max == min, :229-232), threshold at the image
+ * mean -> {0,1} (:236-237) — for a whole batch of same-sized raw images.  Bit-for-bit the CPU arithmetic; the mean
+ * is the correctly rounded one (fp64 sum of the fp32 normalised values), see oracle/input_oracle.py.
+ *
+ * cvae_aa_max_interp: taps per output index of one axis (host-side, no launch; 1 when in == out).
+ * cvae_aa_weights: fills xmin[out], xsize[out], w[out][max_interp] for one axis (cache per (in, out)). */
+int cvae_aa_max_interp(int in_size, int out_size);
+int cvae_aa_weights(int in_size, int out_size, int* xmin, int* xsize, float* w, cvae_stream_t s);
+typedef struct {
+  const float* raw;    /* [B, Hin, Win] raw images */
+  float* resized;      /* [B, H, W] workspace: the resized + flipped fp32 image (16-byte aligned) */
+  void* stats;         /* workspace, 16 bytes per image (zeroed by the call) */
+  float* mask;         /* [B, H, W] output {0,1} == x[B,1,H,W] */
+  float* thr;          /* [B] optional: the fp32 threshold each image was cut at */
+  const int* aug_mode; /* [B] 0..3 or NULL (no flips: validation) */
+  const int* xmin; const int* xsize; const float* xw; /* width axis, cvae_aa_weights(Win, W) */
+  const int* ymin; const int* ysize; const float* yw; /* height axis, cvae_aa_weights(Hin, H) */
+  int B, Hin, Win, H, W;
+} cvae_preproc_t;
+int cvae_vessel_preprocess(const cvae_preproc_t* p, cvae_stream_t s);
+/* StandardScaler.transform of the morphology features in fp64, stored fp32 (dataset.py:113-116,240):
+ * out[r][c] = (float)((m[r][c] - mean[c]) / scale[c]). */
+int cvae_scaler_transform(const double* m, const double* mean, const double* scale, float* out, int64_t rows,
+                          int cols, cvae_stream_t s);
+
 /* ---- debug: role-level wait accounting of the tensor-core kernels (builds with -DCVAE_TIMING only;
  * returns 0 and leaves out16 untouched otherwise).  Not part of the reference-facing surface. */
 int cvae_debug_read(unsigned long long* out16, int reset);
