@@ -84,19 +84,55 @@ __device__ __forceinline__ float aa_taps(LoadF src, const float* __restrict__ w,
   for (; j < n; ++j) t = __fmaf_rn(src(j), w[j], t);
   return t;
 }
+// the same with a compile-time tap count: the runtime loop above costs ~12 instructions per tap (ncu: the kernel
+// issue-bound at 81 %), the unrolled form 2-3 (immediate-offset shared-memory load + FMUL/FADD or FFMA).
+template <int N, typename LoadF>
+__device__ __forceinline__ float aa_taps_n(LoadF src, const float* w) {
+  constexpr int unfused = 1 + ((N - 1) & ~3);
+  float t = __fmul_rn(src(0), w[0]);
+#pragma unroll
+  for (int j = 1; j < N; ++j) t = j < unfused ? __fadd_rn(t, __fmul_rn(src(j), w[j])) : __fmaf_rn(src(j), w[j], t);
+  return t;
+}
+constexpr int kMaxUnrolledTaps = 12;
+#define CVAE_TAP_SWITCH(n, CALL, FALLBACK)                                                              \
+  switch (n) {                                                                                          \
+    case 1: CALL(1); break;  case 2: CALL(2); break;  case 3: CALL(3); break;  case 4: CALL(4); break;   \
+    case 5: CALL(5); break;  case 6: CALL(6); break;  case 7: CALL(7); break;  case 8: CALL(8); break;   \
+    case 9: CALL(9); break;  case 10: CALL(10); break; case 11: CALL(11); break; case 12: CALL(12); break; \
+    default: FALLBACK; break;                                                                           \
+  }
 
 constexpr int kTileW = 64;
 constexpr int kPreThreads = 256;
 
+// width pass of one thread: its column's N weights live in registers across the rows of the chunk
+template <int N>
+__device__ __forceinline__ void width_rows(const float* __restrict__ src, int pitch, float* __restrict__ dst, int rr0,
+                                           int rc, const float* __restrict__ wc) {
+  float w[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) w[j] = wc[j];
+  for (int rr = rr0; rr < rc; rr += kPreThreads / kTileW) {
+    const float* row = src + rr * pitch;
+    dst[rr * kTileW] = aa_taps_n<N>([&](int j) { return row[j]; }, w);
+  }
+}
+
 // grid (ceil(W/64), ceil(H/TH), B).  Dynamic smem: rows_max*64 floats (horizontally resized rows) +
-// 64*mx floats (width-axis weights of the tile) + TH*my floats (height-axis weights).
+// 64*mx floats (width-axis weights of the tile) + TH*my floats (height-axis weights) + stage_floats (raw rows).
+// The raw rows a tile needs are staged through shared memory in chunks with coalesced 128-bit loads, four per
+// thread in flight (the direct strided gather kept one scalar load per thread in flight and ran at 0.16 of the
+// copy bandwidth); the taps are then shared-memory reads.
 __global__ void __launch_bounds__(kPreThreads)
 resize_aa_kernel(const float* __restrict__ raw, float* __restrict__ resized, PreStats* __restrict__ stats,
                  const int* __restrict__ aug_mode, const int* __restrict__ xmin, const int* __restrict__ xsize,
                  const float* __restrict__ xw, int mx, const int* __restrict__ ymin, const int* __restrict__ ysize,
-                 const float* __restrict__ yw, int my, int Hin, int Win, int H, int W, int TH, int rows_max) {
-  extern __shared__ float smem[];
-  float* tmp = smem;                                  // [rows_max][64]
+                 const float* __restrict__ yw, int my, int Hin, int Win, int H, int W, int TH, int rows_max,
+                 int stage_floats) {
+  extern __shared__ __align__(16) float smem[];
+  float* sraw = smem;                                 // [rows per chunk][pitch]
+  float* tmp = sraw + stage_floats;                   // [rows_max][64]
   float* wxs = tmp + (size_t)rows_max * kTileW;       // [64][mx]  (mx is odd: conflict-free)
   float* wys = wxs + kTileW * mx;                     // [TH][my]
   __shared__ unsigned int red_max[kPreThreads / 32], red_min[kPreThreads / 32];
@@ -110,18 +146,61 @@ resize_aa_kernel(const float* __restrict__ raw, float* __restrict__ resized, Pre
   const int r0 = ymin[oy0];
   const int r1 = ymin[oy0 + th - 1] + ysize[oy0 + th - 1];
   const int nrows = r1 - r0;
-  if (nrows > rows_max) __trap();                     // host bound violated: never silently wrong
-  __syncthreads();
+  const int c0 = xmin[ox0] & ~3;                                        // staged columns [c0, c1)
+  const int c1 = xmin[ox0 + tw - 1] + xsize[ox0 + tw - 1];
+  const int pitch = (c1 - c0 + 3) & ~3;
+  if (nrows > rows_max || pitch > stage_floats) __trap();               // host bound violated: never silently wrong
+  const int rows_chunk = stage_floats / pitch;
+  const bool vec = (Win & 3) == 0 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
 
-  // ---- width pass: raw rows r0..r1 -> tmp (fp32, rounded exactly as the CPU path's intermediate image)
   const int c = tid & (kTileW - 1);
-  if (c < tw) {
-    const int lo = xmin[ox0 + c], n = xsize[ox0 + c];
-    const float* wc = wxs + c * mx;
-    const float* base = raw + ((size_t)b * Hin + r0) * Win + lo;
-    for (int rr = tid / kTileW; rr < nrows; rr += kPreThreads / kTileW) {
-      const float* row = base + (size_t)rr * Win;
-      tmp[rr * kTileW + c] = aa_taps([&](int j) { return __ldg(row + j); }, wc, n);
+  const int lo = c < tw ? xmin[ox0 + c] - c0 : 0, n = c < tw ? xsize[ox0 + c] : 0;
+  const float* wc = wxs + c * mx;
+  const float* img = raw + ((size_t)b * Hin + r0) * Win + c0;
+  for (int rbase = 0; rbase < nrows; rbase += rows_chunk) {
+    const int rc = min(rows_chunk, nrows - rbase);
+    __syncthreads();                                                    // previous chunk consumed, weights visible
+    if (vec) {
+      const int p4 = pitch >> 2, total = rc * p4;
+      const unsigned int inv_p4 = 0xffffffffu / (unsigned int)p4 + 1u;   // i / p4 == umulhi(i, inv_p4) for i*p4 < 2^32
+      for (int i0 = tid; i0 < total; i0 += 4 * kPreThreads) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kPreThreads;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < total) {
+            const int rr = p4 == 1 ? i : (int)__umulhi((unsigned int)i, inv_p4), q = i - rr * p4;
+            if (c0 + 4 * q < Win) v[u] = __ldg(reinterpret_cast<const float4*>(img + (size_t)(rbase + rr) * Win) + q);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kPreThreads;
+          if (i < total) reinterpret_cast<float4*>(sraw)[i] = v[u];
+        }
+      }
+    } else {
+      const int total = rc * pitch;
+      for (int i = tid; i < total; i += kPreThreads) {
+        const int rr = i / pitch, q = i - rr * pitch;
+        sraw[i] = c0 + q < Win ? __ldg(img + (size_t)(rbase + rr) * Win + q) : 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- width pass: staged raw rows -> tmp (fp32, rounded exactly as the CPU path's intermediate image)
+    if (c < tw) {
+      const float* src = sraw + lo;
+      float* dst = tmp + rbase * kTileW + c;
+      const int rr0 = tid / kTileW;
+#define CVAE_W(N) width_rows<N>(src, pitch, dst, rr0, rc, wc)
+      CVAE_TAP_SWITCH(n, CVAE_W, {
+        for (int rr = rr0; rr < rc; rr += kPreThreads / kTileW) {
+          const float* row = src + rr * pitch;
+          dst[rr * kTileW] = aa_taps([&](int j) { return row[j]; }, wc, n);
+        }
+      })
+#undef CVAE_W
     }
   }
   __syncthreads();
@@ -135,7 +214,12 @@ resize_aa_kernel(const float* __restrict__ raw, float* __restrict__ resized, Pre
     for (int orow = tid / kTileW; orow < th; orow += kPreThreads / kTileW) {
       const int oy = oy0 + orow;
       const float* col = tmp + (ymin[oy] - r0) * kTileW + c;
-      const float v = aa_taps([&](int j) { return col[j * kTileW]; }, wys + orow * my, ysize[oy]);
+      const float* wr = wys + orow * my;
+      const int ny = ysize[oy];
+      float v;
+#define CVAE_H(N) v = aa_taps_n<N>([&](int j) { return col[j * kTileW]; }, wr)
+      CVAE_TAP_SWITCH(ny, CVAE_H, v = aa_taps([&](int j) { return col[j * kTileW]; }, wr, ny))
+#undef CVAE_H
       const int fy = (aug & 2) ? H - 1 - oy : oy;
       resized[((size_t)b * H + fy) * W + fx] = v;
       vmax = fmaxf(vmax, v);
@@ -261,26 +345,37 @@ extern "C" int cvae_vessel_preprocess(const cvae_preproc_t* p, cvae_stream_t s) 
   const int mx = host_max_interp(p->Win, p->W), my = host_max_interp(p->Hin, p->H);
   // rows of the width-pass image one TH-row output tile can need: TH*scale + the two half windows (+ rounding)
   const float sy = p->Hin == p->H ? 1.0f : (float)p->Hin / (float)p->H;
-  int TH = 16, rows_max = 0;
-  size_t smem = 0;
+  const float sx = p->Win == p->W ? 1.0f : (float)p->Win / (float)p->W;
+  // raw columns a 64-column tile can need (+ 3 for the 16-byte align-down, rounded up to a multiple of 4)
+  const int pitch_max = ((int)ceilf(kTileW * sx) + mx + 2 + 3 + 3) & ~3;
+  const int budget = 47 * 1024 / (int)sizeof(float);   // dynamic + 64 B static must stay under the 48 KB default
+  int TH = 16, rows_max = 0, stage_floats = 0;
   for (; TH >= 1; TH >>= 1) {
     rows_max = (int)ceilf(TH * sy) + my + 2;
-    smem = ((size_t)rows_max * kTileW + (size_t)kTileW * mx + (size_t)TH * my) * sizeof(float);
-    if (smem <= 48 * 1024) break;
+    const long long fixed = (long long)rows_max * kTileW + (long long)kTileW * mx + (long long)TH * my;
+    const long long left = budget - fixed;
+    const int want_rows = TH == 1 ? 1 : (rows_max < 8 ? rows_max : 8);   // rows per staging chunk worth having
+    if (left >= (long long)pitch_max * want_rows) {
+      const long long all = (long long)rows_max * pitch_max;
+      stage_floats = (int)(left < all ? left : all) & ~3;
+      break;
+    }
   }
   if (TH < 1) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  const size_t smem = ((size_t)stage_floats + (size_t)rows_max * kTileW + (size_t)kTileW * mx + (size_t)TH * my) *
+                      sizeof(float);
   cudaStream_t st = as_stream(s);
   if (cudaMemsetAsync(p->stats, 0, (size_t)p->B * sizeof(PreStats), st) != cudaSuccess) return CVAE_ERR_LAUNCH;
   const dim3 grid((p->W + kTileW - 1) / kTileW, (p->H + TH - 1) / TH, p->B);
   if (grid.y > 65535) return CVAE_ERR_UNSUPPORTED_SHAPE;
   resize_aa_kernel<<<grid, kPreThreads, smem, st>>>(p->raw, p->resized, (PreStats*)p->stats, p->aug_mode, p->xmin,
                                                     p->xsize, p->xw, mx, p->ymin, p->ysize, p->yw, my, p->Hin, p->Win,
-                                                    p->H, p->W, TH, rows_max);
+                                                    p->H, p->W, TH, rows_max, stage_floats);
   CVAE_LAUNCH_CHECK();
   const int64_t n = (int64_t)p->H * p->W;
-  int chunks = (int)((n / 4 + 255) / 256);
-  // each CTA covers >= 4 float4 per thread; at least ~4 CTAs per SM over the batch
-  chunks = max(1, min(chunks, max(1, (4 * kNumSMs + p->B - 1) / p->B)));
+  // two 128-bit loads per thread: these passes read L2-resident data, their cost is latency, so many short CTAs
+  int chunks = (int)((n / 4 + 511) / 512);
+  chunks = max(1, min(chunks, 1024));
   const dim3 g2(chunks, p->B);
   norm_sum_kernel<<<g2, 256, 0, st>>>(p->resized, (PreStats*)p->stats, n);
   CVAE_LAUNCH_CHECK();
