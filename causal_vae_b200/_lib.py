@@ -125,6 +125,8 @@ _SIGS = {
     "cvae_rowdiff_l2": [vp, vp, vp, i64, i64, i32, vp],
     "cvae_sumsq": [vp, i64, vp, vp],
     "cvae_clip_adam": [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp, vp],
+    "cvae_upsample2x_fwd": [vp, vp, i32, i32, i32, i32, vp],
+    "cvae_upsample2x_bwd": [vp, vp, i32, i32, i32, i32, vp],
     "cvae_aa_max_interp": [i32, i32],
     "cvae_aa_weights": [i32, i32, vp, vp, vp, vp],
     "cvae_vessel_preprocess": [C.POINTER(PreprocParams), vp],

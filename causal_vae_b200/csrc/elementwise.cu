@@ -333,6 +333,52 @@ __global__ void rowdiff_l2_kernel(const float* __restrict__ a, const float* __re
   if (threadIdx.x == 0) out[row] = (float)sqrt(t);
 }
 
+// nn.Upsample(scale_factor=2, mode='nearest') on NHWC (vessel_analysis/00_core/models.py:123-145, the CNN decoder):
+// y[n, 2h+a, 2w+b, :] = x[n, h, w, :]; backward sums each 2x2 block.  V = 4 (C % 4 == 0) or 1.
+template <int V>
+__global__ void upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n_in, int H, int W,
+                                      int Cv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_in; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cv);
+    const int64_t p = i / Cv;
+    const int w = (int)(p % W);
+    const int64_t q = p / W;
+    const int h = (int)(q % H);
+    const int64_t n = q / H;
+    const int64_t o = (((n * 2 * H + 2 * h) * 2 * W) + 2 * w) * Cv + c;
+    if (V == 4) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      float4* yo = reinterpret_cast<float4*>(y);
+      yo[o] = v; yo[o + Cv] = v; yo[o + (int64_t)2 * W * Cv] = v; yo[o + (int64_t)2 * W * Cv + Cv] = v;
+    } else {
+      const float v = x[i];
+      y[o] = v; y[o + Cv] = v; y[o + (int64_t)2 * W * Cv] = v; y[o + (int64_t)2 * W * Cv + Cv] = v;
+    }
+  }
+}
+template <int V>
+__global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t n_in, int H, int W,
+                                      int Cv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_in; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cv);
+    const int64_t p = i / Cv;
+    const int w = (int)(p % W);
+    const int64_t q = p / W;
+    const int h = (int)(q % H);
+    const int64_t n = q / H;
+    const int64_t o = (((n * 2 * H + 2 * h) * 2 * W) + 2 * w) * Cv + c;
+    const int64_t r = (int64_t)2 * W * Cv;
+    if (V == 4) {
+      const float4* g = reinterpret_cast<const float4*>(dy);
+      const float4 a = g[o], b = g[o + Cv], cc = g[o + r], d = g[o + r + Cv];
+      reinterpret_cast<float4*>(dx)[i] = make_float4((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y),
+                                                     (a.z + b.z) + (cc.z + d.z), (a.w + b.w) + (cc.w + d.w));
+    } else {
+      dx[i] = (dy[o] + dy[o + Cv]) + (dy[o + r] + dy[o + r + Cv]);
+    }
+  }
+}
+
 }  // namespace cvae
 using namespace cvae;
 
@@ -479,6 +525,26 @@ extern "C" int cvae_kld_bwd(const float* mu, const float* logvar, const float* g
   return CVAE_OK;
 }
 
+extern "C" int cvae_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, cvae_stream_t s) {
+  if (!x || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0) return CVAE_ERR_BAD_ARG;
+  const bool v4 = (C & 3) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  const int Cv = v4 ? C / 4 : C;
+  const int64_t n = (int64_t)N * H * W * Cv;
+  if (v4) upsample2x_fwd_kernel<4><<<ew_blocks(n), 256, 0, ST>>>(x, y, n, H, W, Cv);
+  else upsample2x_fwd_kernel<1><<<ew_blocks(n), 256, 0, ST>>>(x, y, n, H, W, Cv);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+extern "C" int cvae_upsample2x_bwd(const float* dy, float* dx, int N, int H, int W, int C, cvae_stream_t s) {
+  if (!dy || !dx || N <= 0 || H <= 0 || W <= 0 || C <= 0) return CVAE_ERR_BAD_ARG;
+  const bool v4 = (C & 3) == 0 && (((uintptr_t)dy | (uintptr_t)dx) & 15) == 0;
+  const int Cv = v4 ? C / 4 : C;
+  const int64_t n = (int64_t)N * H * W * Cv;
+  if (v4) upsample2x_bwd_kernel<4><<<ew_blocks(n), 256, 0, ST>>>(dy, dx, n, H, W, Cv);
+  else upsample2x_bwd_kernel<1><<<ew_blocks(n), 256, 0, ST>>>(dy, dx, n, H, W, Cv);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
 extern "C" int cvae_clamp_fwd(const float* x, float* y, int64_t n, float lo, float hi, cvae_stream_t s) {
   if (!x || !y || n <= 0) return CVAE_ERR_BAD_ARG;
   clamp_fwd_kernel<<<ew_blocks(n), 256, 0, ST>>>(x, y, n, lo, hi);

@@ -261,6 +261,28 @@ def clamp(x, lo, hi):
     return _Clamp.apply(x, float(lo), float(hi))
 
 
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):                                   # x: contiguous [N, H, W, C]
+        N, H, W, Cc = x.shape
+        y = torch.empty(N, 2 * H, 2 * W, Cc, dtype=x.dtype, device=x.device)
+        L.check(L.lib.cvae_upsample2x_fwd(L.ptr(x), L.ptr(y), N, H, W, Cc, L.stream()), "upsample2x_fwd")
+        ctx.shape = (N, H, W, Cc)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, Cc = ctx.shape
+        dx = torch.empty(N, H, W, Cc, dtype=g.dtype, device=g.device)
+        L.check(L.lib.cvae_upsample2x_bwd(L.ptr(g.contiguous()), L.ptr(dx), N, H, W, Cc, L.stream()), "upsample2x_bwd")
+        return dx
+
+
+def upsample_nearest2x(x):
+    """nn.Upsample(scale_factor=2, mode='nearest') on a logical NCHW tensor (vessel_analysis/00_core/models.py:123)."""
+    return from_nhwc(_Upsample2x.apply(to_nhwc(x).contiguous()))
+
+
 # ---- LayerNorm ------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
     @staticmethod

@@ -107,6 +107,18 @@ class Flatten(tnn.Flatten):
         return super().forward(x)
 
 
+class Upsample(tnn.Upsample):
+    """nearest x2 only (the CNN vessel decoder, vessel_analysis/00_core/models.py:123-145)."""
+
+    def forward(self, x):
+        _check_cuda(x)
+        sf = self.scale_factor
+        sf = sf if isinstance(sf, (int, float)) else (sf[0] if sf and sf[0] == sf[-1] else None)
+        if self.mode != "nearest" or sf is None or float(sf) != 2.0 or x.dim() != 4:
+            raise RuntimeError("Upsample: only scale_factor=2, mode='nearest' on 4-D input is implemented")
+        return F.upsample_nearest2x(x)
+
+
 class AdaptiveAvgPool2d(tnn.AdaptiveAvgPool2d):
     """Identity when the input already has the target size (64x64 cascade config: 4x4 -> 4x4,
     causal_cascade/models.py:18); other sizes are outside the B200 hot path."""

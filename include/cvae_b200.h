@@ -362,6 +362,11 @@ int cvae_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float max_norm, float lr, float beta1, float beta2, float eps, float grad_scale,
                    int64_t* step_count, cvae_stream_t s);
 
+/* nn.Upsample(scale_factor=2, mode='nearest') of the CNN vessel decoder (vessel_analysis/00_core/models.py:123-145)
+ * on NHWC: y[n, 2h+a, 2w+b, c] = x[n, h, w, c] (H, W are the INPUT sizes); backward sums each 2x2 block. */
+int cvae_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, cvae_stream_t s);
+int cvae_upsample2x_bwd(const float* dy, float* dx, int N, int H, int W, int C, cvae_stream_t s);
+
 /* ---- vessel input pipeline on the device ---------------------------------------
  * What VesselDataset.__getitem__ does per raw image on DataLoader worker CPUs
  * (vessel_analysis/00_core/dataset.py:186,216-237): transforms.Resize((H, W), antialias=True) (ATen's separable

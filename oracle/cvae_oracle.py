@@ -312,6 +312,76 @@ def vessel_forward(P: SD, x: Tensor, m: Tensor, t: Tensor, eps: Tensor, train: b
     return recon, m_mu, mu, logvar, m_mu, m_logvar
 
 
+# the CNN variant of the vessel model (vessel_analysis/00_core/models.py:9-166), fixed 768x1280 input
+VESSEL_CNN_ENC = (1, 32, 64, 128, 256, 512, 512, 512)
+VESSEL_CNN_DEC = (512, 512, 512, 256, 128, 64, 32, 1)
+
+
+def vessel_cnn_shapes(z_dim=128, m_dim=12, t_dim=19) -> Dict[str, Tuple[int, ...]]:
+    """state_dict key -> shape of CausalVesselVAE (models.py:32-145), in the reference's key order."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(pre, c):
+        s[pre + ".weight"] = (c,); s[pre + ".bias"] = (c,); s[pre + ".running_mean"] = (c,)
+        s[pre + ".running_var"] = (c,); s[pre + ".num_batches_tracked"] = ()
+
+    def lin(pre, i, o):
+        s[pre + ".weight"] = (o, i); s[pre + ".bias"] = (o,)
+    for i, (a, b) in enumerate(zip(VESSEL_CNN_ENC[:-1], VESSEL_CNN_ENC[1:])):
+        s[f"enc_conv.{3 * i}.weight"] = (b, a, 4, 4); s[f"enc_conv.{3 * i}.bias"] = (b,)
+        bn(f"enc_conv.{3 * i + 1}", b)
+    flat = 512 * 6 * 10
+    lin("enc_fc.0", flat + m_dim + t_dim, 1024); bn("enc_fc.1", 1024); lin("enc_fc.3", 1024, 2 * z_dim)
+    lin("morph_predictor_shared.0", t_dim, 64); lin("morph_predictor_shared.2", 64, 64)
+    lin("morph_predictor_mu", 64, m_dim); lin("morph_predictor_logvar", 64, m_dim)
+    lin("dec_fc.0", m_dim + z_dim, 1024); bn("dec_fc.1", 1024); lin("dec_fc.3", 1024, flat)
+    for i, (a, b) in enumerate(zip(VESSEL_CNN_DEC[:-1], VESSEL_CNN_DEC[1:])):
+        s[f"dec_conv.{4 * i + 1}.weight"] = (b, a, 3, 3); s[f"dec_conv.{4 * i + 1}.bias"] = (b,)
+        if b != 1:
+            bn(f"dec_conv.{4 * i + 2}", b)
+    return s
+
+
+def vessel_cnn_decode(P: SD, m: Tensor, z: Tensor, train: bool) -> Tensor:
+    """dec_fc -> view(-1, 512, 6, 10) -> 7 x [nearest x2, Conv3x3, BN, ReLU] (last: Conv3x3, Sigmoid)
+    (models.py:63-69,123-145,161-164) — m first."""
+    h = F.leaky_relu(_bn(P, "dec_fc.1", _lin(P, "dec_fc.0", torch.cat([m, z], dim=1)), train), 0.2)
+    h = F.relu(_lin(P, "dec_fc.3", h)).view(-1, 512, 6, 10)
+    n = len(VESSEL_CNN_DEC) - 1
+    for i in range(n):
+        h = _conv(P, f"dec_conv.{4 * i + 1}", F.interpolate(h, scale_factor=2, mode="nearest"), 1, 1)
+        h = F.relu(_bn(P, f"dec_conv.{4 * i + 2}", h, train)) if i + 1 < n else torch.sigmoid(h)
+    return h
+
+
+def vessel_cnn_forward(P: SD, x: Tensor, m: Tensor, t: Tensor, eps: Tensor, train: bool):
+    """CausalVesselVAE.forward (models.py:153-166) -> 6-tuple."""
+    h = x
+    for i in range(len(VESSEL_CNN_ENC) - 1):
+        h = F.leaky_relu(_bn(P, f"enc_conv.{3 * i + 1}", _conv(P, f"enc_conv.{3 * i}", h, 2, 1), train), 0.2)
+    h = _lin(P, "enc_fc.0", torch.cat([h.flatten(1), m, t], dim=1))
+    mu, logvar = _lin(P, "enc_fc.3", F.leaky_relu(_bn(P, "enc_fc.1", h, train), 0.2)).chunk(2, dim=1)
+    mu, logvar = torch.clamp(mu, -100, 100), torch.clamp(logvar, -10, 10)
+    z = reparameterize(mu, logvar, eps)
+    m_mu, m_logvar = vessel_morph_head(P, t)
+    return vessel_cnn_decode(P, m, z, train), m_mu, mu, logvar, m_mu, m_logvar
+
+
+def vessel_cnn_loss_and_grads(P: SD, x, m, t, eps, beta=0.5):
+    """One training-mode forward + the vessel loss (train.py:18-60,82) + gradients of every parameter."""
+    params = trainable(P)
+    for v in params.values():
+        v.requires_grad_(True)
+    outs = vessel_cnn_forward(P, x, m, t, eps, True)
+    recon, kld, morph, sp = vessel_loss(outs[0], x, outs[1], m, outs[2], outs[3], outs[4], outs[5])
+    loss = vessel_total(recon, kld, morph, sp, beta)
+    grads = dict(zip(params, torch.autograd.grad(loss, list(params.values()))))
+    for v in params.values():
+        v.requires_grad_(False)
+    return outs, {"loss": loss.detach(), "recon": recon.detach(), "kld": kld.detach(), "morph": morph.detach(),
+                  "sparsity": sp.detach()}, grads
+
+
 def vessel_loss(recon_x, x, m_hat, m, mu, logvar, m_mu, m_logvar):
     """loss_function (vessel_analysis/01_train/train.py:18-60): weighted MSE with a
     batch-global pos_weight (no grad), background sparsity L1, KL, Gaussian NLL."""

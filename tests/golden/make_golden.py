@@ -70,7 +70,7 @@ class EpsInjector:
 
 def summarize(t: torch.Tensor, n=8):
     t = t.detach().double().flatten()
-    idx = torch.linspace(0, t.numel() - 1, min(n, t.numel())).long()
+    idx = torch.linspace(0, t.numel() - 1, min(n, t.numel()), dtype=torch.float64).long().clamp_(max=t.numel() - 1)
     return {"numel": t.numel(), "sum": t.sum().item(), "l2": t.norm().item(),
             "absmax": t.abs().max().item(), "idx": idx.tolist(), "val": t[idx].tolist()}
 

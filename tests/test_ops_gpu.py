@@ -486,3 +486,23 @@ def test_counterfactual_helpers():
     d = rowdiff_l2(a.cuda(), b.cuda(), K).cpu()
     ref = (a.view(S, K, -1) - b.view(S, 1, -1)).double().norm(dim=2).view(-1)
     assert_close(d, ref, 1e-5, "rowdiff")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 32, 6, 10), (1, 3, 5, 7), (3, 512, 12, 20)])
+def test_upsample_nearest2x_exact(shape):
+    """nn.Upsample(scale_factor=2, mode='nearest') of the CNN vessel decoder: forward is a copy, backward a 2x2 sum —
+    both bit-exact against torch on the same device-independent inputs."""
+    from causal_vae_b200 import nn
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(*shape, generator=g)
+    dy = torch.randn(shape[0], shape[1], 2 * shape[2], 2 * shape[3], generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.interpolate(xr, scale_factor=2, mode="nearest")
+    yr.backward(dy)
+    xg = x.cuda().requires_grad_(True)
+    y = nn.Upsample(scale_factor=2, mode="nearest")(xg)
+    y.backward(dy.cuda())
+    assert torch.equal(y.detach().cpu(), yr.detach())
+    # 2x2 sums: (a + b) + (c + d) here, torch's order may differ by an ulp
+    assert torch.allclose(xg.grad.cpu(), xr.grad, rtol=0, atol=4e-7 * float(dy.abs().max()))

@@ -248,3 +248,74 @@ def test_training_with_dropout_runs_and_is_reproducible():
     model0, _ = build(H, W, p_drop=0.0)
     l0 = float(train.VesselTrainer(model0, lr=1e-4).step(x, m, t, eps)[0])
     assert abs(out[0][0] - l0) / l0 < 0.2 and out[0][0] != l0
+
+
+def test_vessel_cnn_variant_matches_oracle_and_golden():
+    """CausalVesselVAE (vessel_analysis/00_core/models.py:9-166; fixed 768x1280 input), B = 4: state_dict keys,
+    eval forward, train-mode forward, the four loss terms (1e-5 relative) and every parameter gradient against the
+    fp64 oracle, and the losses against the live-reference golden."""
+    from causal_vae_b200.vessel import models, train
+    with open(os.path.join(G, "vessel_cnn_768x1280_b4.json")) as f:
+        gold = json.load(f)
+    c = gold["config"]
+    shapes = O.vessel_cnn_shapes(c["z_dim"], c["m_dim"], c["t_dim"])
+    models.CONFIG.update(Z_DIM=c["z_dim"], M_DIM=c["m_dim"], T_DIM=c["t_dim"])
+    sd = O.fill_state_dict(shapes, seed=0)
+    model = models.CausalVesselVAE()
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == shapes
+    assert list(model.state_dict()) == list(gold["state_dict_shapes"]), "key order"
+    assert not hasattr(model, "dec_adapter")                 # analyze_vessel.py:93 tells the variants apart by this
+    model.load_state_dict(sd)
+    model = model.cuda()
+    x, m, t, eps = O.vessel_inputs(c["B"], c["H"], c["W"], c["m_dim"], c["t_dim"], c["z_dim"], seed=0)
+    xc, mc, tc, ec = (a.cuda() for a in (x, m, t, eps))
+    names = ["recon_x", "m_hat", "mu", "logvar", "m_mu", "m_logvar"]
+
+    model.eval()
+    with torch.no_grad():
+        got = model(xc, mc, tc, ec)
+        want = O.vessel_cnn_forward({k: v.clone() for k, v in sd.items()}, x, m, t, eps, train=False)
+    for n, a, b in zip(names, got, want):
+        assert a.shape == b.shape and rel(a, b) <= 1e-5, ("eval", n, rel(a, b))
+    # submodule access the analysis scripts use (analyze_vessel.py:97-98)
+    with torch.no_grad():
+        h = model.dec_fc(torch.cat([mc, got[2]], dim=1)).view(-1, 512, 6, 10)
+        img = model.dec_conv(h)
+        want_img = O.vessel_cnn_decode({k: v.clone() for k, v in sd.items()}, m, want[2], False)
+    assert img.shape == (c["B"], 1, c["H"], c["W"]) and rel(img, want_img) <= 1e-5
+
+    model.train()
+    outs = model(xc, mc, tc, ec)
+    parts = train.loss_function(outs[0], xc, outs[1], mc, outs[2], outs[3], outs[4], outs[5])
+    loss = train.total_loss(*parts, beta=c["beta"])
+    loss.backward()
+    torch.cuda.synchronize()
+    P64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    o64, l64, g64 = O.vessel_cnn_loss_and_grads(P64, x.double(), m.double(), t.double(), eps.double(), c["beta"])
+    for n, a, b in zip(names, outs, o64):
+        assert rel(a, b) <= 2e-5, ("train", n, rel(a, b))
+    for n, v in zip(["recon", "kld", "morph", "sparsity"], parts):
+        e = abs(float(v) - float(l64[n])) / abs(float(l64[n]))
+        assert e <= 1e-5, (n, float(v), float(l64[n]), e)
+    assert abs(float(loss) - float(l64["loss"])) <= 1e-5 * abs(float(l64["loss"]))
+    assert abs(float(loss) - gold["train"]["loss"]) <= 2e-5 * abs(gold["train"]["loss"])
+    # gradients: 1e-4 of each tensor's max |g|, widened to 4x the REFERENCE's own fp32-vs-fp64 discrepancy of that
+    # tensor (recorded in the golden: median 1.6e-3, max 2e-2 — BatchNorm over a batch of 4 makes whole-network
+    # gradients ill-conditioned); biases in front of a BatchNorm have an exactly zero gradient (pure rounding noise
+    # in fp32), they are bounded against their layer's weight gradient.
+    noise = gold["train"]["grad_noise_fp32_vs_fp64"]
+    worst = {}
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        if noise[k] > 1.0:
+            wk = k[:-len("bias")] + "weight"
+            assert p.grad.abs().max().item() <= 1e-3 * g64[wk].abs().max().item(), k
+            continue
+        worst[k] = rel(p.grad, g64[k]) / max(1e-4, 4 * noise[k])
+    bad = {k: v for k, v in worst.items() if v > 1.0}
+    assert not bad, bad
+    # running statistics updated as BatchNorm does (momentum 0.1, unbiased variance)
+    after = model.state_dict()
+    for k in after:
+        if k.endswith(("running_mean", "running_var")):
+            assert rel(after[k], P64[k]) <= 1e-4, k
