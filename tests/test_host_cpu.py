@@ -52,6 +52,19 @@ def test_state_dict_keys_match_reference():
         assert sd["backbone.stem.1.num_batches_tracked"].dtype == torch.int64
 
 
+def test_cnn_variant_state_dict_keys_match_reference():
+    """CausalVesselVAE (vessel_analysis/00_core/models.py:9-166): key names, order and shapes of the live reference."""
+    from causal_vae_b200.vessel import models
+    g = json.load(open(os.path.join(G, "vessel_cnn_768x1280_b4.json")))
+    models.CONFIG.update(Z_DIM=g["config"]["z_dim"], M_DIM=g["config"]["m_dim"], T_DIM=g["config"]["t_dim"])
+    model = models.CausalVesselVAE()
+    sd = model.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == g["state_dict_shapes"]
+    assert list(sd.keys()) == list(g["state_dict_shapes"].keys()), "key order"
+    assert not hasattr(model, "dec_adapter") and hasattr(model, "dec_fc") and len(model.dec_conv) == 27
+    assert isinstance(model.dec_conv[0], torch.nn.Upsample) and isinstance(model.enc_conv[21], torch.nn.Flatten)
+
+
 def test_no_cpu_fallback():
     from causal_vae_b200 import nn
     with pytest.raises(RuntimeError, match="CUDA"):
