@@ -105,3 +105,17 @@ class LatentDiscriminator(tnn.Module):
 
     def forward(self, z):
         return self.net(z)
+
+
+class SimpleClassifier(tnn.Module):
+    """Name kept so that `from models import CausalMorphVAE12, SimpleClassifier, LatentDiscriminator`
+    (mnist_test/01_baseline_causal_vae/train.py:9) imports.  The class itself — the external evaluation classifier
+    (models.py:74-91: two 5x5 convolutions with max-pooling, trained with SGD on real MNIST by
+    `train_external_classifier`, train.py:105-128) — is outside the accelerated path (SURVEY 8a lists a11-a13 only) and
+    has no native kernels yet (5x5 taps, max-pool, NLL); constructing it fails loudly instead of silently running on
+    ATen."""
+
+    def __init__(self):
+        super().__init__()
+        raise RuntimeError("SimpleClassifier (external evaluation classifier, mnist_test/*/models.py:74-91) is not part of "
+                           "the B200 hot path and has no native implementation; use the reference's class for it")

@@ -97,3 +97,42 @@ def test_sequential_fusion_plan():
     mlp = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Dropout(0.1), nn.Linear(16, 8), nn.Dropout(0.1))
     kinds = [k for k, _ in mlp._plan()]
     assert kinds == ["chain", "mod", "mod", "chain", "mod"]
+
+
+def test_runner_redirects_models_for_an_unmodified_script(tmp_path):
+    """SURVEY 8b last row: `python -m causal_vae_b200.run <reference script>` makes bare `import models` /
+    `from vit_backbone import ViTVAE` resolve to the native classes while `config` stays the script tree's own."""
+    core = tmp_path / "vessel_analysis" / "00_core"
+    work = tmp_path / "vessel_analysis" / "01_train"
+    core.mkdir(parents=True); work.mkdir(parents=True)
+    (core / "config.py").write_text(
+        "import torch\nCONFIG = dict(DEVICE=torch.device('cpu'), IMG_HEIGHT=64, IMG_WIDTH=64, T_DIM=19, M_DIM=12, "
+        "Z_DIM=128, BETA=0.5, LEARNING_RATE=1e-4, BATCH_SIZE=8, EPOCHS=1, LAMBDA_MORPH=10000)\n")
+    (core / "models.py").write_text("raise RuntimeError('the reference models.py must not be imported')\n")
+    (core / "vit_backbone.py").write_text("raise RuntimeError('the reference vit_backbone.py must not be imported')\n")
+    (work / "script.py").write_text(
+        "import sys, os, json\n"
+        "sys.path.append(os.path.abspath(os.path.join(os.path.dirname(__file__), '..', '00_core')))\n"
+        "from models import CausalVesselVAE, CausalViTVAE\n"
+        "from vit_backbone import ViTVAE\n"
+        "from config import CONFIG\n"
+        "import models\n"
+        "CONFIG['IMG_HEIGHT'] = 96\n"
+        "m = CausalViTVAE()\n"
+        "json.dump({'cls': CausalViTVAE.__module__, 'vit': ViTVAE.__module__, 'same_config': models.CONFIG is CONFIG,\n"
+        "           'pos': list(m.backbone.pos_embedding.shape), 'argv': sys.argv[1:], 'name': __name__}, open(sys.argv[1], 'w'))\n")
+    out = tmp_path / "out.json"
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "causal_vae_b200.run", str(work / "script.py"), str(out)],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.load(open(out))
+    assert got["cls"] == "causal_vae_b200.vessel.models" and got["vit"] == "causal_vae_b200.vessel.vit_backbone"
+    assert got["same_config"] and got["name"] == "__main__" and got["argv"] == [str(out)]
+    assert got["pos"] == [1, (96 // 32) * (64 // 32) + 1, 256]          # the script's CONFIG edit reached the native model
+
+    from causal_vae_b200 import run
+    assert run.family_of("/x/mnist_test/06_model_experiment/main.py") == "mnist06"
+    assert run.family_of("/x/mnist_test/01_baseline_causal_vae/main.py") == "mnist01"
+    assert run.family_of("/x/causal_cascade/main.py") == "cascade"
+    assert run.family_of("/x/latent_translator/main.py") == "latent_translator"
