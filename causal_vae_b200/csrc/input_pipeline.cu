@@ -113,7 +113,21 @@ __device__ __forceinline__ void width_rows(const float* __restrict__ src, int pi
   float w[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) w[j] = wc[j];
-  for (int rr = rr0; rr < rc; rr += kPreThreads / kTileW) {
+  // three rows per trip: their shared-memory loads are independent, and the loop / address arithmetic is amortised
+  constexpr int kStep = kPreThreads / kTileW;
+  int rr = rr0;
+  for (; rr + 2 * kStep < rc; rr += 3 * kStep) {
+    const float* r0 = src + rr * pitch;
+    const float* r1 = r0 + kStep * pitch;
+    const float* r2 = r1 + kStep * pitch;
+    const float a = aa_taps_n<N>([&](int j) { return r0[j]; }, w);
+    const float b = aa_taps_n<N>([&](int j) { return r1[j]; }, w);
+    const float c = aa_taps_n<N>([&](int j) { return r2[j]; }, w);
+    dst[rr * kTileW] = a;
+    dst[(rr + kStep) * kTileW] = b;
+    dst[(rr + 2 * kStep) * kTileW] = c;
+  }
+  for (; rr < rc; rr += kStep) {
     const float* row = src + rr * pitch;
     dst[rr * kTileW] = aa_taps_n<N>([&](int j) { return row[j]; }, w);
   }
@@ -161,24 +175,21 @@ resize_aa_kernel(const float* __restrict__ raw, float* __restrict__ resized, Pre
     const int rc = min(rows_chunk, nrows - rbase);
     __syncthreads();                                                    // previous chunk consumed, weights visible
     if (vec) {
-      const int p4 = pitch >> 2, total = rc * p4;
-      const unsigned int inv_p4 = 0xffffffffu / (unsigned int)p4 + 1u;   // i / p4 == umulhi(i, inv_p4) for i*p4 < 2^32
-      for (int i0 = tid; i0 < total; i0 += 4 * kPreThreads) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * kPreThreads;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < total) {
-            const int rr = p4 == 1 ? i : (int)__umulhi((unsigned int)i, inv_p4), q = i - rr * p4;
-            if (c0 + 4 * q < Win) v[u] = __ldg(reinterpret_cast<const float4*>(img + (size_t)(rbase + rr) * Win) + q);
-          }
+      // thread = (float4 column q, row ty + 4k): no index division; four independent 128-bit loads in flight per thread
+      const int p4 = pitch >> 2, w4 = Win >> 2;
+      const int tx = tid & (kTileW - 1), ty = tid / kTileW;
+      constexpr int kStep = kPreThreads / kTileW;
+      for (int q = tx; q < p4; q += kTileW) {
+        if (c0 + 4 * q >= Win) continue;                                // right of the image: never read by a tap
+        const float4* g = reinterpret_cast<const float4*>(img + (size_t)rbase * Win) + q;
+        float4* d = reinterpret_cast<float4*>(sraw) + q;
+        int rr = ty;
+        for (; rr + 3 * kStep < rc; rr += 4 * kStep) {
+          const float4 v0 = __ldg(g + (size_t)rr * w4), v1 = __ldg(g + (size_t)(rr + kStep) * w4);
+          const float4 v2 = __ldg(g + (size_t)(rr + 2 * kStep) * w4), v3 = __ldg(g + (size_t)(rr + 3 * kStep) * w4);
+          d[rr * p4] = v0; d[(rr + kStep) * p4] = v1; d[(rr + 2 * kStep) * p4] = v2; d[(rr + 3 * kStep) * p4] = v3;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * kPreThreads;
-          if (i < total) reinterpret_cast<float4*>(sraw)[i] = v[u];
-        }
+        for (; rr < rc; rr += kStep) d[rr * p4] = __ldg(g + (size_t)rr * w4);
       }
     } else {
       const int total = rc * pitch;
