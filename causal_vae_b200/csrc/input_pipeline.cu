@@ -14,6 +14,7 @@
 // HBM-shaped: the raw batch is read once (66 MB at B = 64, 512^2), the resized image (L2-sized per chunk) is written
 // once and re-read twice, the mask is written once.  One CTA = a 64-column x TH-row output tile: the horizontally
 // resized rows it needs live in shared memory, so the intermediate [Hin, W] image of the CPU path never exists.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cvae {
@@ -361,6 +362,10 @@ extern "C" int cvae_vessel_preprocess(const cvae_preproc_t* p, cvae_stream_t s) 
   const int pitch_max = ((int)ceilf(kTileW * sx) + mx + 2 + 3 + 3) & ~3;
   const int budget = 47 * 1024 / (int)sizeof(float);   // dynamic + 64 B static must stay under the 48 KB default
   int TH = 16, rows_max = 0, stage_floats = 0;
+  if (const char* e = getenv("CVAE_PRE_TH")) {          // tile-height experiment switch (power of two)
+    const int v = atoi(e);
+    if (v >= 1 && v <= 128 && (v & (v - 1)) == 0) TH = v;
+  }
   for (; TH >= 1; TH >>= 1) {
     rows_max = (int)ceilf(TH * sy) + my + 2;
     const long long fixed = (long long)rows_max * kTileW + (long long)kTileW * mx + (long long)TH * my;
