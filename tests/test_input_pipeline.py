@@ -197,3 +197,31 @@ def test_gpu_scaler_one_hot_and_edges():
     assert tf.transform(torch.empty(0, 40, 40, device="cuda")).shape == (0, 1, 32, 32)
     with pytest.raises(RuntimeError, match="CUDA"):
         tf.transform(torch.zeros(1, 40, 40))
+
+
+def test_oracle_resize_matches_this_machines_aten_kernel():
+    """Live pin of the resize restatement wherever the tests run: ATen's antialiased bilinear kernel (a third-party
+    library, not the reference tree) on random (in, out) pairs.  The fused / unfused tap pattern is a property of the
+    compiled loop: the AVX2 / AVX512 builds follow the 'aten' pattern, the DEFAULT (no-FMA) build is all-unfused."""
+    import torch.nn.functional as TF
+    cap = torch.backends.cpu.get_cpu_capability()
+    if cap == "DEFAULT":
+        fma = False
+    elif cap in ("AVX2", "AVX512"):
+        fma = "aten"
+    else:                      # other ISAs (VSX, ZVECTOR, SVE): pattern not established here
+        pytest.skip(f"tap-fusion pattern of the {cap} build of ATen not established")
+    rng = np.random.default_rng(11)
+    pairs = [(512, 256), (1280, 256), (96, 128), (300, 128), (379, 289), (2230, 250)]
+    pairs += [(int(rng.integers(20, 2000)), int(rng.integers(16, 300))) for _ in range(24)]
+    for n_in, n_out in pairs:
+        raw = rng.uniform(-500, 1000, size=(3, n_in)).astype(np.float32)
+        want = TF.interpolate(torch.from_numpy(raw)[None, None], size=(3, n_out), mode="bilinear", antialias=True,
+                              align_corners=False)[0, 0].numpy()
+        got = IO.resize_aa(raw, 3, n_out, fma)
+        assert np.array_equal(got, want), (n_in, n_out, int((got != want).sum()))
+    # both axes, the reference's aspect ratio
+    raw = rng.uniform(0, 4000, size=(192, 320)).astype(np.float32)
+    want = TF.interpolate(torch.from_numpy(raw)[None, None], size=(64, 64), mode="bilinear", antialias=True,
+                          align_corners=False)[0, 0].numpy()
+    assert np.array_equal(IO.resize_aa(raw, 64, 64, fma), want)
