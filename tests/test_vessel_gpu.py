@@ -352,3 +352,44 @@ def test_vessel_cnn_variant_matches_oracle_and_golden():
     print("gradient error / tolerance, five worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
     print("violations:", bad)
     assert not bad, bad
+
+
+def test_vessel_cnn_variant_train_step():
+    """train.py:77-86 on the CNN variant through the same fused trainer (flat gradients written in place, weight
+    gradients on the side stream, clip_grad_norm_(5) + Adam in one launch): the loss of the step, the global gradient
+    norm and the first Adam update against the fp64 oracle."""
+    from causal_vae_b200.vessel import models, train
+    with open(os.path.join(G, "vessel_cnn_768x1280_b4.json")) as f:
+        c = json.load(f)["config"]
+    shapes = O.vessel_cnn_shapes(c["z_dim"], c["m_dim"], c["t_dim"])
+    models.CONFIG.update(Z_DIM=c["z_dim"], M_DIM=c["m_dim"], T_DIM=c["t_dim"])
+    sd = O.fill_state_dict(shapes, seed=0)
+    model = models.CausalVesselVAE()
+    model.load_state_dict(sd)
+    model = model.cuda()
+    x, m, t, eps = O.vessel_inputs(c["B"], c["H"], c["W"], c["m_dim"], c["t_dim"], c["z_dim"], seed=0)
+    lr = 1e-4
+    trainer = train.VesselTrainer(model, lr=lr, max_norm=5.0, beta=c["beta"])
+    losses = trainer.step(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    gnorm = float(trainer.flat.grad.double().norm())
+    torch.cuda.synchronize()
+    P64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    _, l64, g64 = O.vessel_cnn_loss_and_grads(P64, x.double(), m.double(), t.double(), eps.double(), c["beta"])
+    assert abs(float(losses[0]) - float(l64["loss"])) <= 1e-5 * abs(float(l64["loss"]))
+    clipped, total = O.clip_grad_norm(g64, 5.0)
+    assert abs(gnorm - float(total)) <= 2e-2 * float(total), (gnorm, float(total))     # whole-network gradient noise floor
+    # first Adam step: every weight moves by lr * gc / (|gc| + 1e-8) with gc the CLIPPED gradient (the global norm is
+    # ~1e6, so gc ~ 1e-7..1e-5 and the 1e-8 matters): just under lr, against the sign of its gradient
+    after = model.state_dict()
+    for k in ("dec_conv.25.weight", "enc_fc.3.weight", "dec_fc.0.weight", "morph_predictor_mu.weight", "enc_conv.0.weight"):
+        d = (after[k].cpu().double() - sd[k].double())
+        assert float(d.abs().max()) <= lr * (1 + 1e-3), k
+        g = g64[k]
+        strong = g.abs() > 1e-2 * g.abs().max()                 # elements whose gradient is far above the noise
+        agree = (torch.sign(d[strong]) == -torch.sign(g[strong])).double().mean().item()
+        assert agree >= 0.99, (k, agree)
+        # magnitude: sensitivity to the ~1-2 % whole-network gradient noise is eps / (|gc| + eps) of it -> 5 % bound
+        want = -lr * clipped[k] / (clipped[k].abs() + 1e-8)
+        assert torch.allclose(d[strong], want[strong], rtol=5e-2, atol=1e-9), (k, float((d - want)[strong].abs().max()))
+    l2 = trainer.step(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    assert float(l2[0]) < float(losses[0])
