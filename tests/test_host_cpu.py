@@ -136,3 +136,19 @@ def test_runner_redirects_models_for_an_unmodified_script(tmp_path):
     assert run.family_of("/x/mnist_test/01_baseline_causal_vae/main.py") == "mnist01"
     assert run.family_of("/x/causal_cascade/main.py") == "cascade"
     assert run.family_of("/x/latent_translator/main.py") == "latent_translator"
+
+
+def test_step_roofline_bytes_follow_the_counting_rule():
+    """bench.py's BYTES_PER_SAMPLE (77 MB activations + 8.8 MB parameter traffic per sample at B = 64)
+    against the layer-table derivation of scripts/algorithmic_bytes.py."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("algbytes", os.path.join(ROOT, "scripts", "algorithmic_bytes.py"))
+    ab = importlib.util.module_from_spec(spec); spec.loader.exec_module(ab)
+    r = ab.vessel_step_bytes(256, 256, 64)
+    assert r["stem_KB"] == [2048, 1024, 512, 256, 64] and sum(r["decoder_KB"]) == 8128 and r["skip_KB"] == 896
+    assert r["params"] == 14065897 and abs(r["param_MB_per_sample"] - 8.8) < 0.05
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    m = re.search(r"BYTES_PER_SAMPLE\s*=\s*([0-9.e+]+)\s*\+\s*([0-9.e+]+)", src)
+    bench_bytes = float(m.group(1)) + float(m.group(2))
+    # the rule gives 80.7 + 8.8 MB in decimal bytes; bench.py uses SURVEY's MiB-rounded 77 + 8.8 (stricter): within 5 %
+    assert bench_bytes <= r["total_MB_per_sample"] * 1e6 <= 1.05 * bench_bytes
