@@ -48,7 +48,10 @@ def counterfactual_sweep(model, m, z, delta=5.0, value=None, return_images=False
     S, K = m.shape
     base = model.decode(m, z)
     rows = do_expand(m, z, delta=delta, value=value)
-    x_cf = model.backbone.decode(model.dec_adapter(rows))
+    if hasattr(model, "dec_adapter"):                      # the ViT / CNN switch of analyze_vessel.py:93-98
+        x_cf = model.backbone.decode(model.dec_adapter(rows))
+    else:
+        x_cf = model.dec_conv(model.dec_fc(rows).view(-1, 512, *model.GRID))
     l2 = rowdiff_l2(x_cf, base, K).view(S, K)
     return l2, (x_cf if return_images else None), base
 

@@ -393,3 +393,33 @@ def test_vessel_cnn_variant_train_step():
         assert torch.allclose(d[strong], want[strong], rtol=5e-2, atol=1e-9), (k, float((d - want)[strong].abs().max()))
     l2 = trainer.step(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
     assert float(l2[0]) < float(losses[0])
+
+
+def test_vessel_cnn_variant_counterfactual_sweep():
+    """do(M_k += 5) over all 12 concepts through the CNN decoder (the `else` branch of analyze_vessel.py:93-98):
+    per-image effect sizes and two decoded images against the oracle decoder, eval mode."""
+    from causal_vae_b200 import counterfactual as CF
+    from causal_vae_b200.vessel import models
+    with open(os.path.join(G, "vessel_cnn_768x1280_b4.json")) as f:
+        c = json.load(f)["config"]
+    models.CONFIG.update(Z_DIM=c["z_dim"], M_DIM=c["m_dim"], T_DIM=c["t_dim"])
+    sd = O.fill_state_dict(O.vessel_cnn_shapes(c["z_dim"], c["m_dim"], c["t_dim"]), seed=0)
+    model = models.CausalVesselVAE()
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    S, K = 2, c["m_dim"]
+    g = torch.Generator().manual_seed(3)
+    m, z = torch.randn(S, K, generator=g), torch.randn(S, c["z_dim"], generator=g)
+    l2, images, base = CF.counterfactual_sweep(model, m.cuda(), z.cuda(), delta=5.0, return_images=True)
+    torch.cuda.synchronize()
+    assert l2.shape == (S, K) and images.shape == (S * K, 1, c["H"], c["W"]) and base.shape == (S, 1, c["H"], c["W"])
+    with torch.no_grad():
+        P = {k: v.double() if v.is_floating_point() else v.clone() for k, v in sd.items()}
+        want_base = O.vessel_cnn_decode(P, m.double(), z.double(), False)
+        assert rel(base, want_base) <= 1e-5
+        for s_, k in ((0, 0), (1, 7)):
+            mp = O.counterfactual_do(m.double(), k, delta=5.0)
+            want = O.vessel_cnn_decode(P, mp[s_:s_ + 1], z[s_:s_ + 1].double(), False)
+            assert rel(images[s_ * K + k], want[0]) <= 1e-5
+            want_l2 = (want[0] - want_base[s_]).flatten().norm().item()
+            assert abs(float(l2[s_, k]) - want_l2) <= 1e-4 * want_l2 + 5e-3, (float(l2[s_, k]), want_l2)
