@@ -3,9 +3,9 @@
 256x256x1 vessel batches, B = 64 per GPU (BASELINE.json configs[3], the config the metric is quoted on).
 
     python bench.py --gpus N --steps K --warmup W            # native sm_100a path (this repo)
-    python bench.py --impl reference ...                      # the reference algorithm on host cores
-                                                              # (oracle port; /root/reference is a
-                                                              # pure-PyTorch repo that cannot travel)
+    python bench.py --impl reference ...                      # the UNMODIFIED reference (baseline/_ref, installed by
+                                                              # baseline/install_reference.py) on the host cores,
+                                                              # same config: B = 64, 256x256, all threads
 Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM (CUDA-graph
 replay of the whole step); `e2e` = the same step driven from pinned HOST buffers with the H2D copies
 and a D2H read of the loss inside the timed region.
@@ -29,6 +29,7 @@ BYTES_PER_SAMPLE = 77e6 + 8.8e6    # irreducible fp32 activation 
 # `ncu --set full` capture summarised in profiles/r1_ncu_halo_stem3_raw.txt (launch 1: 201.6 MB read + 98.5 MB
 # written); algorithmic bytes of that launch: 335.5e6 (part of the re-read reference tensor is served by L2)
 NCU_TRAFFIC_BYTES = 300.1e6
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_halo_stem3_raw.txt launch 1 (dram__bytes_read.sum + dram__bytes_write.sum)"
 
 
 def peaks():
@@ -79,12 +80,18 @@ def synthetic(B, seed):
 
 
 def cpu_reference_step_rate(steps, warmup, B, threads):
-    """The reference algorithm (oracle port of vessel_analysis/01_train/train.py:77-86) on host cores."""
+    """The reference step (vessel_analysis/01_train/train.py:62-98) on host cores: the UNMODIFIED reference modules,
+    loss_function, clip_grad_norm_ and Adam from baseline/_ref (kind "reference"); the oracle port only if that
+    install is missing (kind "port")."""
     import torch
+    from baseline import ref_harness as R
+    x, m, t, eps = synthetic(B, 0)
+    if R.available():
+        v, ms = R.vessel_rate("cpu", B, steps, warmup, (x, m, t), H, W, threads=threads)
+        return v, ms, "reference"
     from oracle import cvae_oracle as O
     torch.set_num_threads(threads)
     P = O.fill_state_dict(O.vessel_shapes(H, W), seed=0)
-    x, m, t, eps = O.vessel_inputs(B, H, W, seed=0)
     state = {}
     times = []
     for i in range(warmup + steps):
@@ -93,7 +100,7 @@ def cpu_reference_step_rate(steps, warmup, B, threads):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return B / dt, dt * 1e3
+    return B / dt, dt * 1e3, "port"
 
 
 def run_reference(args):
@@ -101,15 +108,20 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B = 16
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    v, ms = cpu_reference_step_rate(steps, warmup, B, threads)
+    B = B_PER_GPU
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))      # ~2-5 s per step on the host cores
+    v, ms, kind = cpu_reference_step_rate(steps, warmup, B, threads)
+    what = ("unmodified reference modules + loss_function + clip_grad_norm_ + Adam from baseline/_ref, "
+            "train_one_epoch loop of vessel_analysis/01_train/train.py:62-98") if kind == "reference" else \
+        "oracle port of the reference step (baseline/_ref missing)"
     line = {"impl": "reference", "metric": "train samples/sec (fwd+bwd+step)", "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "vessel_analysis 01_train CausalViTVAE 256x256x1, CPU sample batch 16"},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} steps of batch {B} at 256x256 (oracle port of the reference step)"},
+            "config": {"workload": "vessel_analysis 01_train CausalViTVAE 256x256x1, batch 64 per GPU, dropout 0.1, "
+                                   "fwd+loss+bwd+clip_grad_norm(5)+Adam(1e-4), data-parallel grad all-reduce (SUM)",
+                       "global_batch": B, "parallelism": "cpu"},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": kind,
+                             "sample": f"{steps} timed steps of batch {B} at 256x256 after {warmup} warm-up: {what}"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -251,11 +263,14 @@ def input_pipeline_probe(torch, hbm):
                              "port_value": port, "port_sample": "4 images through oracle/input_oracle.py (numpy, 1 core)"}}
 
 
-def counterfactual_rate(torch, model, sources=256, chunk=32):
+CF_SOURCES = 65536      # BASELINE configs[4]: 65536 source samples, do() on every one of the 12 concepts
+
+
+def counterfactual_rate(torch, model, sources, chunk=32):
     """BASELINE configs[4]: do(M_k += 5) on every concept k of every source, decode, reduce each image to
     ||x_cf - x_base||_2 on device (vessel_analysis/04_generate_counterfactual/generate_counterfactual.py:83-99,
-    analyze_vessel.py:101-115).  A bounded sample of the 65536-source job: `sources` sources x 12 concepts,
-    streamed in chunks; inputs resident in HBM, eval mode."""
+    analyze_vessel.py:101-115).  `sources` = this rank's shard of the 65536-source job (sources shard across ranks
+    with no collective), streamed in chunks; inputs resident in HBM, eval mode."""
     from causal_vae_b200 import counterfactual as CF
     from causal_vae_b200.vessel import models
     model.eval()
@@ -278,6 +293,225 @@ def counterfactual_rate(torch, model, sources=256, chunk=32):
     return sources * K / (ms * 1e-3), ms, float(acc)
 
 
+def parity_check(torch, models, train):
+    """One dropout-free step of the SAME trainer code on the golden weights / inputs at the bench shape
+    (256x256, B = 64) against the live-reference golden tests/golden/vessel_256x256_b64.json: a bench line is also
+    a parity line.  Loss terms at the north-star 1e-5, the clipped-norm input (global gradient norm) at
+    max(1e-4, 4 x the reference's own fp32-vs-fp64 discrepancy recorded in the golden)."""
+    from oracle import cvae_oracle as O          # deterministic weight / input generator only
+    gpath = os.path.join(ROOT, "tests", "golden", "vessel_256x256_b64.json")
+    gold = json.load(open(gpath))["train"]
+    model = models.CausalViTVAE()
+    model.load_state_dict(O.fill_state_dict(O.vessel_shapes(H, W), seed=0))
+    model = model.cuda()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if hasattr(mod, "in_proj_weight"):
+            mod.dropout = 0.0
+    x, m, t, eps = (a.cuda() for a in O.vessel_inputs(B_PER_GPU, H, W, seed=0))
+    tr = train.VesselTrainer(model, lr=1e-4)
+    losses = tr._fwd_bwd(x, m, t, eps)
+    gnorm = float(tr.flat.grad.double().norm())
+    names = ["loss", "recon", "kld", "morph", "sparsity"]
+    out = {"golden": "tests/golden/vessel_256x256_b64.json (live reference, CPU fp32)", "tolerance_losses": 1e-5}
+    worst = 0.0
+    for n, v in zip(names, losses):
+        e = abs(float(v) - gold[n]) / abs(gold[n])
+        out[n] = {"got": float(v), "want": gold[n], "rel_err": e}
+        worst = max(worst, e)
+    noise = sorted(v for v in gold["grad_noise_fp32_vs_fp64"].values() if v < 1.0)
+    tol_g = max(1e-4, 4 * noise[len(noise) // 2])
+    eg = abs(gnorm - gold["grad_total_norm"]) / gold["grad_total_norm"]
+    out["grad_total_norm"] = {"got": gnorm, "want": gold["grad_total_norm"], "rel_err": eg, "tolerance": tol_g}
+    out["ok"] = bool(worst <= 1e-5 and eg <= tol_g)
+    del tr, model
+    torch.cuda.empty_cache()
+    if not out["ok"]:
+        raise SystemExit("bench parity check failed: " + json.dumps(out))
+    return out
+
+
+def tf32_gemm_peak(torch):
+    """cuBLAS TF32 GEMM rate (torch.matmul on fp32 8192^3 with allow_tf32): the single-pass tensor ceiling the
+    3xTF32 kernels are a third of (SURVEY 8d asked for it beside the bf16 figure of MEASURED_PEAKS.json)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    a = torch.randn(n, n, device="cuda"); b = torch.randn(n, n, device="cuda")
+    for _ in range(3):
+        a @ b
+    best = 1e9
+    for _ in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def eager_gpu_baseline(torch, steps=10, warmup=3):
+    """The UNMODIFIED reference (baseline/_ref) in eager PyTorch on the SAME B200, same batch: the number to beat
+    (BASELINE.md 3).  TF32 at PyTorch's defaults (cuDNN conv TF32 on, matmul TF32 off) and fully off
+    (the fp32-parity setting).  Wall clock around the reference's own epoch loop with a device synchronize on both
+    sides; includes its per-step H2D copies and .item() reads, exactly as the reference runs."""
+    from baseline import ref_harness as R
+    if not R.available():
+        return {"unavailable": "baseline/_ref missing (run baseline/install_reference.py in the build container)"}
+    out = {"impl": "unmodified reference, eager PyTorch " + torch.__version__, "batch": B_PER_GPU, "steps": steps,
+           "warmup": warmup}
+    x, m, t, _ = synthetic(B_PER_GPU, 0)
+    for key, cud, mm in (("tf32_default", True, False), ("tf32_off", False, False), ("tf32_all", True, True)):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = cud, mm
+        v, ms = R.vessel_rate("cuda", B_PER_GPU, steps, warmup, (x, m, t), H, W)
+        out[key] = {"value": v, "unit": "samples/s", "ms_per_step": ms, "cudnn_tf32": cud, "matmul_tf32": mm}
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = False, False
+    cf, cf_ms, done = R.vessel_counterfactual_rate("cuda", 2048, 32, max_seconds=10.0)
+    out["counterfactual_tf32_off"] = {"value": cf, "unit": "images/s", "sample": f"{done} sources x 12 concepts, chunks of 32"}
+    torch.backends.cudnn.allow_tf32 = True
+    cf, cf_ms, done = R.vessel_counterfactual_rate("cuda", 2048, 32, max_seconds=10.0)
+    out["counterfactual_tf32_default"] = {"value": cf, "unit": "images/s", "sample": f"{done} sources x 12 concepts, chunks of 32"}
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---- BASELINE configs[0..2]: mnist 01 / causal_cascade / latent_translator -------------------------------------------
+# Algorithmic bytes per sample, same counting rule as the vessel step (scripts/algorithmic_bytes.py): every activation
+# that must cross a kernel boundary is written once and read once in forward (2 x A), backward costs twice the forward
+# (=> 6 x A per fwd+bwd; the MNIST adversarial step is 3 forwards + 1 backward + the discriminator => 10 x A), plus
+# 40 B per parameter per optimizer step (weights read in fwd and bwd, gradient written, 28 B fused Adam) / batch.
+# A (activation bytes per sample) and the parameter counts are SURVEY 8(d)'s measured figures.
+SMALL = {
+    "mnist01": {"workload": "mnist_test 01_baseline_causal_vae CausalMorphVAE12 + LatentDiscriminator, 28x28x1, "
+                            "4 concepts, batch 64 per GPU, adversarial step (D step + VAE step, 2 Adams lr 1e-3)",
+                "B": 64, "act": 0.17e6, "passes": 10, "params": 1.77e6, "flop": 0.051e9},
+    "cascade": {"workload": "causal_cascade CausalBioVAE 64x64x1, 8 concepts, 19 treatments, batch 256 per GPU, "
+                            "fwd+loss+bwd+Adam(1e-3)",
+                "B": 256, "act": 1.0e6, "passes": 6, "params": 3.96e6, "flop": 0.323e9},
+    "latent_translator": {"workload": "latent_translator ViTVAE 128x128x1, latent 512, batch 128 per GPU, dropout 0.1, "
+                                      "fwd+loss+bwd+Adam(1e-4)",
+                          "B": 128, "act": 11.4e6, "passes": 6, "params": 7.30e6, "flop": 1.378e9},
+}
+
+
+def _small_trainer(torch, name, dist):
+    """(graphed step, pinned host batch dict, loss getter) of one small config on the native path."""
+    g = torch.Generator().manual_seed(19)
+    B = SMALL[name]["B"]
+    torch.manual_seed(0)
+    if name == "mnist01":
+        from causal_vae_b200.mnist import models, train
+        models.CONFIG["M_DIM"], models.CONFIG["T_DIM"], models.CONFIG["Z_DIM"] = 4, 10, 10
+        vae, disc = models.CausalMorphVAE12().cuda(), models.LatentDiscriminator().cuda()
+        tr = train.AdversarialTrainer(vae, disc, lr=1e-3, distributed=dist)
+        gs = tr.capture(B)
+        host = dict(x=torch.rand(B, 1, 28, 28, generator=g), m=torch.rand(B, 4, generator=g),
+                    t=torch.eye(10)[torch.randint(0, 10, (B,), generator=g)], eps_d=torch.randn(B, 10, generator=g),
+                    eps=torch.randn(B, 10, generator=g), eps_adv=torch.randn(B, 10, generator=g))
+        loss = lambda out: out[1][0]
+        mods = [vae, disc]
+    elif name == "cascade":
+        from causal_vae_b200.cascade import models, train
+        model = models.CausalBioVAE(img_channels=1, m_dim=8, t_dim=19, latent_dim=64).cuda()
+        tr = train.CascadeTrainer(model, lr=1e-3, distributed=dist)
+        gs = tr.capture(B)
+        host = dict(x=torch.randn(B, 1, 64, 64, generator=g), m=torch.rand(B, 8, generator=g),
+                    t=torch.randint(0, 19, (B,), generator=g), eps=torch.randn(B, 64, generator=g))
+        loss = lambda out: out[0]
+        mods = [model]
+    else:
+        from causal_vae_b200.latent_translator import engine, models
+        model = models.ViTVAE(img_size=(128, 128)).cuda()
+        tr = engine.ViTVAETrainer(model, lr=1e-4, distributed=dist)
+        gs = tr.capture(B, 128, 128)
+        host = dict(x=torch.rand(B, 1, 128, 128, generator=g), eps=torch.randn(B, 512, generator=g))
+        loss = lambda out: out[0]
+        mods = [model]
+    if dist:
+        import torch.distributed as td
+        for mod in mods:
+            for p in mod.parameters():
+                td.broadcast(p.data, 0)
+    return gs, {k: v.pin_memory() for k, v in host.items()}, loss, tr
+
+
+def small_config_line(torch, name, world, rank, dist, barrier, steps, hbm, with_baselines):
+    from causal_vae_b200 import _lib as L
+    cfg = SMALL[name]
+    B = cfg["B"]
+    n0 = L.launch_count
+    gs, pin, loss_of, tr = _small_trainer(torch, name, dist)
+    launches = (L.launch_count - n0) // 4          # 3 eager warm-up steps + the captured one
+    gs.load(**{k: v.cuda() for k, v in pin.items()})
+    for _ in range(5):
+        gs.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = gs.replay()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    first = float(loss_of(out))
+    # end to end: pinned host batch -> H2D -> graph replay -> D2H read of the loss, every step
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(steps):
+        gs.load(**pin)
+        out = gs.replay()
+        last = loss_of(out).item()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    if dist:
+        import torch.distributed as td
+        tt = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        td.all_reduce(tt, op=td.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+    if rank != 0:
+        return None
+    bytes_per_sample = cfg["passes"] * cfg["act"] + 40.0 * cfg["params"] / B
+    value = world * B * steps / (ms * 1e-3)
+    roof = hbm * 1e9 / bytes_per_sample
+    line = {"metric": "train samples/sec (fwd+bwd+step)", "config": {"workload": cfg["workload"], "global_batch": world * B},
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "ms_per_step": ms / steps,
+            "gpu_launches": launches * steps, "loss_first": first, "loss_last": last,
+            "e2e": {"value": world * B * steps / (ms_e2e * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pin.values()), "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "hbm", "bytes_per_sample": bytes_per_sample, "peak": hbm, "unit": "GB/s",
+                         "achieved": value / world * bytes_per_sample / 1e9, "frac": (value / world) / roof,
+                         "roofline_samples_per_s_per_gpu": roof,
+                         "achieved_tflops": value / world * cfg["flop"] / 1e12,
+                         "note": f"whole step: {launches} launches in {ms / steps * 1e3:.0f} us -> "
+                                 f"{ms / steps * 1e3 / max(launches, 1):.1f} us per launch; at this size the step is "
+                                 "launch/latency-bound (SURVEY 8d), the HBM figure is the ceiling, not the limiter"}}
+    if with_baselines:
+        from baseline import ref_harness as R
+        if R.available():
+            threads = os.cpu_count() or 1
+            fn = {"mnist01": lambda dev, st, wu, **kw: R.mnist_rate(dev, B, st, wu, M=4, **kw),
+                  "cascade": lambda dev, st, wu, **kw: R.cascade_rate(dev, B, st, wu, **kw),
+                  "latent_translator": lambda dev, st, wu, **kw: R.lt_rate(dev, B, st, wu, **kw)}[name]
+            cst = {"mnist01": 20, "cascade": 4, "latent_translator": 2}[name]
+            v, cms = fn("cpu", cst, 1, threads=threads)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "reference",
+                                    "sample": f"{cst} timed steps of batch {B} (unmodified reference modules and loop, baseline/_ref)"}
+            eg = {}
+            for key, cud in (("tf32_default", True), ("tf32_off", False)):
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = cud, False
+                v, gms = fn("cuda", 20, 5)
+                eg[key] = {"value": v, "unit": "samples/s", "ms_per_step": gms}
+            torch.backends.cudnn.allow_tf32 = True
+            line["eager_gpu_baseline"] = eg
+    del gs, tr
+    torch.cuda.empty_cache()
+    return line
+
+
 def run_native(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -293,6 +527,14 @@ def run_native(args):
     from causal_vae_b200 import ops
     from causal_vae_b200.vessel import models, train
     models.CONFIG["IMG_HEIGHT"], models.CONFIG["IMG_WIDTH"] = H, W
+    strong = args.global_batch is not None
+    B = B_PER_GPU if not strong else args.global_batch // world
+    if strong and B * world != args.global_batch:
+        raise SystemExit("--global-batch must be divisible by the number of GPUs")
+
+    # ---- parity at the bench shape first: a line whose numbers differ from the reference's is not a result ----
+    parity = parity_check(torch, models, train) if rank == 0 and not args.no_parity else None
+
     torch.manual_seed(0)
     model = models.CausalViTVAE().cuda()            # random init of the reference architecture (dropout 0.1 as shipped)
     if dist:
@@ -301,7 +543,6 @@ def run_native(args):
         for b in model.buffers():
             td.broadcast(b, 0)
     trainer = train.VesselTrainer(model, lr=1e-4, max_norm=5.0, distributed=dist)
-    B = B_PER_GPU
     x, m, t, eps = synthetic(B, seed=rank)
     pin = [a.pin_memory() for a in (x, m, t, eps)]
     n0 = L.launch_count
@@ -348,48 +589,70 @@ def run_native(args):
         loss_e2e = trainer.static_losses[0].detach().item()      # D2H read of the step's loss
     e3.record()
     barrier()
-    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 * 0.0)
+    ms_e2e = e2.elapsed_time(e3)
+    wall_e2e = (time.perf_counter() - t0) * 1e3      # host clock around the same region, reported beside the events
     h2d = sum(a.numel() * a.element_size() for a in pin)
 
-    # ---- counterfactual generation (every rank decodes its own shard of sources; no collective) ----
+    # ---- counterfactual generation: the full 65536-source job, sources sharded over the ranks, no collective ----
+    cf_sources = max(32, (args.cf_sources // world) // 32 * 32)
     barrier()
-    cf_rate, cf_ms, _ = counterfactual_rate(torch, model)
+    cf_rate, cf_ms, _ = counterfactual_rate(torch, model, cf_sources)
     barrier()
 
     if dist:
         tt = torch.tensor([ms, ms_e2e, cf_ms], device="cuda", dtype=torch.float64)
         td.all_reduce(tt, op=td.ReduceOp.MAX)
         ms, ms_e2e, cf_ms = tt.tolist()
-    cf_rate = 256 * 12 / (cf_ms * 1e-3)                 # per-GPU rate at the slowest rank
+    cf_rate = cf_sources * 12 / (cf_ms * 1e-3)          # per-GPU rate at the slowest rank
+
+    hbm, bf16_burst, bf16_sus, how = peaks()
+    del trainer
+    torch.cuda.empty_cache()
+    # ---- BASELINE configs[0..2] on the same ranks (every rank takes part: data-parallel all-reduce inside) ----
+    small = {}
+    if not args.no_small and not strong:
+        for name in ("mnist01", "cascade", "latent_translator"):
+            try:
+                small[name] = small_config_line(torch, name, world, rank, dist, barrier, max(args.steps, 20), hbm,
+                                                with_baselines=(world == 1 and not args.no_baselines))
+            except Exception as e:                       # never lose the headline line to an auxiliary config
+                small[name] = {"error": repr(e)}
     if rank != 0:
         _finish(dist)
         return
 
-    hbm, bf16_burst, bf16_sus, how = peaks()
     ms_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
     e2e_v = world * B * args.steps / (ms_e2e * 1e-3)
     probe = dominant_kernel_probe(torch, ops, L)
     threads = os.cpu_count() or 1
-    cpu_v, cpu_ms = cpu_reference_step_rate(2, 1, 16, threads)
+    base = world == 1 and not args.no_baselines
+    if base:
+        cpu_v, cpu_ms, cpu_kind = cpu_reference_step_rate(2, 1, B_PER_GPU, threads)
+        eager = eager_gpu_baseline(torch)
+        tf32_peak = tf32_gemm_peak(torch)
+    else:
+        cpu_v = cpu_kind = eager = tf32_peak = None
     try:
-        input_line = input_pipeline_probe(torch, hbm)
+        input_line = input_pipeline_probe(torch, hbm) if base else None
     except Exception as e:                               # never lose the training line to the auxiliary probe
         input_line = {"error": repr(e)}
     ach_gbs = probe["hbm_bytes"] / (probe["hbm_ms"] * 1e-3) / 1e9
     ach_tf = probe["tc_flops"] / (probe["tc_ms"] * 1e-3) / 1e12
+    bytes_per_sample = 77e6 + 8.8e6 * B_PER_GPU / B     # parameter / optimizer traffic is per step, not per sample
     line = {
         "metric": "train samples/sec (fwd+bwd+step)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "vessel_analysis 01_train CausalViTVAE 256x256x1, batch 64 per GPU, dropout 0.1, "
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"vessel_analysis 01_train CausalViTVAE 256x256x1, batch {B} per GPU, dropout 0.1, "
                                "fwd+loss+bwd+clip_grad_norm(5)+Adam(1e-4), data-parallel grad all-reduce (SUM)",
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "per-step working set (~5 GB of fp32 activations at B=64) is >> the 126 MB L2; "
                          "the kernel probes flush L2 with a 256 MiB write between launches"},
         "loss": loss,
+        "parity": parity,
         "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "ms_per_step_host_clock": wall_e2e / args.steps},
         "gpu_launches": per_step_calls * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
@@ -398,7 +661,7 @@ def run_native(args):
                                "stem.3 Conv2d(32->64, s2) input gradient, 64^2 -> 128^2, B=64",
                      "bytes_per_launch": probe["hbm_bytes"], "ms_per_launch": probe["hbm_ms"],
                      "peak_source": f"{how} copy bandwidth (burst: kernel timed alone)",
-                     "traffic_source": "profiles/r1_ncu_halo_stem3_raw.txt launch 1 (dram__bytes_read.sum + dram__bytes_write.sum)"},
+                     "traffic_source": NCU_TRAFFIC_SOURCE},
         "roofline_stream": {"bound": "hbm", "achieved": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9, "peak": hbm,
                             "unit": "GB/s", "frac": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9 / hbm,
                             "traffic": 286.5e6,
@@ -407,24 +670,32 @@ def run_native(args):
                             "bytes_per_launch": probe["few_bytes"], "ms_per_launch": probe["few_ms"],
                             "traffic_source": "profiles/r1_ncu_few_raw.txt launch 0"},
         "roofline_tensor": {"bound": "tensor", "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s",
-                            "frac": ach_tf / bf16_burst,
+                            "frac": ach_tf / bf16_burst, "tf32_gemm_peak_tflops": tf32_peak,
+                            "frac_of_tf32_gemm_peak": (ach_tf / tf32_peak) if tf32_peak else None,
                             "kernel": "conv_halo_tc_kernel on stem.6 forward (Conv 64->128 s2 @64^2, B=64)",
                             "flops_per_launch": probe["tc_flops"], "ms_per_launch": probe["tc_ms"],
-                            "peak_source": f"{how} bf16 burst; fp32-grade 3xTF32 issues 3 tf32 MMAs per product and a "
-                                           "kind::tf32 MMA (K=8) costs >= 96 clk from shared memory whatever N <= 128 is "
-                                           "(scripts/umma_rate.cu, profiles/r1_umma_probes.txt): ceiling = 128*N*8 MAC / 96 clk / 3"},
-        "step_roofline": {"bound": "hbm", "bytes_per_sample": BYTES_PER_SAMPLE, "peak_gbs": hbm,
-                          "roofline_samples_per_s_per_gpu": hbm * 1e9 / BYTES_PER_SAMPLE,
-                          "frac": (value / world) / (hbm * 1e9 / BYTES_PER_SAMPLE),
+                            "peak_source": f"{how} bf16 burst; tf32_gemm_peak_tflops = cuBLAS TF32 8192^3 measured in this run; "
+                                           "fp32-grade split-TF32 issues 2-3 tf32 MMAs per product and a kind::tf32 MMA "
+                                           "(K=8) costs >= 96 clk from shared memory whatever N <= 128 is "
+                                           "(scripts/umma_rate.cu, profiles/r1_umma_probes.txt)"},
+        "step_roofline": {"bound": "hbm", "bytes_per_sample": bytes_per_sample, "peak_gbs": hbm,
+                          "roofline_samples_per_s_per_gpu": hbm * 1e9 / bytes_per_sample,
+                          "frac": (value / world) / (hbm * 1e9 / bytes_per_sample),
                           "achieved_tflops": value / world * FLOP_PER_SAMPLE / 1e12},
         "counterfactual": {"metric": "counterfactuals/sec (do(M_k += 5) over all 12 concepts, decode 256x256, "
                                      "per-image L2 effect reduced on device)",
                            "value": cf_rate * world, "unit": "images/s", "n_gpus": world,
-                           "sample": "256 sources x 12 concepts per GPU in chunks of 32 sources (bounded sample of the "
-                                     "65536-source job of BASELINE configs[4]; sources shard across GPUs with no collective)",
-                           "ms": cf_ms},
-        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": "2 timed steps of batch 16 at 256x256 (oracle port of the reference step)"},
+                           "sample": f"{cf_sources * world} sources x 12 concepts = {cf_sources * world * 12} decoded images "
+                                     f"({cf_sources} sources per GPU in chunks of 32; BASELINE configs[4] is 65536 sources; "
+                                     "sources shard across GPUs with no collective)",
+                           "ms": cf_ms,
+                           "roofline": {"bound": "hbm", "bytes_per_image": 16.5e6, "peak": hbm, "unit": "GB/s",
+                                        "frac": cf_rate * 16.5e6 / 1e9 / hbm}},
+        "cpu_baseline": ({"value": cpu_v, "unit": "samples/s", "cores": threads, "kind": cpu_kind,
+                          "sample": f"2 timed steps of batch {B_PER_GPU} at 256x256 after 1 warm-up (unmodified reference "
+                                    "modules, loss_function, clip_grad_norm_, Adam: baseline/_ref)"} if base else None),
+        "eager_gpu_baseline": eager,
+        "configs": small,
         "input_pipeline": input_line,
     }
     print(json.dumps(line))
@@ -447,6 +718,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--global-batch", type=int, default=None,
+                    help="strong-scaling point: total batch split over the GPUs (default: weak scaling, 64 per GPU)")
+    ap.add_argument("--cf-sources", type=int, default=CF_SOURCES, help="counterfactual job size (sources, all ranks)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden parity step (profiling runs)")
+    ap.add_argument("--no-small", action="store_true", help="skip BASELINE configs[0..2]")
+    ap.add_argument("--no-baselines", action="store_true", help="skip the CPU / eager-GPU reference legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

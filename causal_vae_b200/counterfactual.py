@@ -114,6 +114,8 @@ class CounterfactualEngine:
         model.eval()
         p0 = next(model.parameters())
         self.plan = ops.PackPlan()
+        self._params = list(model.parameters())
+        self._wver = self._weight_version()
         self.lanes = []
         self._next = 0
         for _ in range(max(1, int(lanes))):
@@ -141,9 +143,14 @@ class CounterfactualEngine:
             self.plan.finalize()
         return l2
 
+    def _weight_version(self):
+        """changes whenever a parameter is written in place (optimizer step, load_state_dict, copy_)"""
+        return sum(p._version for p in self._params) + sum(p.data_ptr() for p in self._params[:1])
+
     def refresh(self):
         """re-pack every weight layout from the model's current parameters (one launch)"""
         self.plan.run()
+        self._wver = self._weight_version()
 
     def _launch(self, m, z):
         if m.shape[0] != self.chunk:
@@ -152,6 +159,11 @@ class CounterfactualEngine:
         self._next = (self._next + 1) % len(self.lanes)
         st = lane["stream"]
         st.wait_stream(torch.cuda.current_stream())       # inputs are ready; the lane's previous result was consumed
+        if self._weight_version() != self._wver:          # weights moved since the layouts were packed: repack first
+            for ln in self.lanes:                         # (every lane's graph reads the same packed buffers)
+                torch.cuda.current_stream().wait_stream(ln["stream"])
+            self.refresh()
+            st.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(st):
             lane["m"].copy_(m, non_blocking=True)
             lane["z"].copy_(z, non_blocking=True)

@@ -8,20 +8,67 @@ from . import ops
 # Every dropout site of a forward pass takes a fresh `offset`; (seed, offset) are host integers baked
 # into the launch, and `counter` is an optional device int64 (e.g. the optimizer step) mixed into the
 # seed on the device so that a replayed CUDA graph still draws new masks every step.
-_rng = {"seed": 0x5EED, "offset": 0, "counter": None}
+#
+# The state is an object, not a module global: every trainer owns one (seed derived from the user's
+# torch.manual_seed / F.manual_seed and from the data-parallel RANK, so shards draw independent masks as the
+# reference's single-device run over the concatenated batch would; counter = that trainer's own step counter)
+# and installs it around its forward pass with `use_rng`.  Code outside a trainer uses the default state.
+_MASK63 = 2 ** 63 - 1
+
+
+class RngState:
+    def __init__(self, seed=None, counter=None, rank=0):
+        base = default_seed() if seed is None else int(seed)
+        # splitmix-style mixing: distinct (seed, rank) pairs give unrelated Philox keys
+        self.seed = ((base + 1) * 0x9E3779B97F4A7C15 + int(rank) * 0xD1B54A32D192ED03) & _MASK63
+        self.offset = 0
+        self.counter = counter
+
+
+_explicit_seed = [None]
+_default = [None]
+_current = [None]
+
+
+def default_seed():
+    """F.manual_seed(s) if it was called, else the seed of torch's default generator (torch.manual_seed)."""
+    return torch.initial_seed() & _MASK63 if _explicit_seed[0] is None else _explicit_seed[0]
 
 
 def manual_seed(seed):
-    _rng["seed"], _rng["offset"] = int(seed) & (2 ** 63 - 1), 0
+    _explicit_seed[0] = int(seed) & _MASK63
+    _default[0] = None
+
+
+def _state():
+    if _current[0] is not None:
+        return _current[0]
+    if _default[0] is None:
+        _default[0] = RngState()
+    return _default[0]
+
+
+class use_rng:
+    """with use_rng(state): dropout sites inside draw from `state` (trainers wrap their forward pass)."""
+    def __init__(self, state):
+        self.state = state
+    def __enter__(self):
+        self.prev = _current[0]
+        _current[0] = self.state
+        return self.state
+    def __exit__(self, *a):
+        _current[0] = self.prev
 
 
 def set_rng_counter(t):
-    _rng["counter"] = t
+    """device step counter of the DEFAULT state (trainers pass theirs through RngState(counter=...))."""
+    _state().counter = t
 
 
 def next_rng():
-    _rng["offset"] += 1
-    return _rng["seed"], _rng["offset"], _rng["counter"]
+    st = _state()
+    st.offset += 1
+    return st.seed, st.offset, st.counter
 
 
 # ---- layout -------------------------------------------------------------------------------------

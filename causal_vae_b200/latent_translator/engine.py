@@ -5,7 +5,9 @@ import torch
 
 from .. import functional as F
 from ..chain import direct_grads
+from ..graph import GraphedStep, trainer_state
 from ..optim import FlatParams, FusedClipAdam
+from ..parallel import allreduce_gradients
 
 
 def loss_function(recons, x, mu, log_var, beta=1.0):
@@ -19,19 +21,38 @@ class ViTVAETrainer:
     """zero_grad, forward, loss, backward, Adam(lr=1e-4) step (engine.py:19-30; main.py:29).
     Data-parallel use averages the gradients (mean-reduced loss): grad_scale = 1/world."""
 
-    def __init__(self, model, lr=1e-4, beta=1.0, grad_scale=1.0):
+    def __init__(self, model, lr=1e-4, beta=1.0, grad_scale=1.0, distributed=False, process_group=None):
         self.model, self.beta = model, beta
+        self.distributed, self.pg = distributed, process_group
+        rank = 0
+        if distributed:
+            import torch.distributed as dist
+            rank = dist.get_rank(process_group)
+            grad_scale = grad_scale / dist.get_world_size(process_group)      # mean-reduced loss: average
         self.opt = FusedClipAdam(FlatParams(model), lr, grad_scale=grad_scale)
+        self.rng = F.RngState(counter=self.opt.step_count, rank=rank)         # this trainer's dropout generator
+        self.graphed = None
 
     def step(self, x, eps=None):
         self.model.train()
         self.opt.zero_grad()
-        recons, _, mu, log_var = self.model(x, eps)
+        with F.use_rng(self.rng):
+            recons, _, mu, log_var = self.model(x, eps)
         loss, rl, kl = loss_function(recons, x, mu, log_var, self.beta)
         with direct_grads():
             loss.backward()
+        if self.distributed:
+            allreduce_gradients(self.opt.flat.grad, group=self.pg)
         self.opt.step()
         return loss, rl, kl
+
+    def capture(self, B, H, W, latent=512, warmup=3):
+        """The whole step (engine.py:19-30) as one CUDA graph over static x and eps."""
+        dev = self.opt.flat.data.device
+        st = dict(x=torch.zeros(B, 1, H, W, device=dev), eps=torch.zeros(B, latent, device=dev))
+        self.graphed = GraphedStep(lambda: self.step(st["x"], st["eps"]), st,
+                                   trainer_state([self.model], [self.opt]), warmup)
+        return self.graphed
 
 
 def train_vit_vae(model, loader, optimizer, device, epochs, beta=1.0):

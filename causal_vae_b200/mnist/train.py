@@ -4,7 +4,9 @@ mnist_test/06_model_experiment/train.py:41-96) on the native kernels: discrimina
 import torch
 
 from .. import functional as F
+from ..graph import GraphedStep, trainer_state
 from ..optim import FlatParams, FusedClipAdam
+from ..parallel import allreduce_gradients
 from .models import CONFIG
 
 
@@ -35,9 +37,11 @@ def disc_loss(vae, disc, x, m, t, eps=None):
 class AdversarialTrainer:
     """opt_d / opt_vae = Adam(lr=CONFIG['LR']) over flat parameter buffers (train.py:21-22)."""
 
-    def __init__(self, vae, disc, lr=None):
+    def __init__(self, vae, disc, lr=None, distributed=False, process_group=None):
         lr = CONFIG["LR"] if lr is None else lr
         self.vae, self.disc = vae, disc
+        self.distributed, self.pg = distributed, process_group
+        self.graphed = None
         self.opt_vae = FusedClipAdam(FlatParams(vae), lr)
         self.opt_d = FusedClipAdam(FlatParams(disc), lr)
 
@@ -46,9 +50,26 @@ class AdversarialTrainer:
         self.opt_d.zero_grad()
         loss_d = disc_loss(self.vae, self.disc, x, m, t, eps_d)
         loss_d.backward()
+        if self.distributed:        # CE is batch-MEAN reduced (train.py:55): average the shard gradients
+            allreduce_gradients(self.opt_d.flat.grad, group=self.pg, mean=True)
         self.opt_d.step()
         self.opt_vae.zero_grad()
         losses = vae_loss(self.vae, self.disc, x, m, t, eps, eps_adv)
         losses[0].backward()
+        if self.distributed:        # sum-reduced terms: SUM (the batchmean confusion term is left per shard)
+            allreduce_gradients(self.opt_vae.flat.grad, group=self.pg)
         self.opt_vae.step()
         return loss_d, losses
+
+    def capture(self, B, warmup=3):
+        """Both halves of the adversarial step (train.py:41-89) as one CUDA graph over static x, m, t and the three
+        reparameterisation noises (discriminator pass, VAE pass, confusion-loss sample)."""
+        dev = self.opt_vae.flat.data.device
+        Z, M, T = CONFIG["Z_DIM"], CONFIG["M_DIM"], CONFIG["T_DIM"]
+        st = dict(x=torch.zeros(B, 1, 28, 28, device=dev), m=torch.zeros(B, M, device=dev),
+                  t=torch.zeros(B, T, device=dev), eps_d=torch.zeros(B, Z, device=dev),
+                  eps=torch.zeros(B, Z, device=dev), eps_adv=torch.zeros(B, Z, device=dev))
+        st["t"][:, 0] = 1.0
+        self.graphed = GraphedStep(lambda: self.step(st["x"], st["m"], st["t"], st["eps_d"], st["eps"], st["eps_adv"]),
+                                   st, trainer_state([self.vae, self.disc], [self.opt_vae, self.opt_d]), warmup)
+        return self.graphed

@@ -55,7 +55,13 @@ class VesselTrainer:
             if self._seg is not None:
                 self.comm = torch.cuda.Stream()
                 model._decoder_grad_hook = self._early_allreduce
-        F.set_rng_counter(self.opt.step_count)
+        rank = 0
+        if distributed:
+            import torch.distributed as dist
+            rank = dist.get_rank(process_group)
+        # this trainer's own dropout generator: seeded from torch.manual_seed / F.manual_seed and the rank (shards of a
+        # data-parallel batch draw independent masks), keyed on this trainer's step counter so graph replays differ
+        self.rng = F.RngState(counter=self.opt.step_count, rank=rank)
 
     def _fwd_bwd(self, x, m, t, eps):
         ops.arena_begin(self.flat.data.device)
@@ -77,7 +83,8 @@ class VesselTrainer:
             if packed:
                 self.pack_plan.run()      # every weight layout of the step, one launch
         try:
-            out = self.model(x, m, t, eps)
+            with F.use_rng(self.rng):
+                out = self.model(x, m, t, eps)
             recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
             loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
             # zero_grad() above zeroed the flat buffer and every parameter is used once: gradients are written

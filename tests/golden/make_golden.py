@@ -71,8 +71,10 @@ class EpsInjector:
 def summarize(t: torch.Tensor, n=8):
     t = t.detach().double().flatten()
     idx = torch.linspace(0, t.numel() - 1, min(n, t.numel()), dtype=torch.float64).long().clamp_(max=t.numel() - 1)
+    s101 = t[::101]                                  # strided ~1 % sample: a second, position-sensitive checksum
     return {"numel": t.numel(), "sum": t.sum().item(), "l2": t.norm().item(),
-            "absmax": t.abs().max().item(), "idx": idx.tolist(), "val": t[idx].tolist()}
+            "absmax": t.abs().max().item(), "idx": idx.tolist(), "val": t[idx].tolist(),
+            "s101_sum": s101.sum().item(), "s101_l2": s101.norm().item()}
 
 
 def noise_floor(g32, g64):
@@ -175,7 +177,7 @@ def golden_vessel(H, W, B, tag, out):
     out[tag] = rec
 
 
-def golden_lt(H, W, B, out):
+def golden_lt(H, W, B, out, tag="latent_translator"):
     mod = load_ref(os.path.join(REF, "latent_translator/models.py"), "ref_lt_models")
     model = mod.ViTVAE(img_size=(H, W))
     set_dropout_zero(model)
@@ -202,7 +204,7 @@ def golden_lt(H, W, B, out):
     (torch.nn.functional.mse_loss(r64, x.double()) - 0.5 * torch.mean(1 + lv64 - mu64.pow(2) - lv64.exp())).backward()
     noise = noise_floor({k: p.grad for k, p in model.named_parameters() if p.grad is not None},
                         {k: p.grad for k, p in m64.named_parameters() if p.grad is not None})
-    out["latent_translator"] = {
+    out[tag] = {
         "grad_noise_fp32_vs_fp64": noise,
         "config": {"H": H, "W": W, "B": B, "wseed": 3, "xseed": 5}, "state_dict_shapes": shp,
         "loss": loss.item(), "recon": rl.item(), "kld": kl.item(),
@@ -210,7 +212,7 @@ def golden_lt(H, W, B, out):
         "grads": {k: summarize(p.grad) for k, p in model.named_parameters() if p.grad is not None}}
 
 
-def golden_cascade(B, out):
+def golden_cascade(B, out, tag="cascade"):
     mod = load_ref(os.path.join(REF, "causal_cascade/models.py"), "ref_cascade_models")
     _stub(["tqdm"]); sys.modules["tqdm"].tqdm = lambda x, **k: x
     tr = load_ref(os.path.join(REF, "causal_cascade/train.py"), "ref_cascade_train")
@@ -240,7 +242,7 @@ def golden_cascade(B, out):
         O.cascade_loss(o[0], x.to(dt), o[1], m.to(dt), o[2], o[3])[0].backward()
         return {k: v.grad for k, v in Wq.items()}
     noise = noise_floor(ograds(torch.float32), ograds(torch.float64))
-    out["cascade"] = {
+    out[tag] = {
         "grad_noise_fp32_vs_fp64": noise,
         "config": {"B": B, "wseed": 7, "xseed": 11}, "state_dict_shapes": shp,
         "loss": loss.item(), "recon": rl.item(), "m_loss": ml.item(),
@@ -248,7 +250,7 @@ def golden_cascade(B, out):
         "grads": {k: summarize(p.grad) for k, p in model.named_parameters() if p.grad is not None}}
 
 
-def golden_mnist(variant, M, B, out):
+def golden_mnist(variant, M, B, out, tag=None):
     d = os.path.join(REF, "mnist_test", "01_baseline_causal_vae" if variant == "01" else "06_model_experiment")
     sys.modules.pop("config", None)
     sys.path.insert(0, d)
@@ -295,7 +297,7 @@ def golden_mnist(variant, M, B, out):
         z = O.reparameterize(mu, logvar, eps)
     loss_d = F.cross_entropy(disc(z.detach()), t.argmax(1))
     loss_d.backward()
-    out[f"mnist{variant}_M{M}"] = {
+    out[tag or f"mnist{variant}_M{M}"] = {
         "config": {"B": B, "M": M, "wseed": 13, "dseed": 17, "xseed": 19, "variant": variant},
         "state_dict_shapes": shp, "disc_shapes": dshp,
         "loss": loss.item(), "recon": loss_recon.item(), "kld": loss_kld.item(),
@@ -316,6 +318,11 @@ def main():
     golden_mnist("01", 4, 8, out)
     golden_mnist("01", 12, 8, out)
     golden_mnist("06", 12, 8, out)
+    # the BASELINE.json batch sizes (configs[3], [2], [1], [0]): B = 64 / 128 / 256 / 64
+    golden_vessel(256, 256, 64, "vessel_256x256_b64", out)
+    golden_lt(128, 128, 128, out, tag="latent_translator_b128")
+    golden_cascade(256, out, tag="cascade_b256")
+    golden_mnist("01", 4, 64, out, tag="mnist01_M4_b64")
     for k, v in out.items():
         with open(os.path.join(os.path.dirname(__file__), k + ".json"), "w") as f:
             json.dump(v, f, indent=1)

@@ -25,13 +25,17 @@ def check_summary(t, s, rtol=RTOL, what=""):
     err = (t[idx] - torch.tensor(s["val"], dtype=torch.float64)).abs().max().item()
     assert err <= rtol * scale + 1e-7, f"{what}: sampled err {err} vs scale {scale}"
     assert abs(t.norm().item() - s["l2"]) <= rtol * max(s["l2"], 1e-6) * 4 + 1e-7, f"{what}: l2"
+    if "s101_sum" in s:        # strided ~1 % sample: position-sensitive checksum (sum bounded by sqrt(n) * rtol * scale)
+        q = t[::101]
+        assert abs(q.sum().item() - s["s101_sum"]) <= rtol * scale * max(q.numel(), 1) ** 0.5 * 4 + 1e-7, f"{what}: s101 sum"
+        assert abs(q.norm().item() - s["s101_l2"]) <= rtol * max(s["s101_l2"], scale) * 4 + 1e-7, f"{what}: s101 l2"
 
 
 def close(a, b, rtol=RTOL):
     assert abs(float(torch.as_tensor(a).detach()) - b) <= rtol * max(abs(b), 1e-6), (float(a), b)
 
 
-@pytest.mark.parametrize("tag", ["vessel_64x64_b4", "vessel_128x96_b8", "vessel_256x256_b8"])
+@pytest.mark.parametrize("tag", ["vessel_64x64_b4", "vessel_128x96_b8", "vessel_256x256_b8", "vessel_256x256_b64"])
 def test_vessel_oracle_matches_reference(tag):
     g = load(tag)
     c = g["config"]
@@ -70,8 +74,9 @@ def test_vessel_oracle_matches_reference(tag):
             check_summary(P[k], s, rtol=1e-4, what="after." + k)
 
 
-def test_latent_translator_oracle():
-    g = load("latent_translator")
+@pytest.mark.parametrize("tag", ["latent_translator", "latent_translator_b128"])
+def test_latent_translator_oracle(tag):
+    g = load(tag)
     c = g["config"]
     assert {k: tuple(v) for k, v in g["state_dict_shapes"].items()} == O.lt_shapes(c["H"], c["W"])
     P = O.fill_state_dict(O.lt_shapes(c["H"], c["W"]), seed=c["wseed"])
@@ -90,8 +95,9 @@ def test_latent_translator_oracle():
         check_summary(W[k].grad, s, rtol=max(1e-4, 4 * g["grad_noise_fp32_vs_fp64"][k]), what="grad." + k)
 
 
-def test_cascade_oracle():
-    g = load("cascade")
+@pytest.mark.parametrize("tag", ["cascade", "cascade_b256"])
+def test_cascade_oracle(tag):
+    g = load(tag)
     c = g["config"]
     P = O.fill_state_dict(O.cascade_shapes(8, 19), seed=c["wseed"])
     gen = torch.Generator().manual_seed(c["xseed"])
@@ -113,7 +119,7 @@ def test_cascade_oracle():
         check_summary(W[k].grad, s, rtol=max(1e-4, 4 * g["grad_noise_fp32_vs_fp64"][k]), what="grad." + k)
 
 
-@pytest.mark.parametrize("tag", ["mnist01_M4", "mnist01_M12", "mnist06_M12"])
+@pytest.mark.parametrize("tag", ["mnist01_M4", "mnist01_M12", "mnist06_M12", "mnist01_M4_b64"])
 def test_mnist_oracle(tag):
     g = load(tag)
     c = g["config"]
