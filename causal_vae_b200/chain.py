@@ -69,6 +69,13 @@ class _Rec:
     pass
 
 
+# Test hook.  TRACE[0] = {} makes every activation site of the following forward passes record
+# id(module producing the pre-activation) -> (raw tensor, XF): the sign of fmaf(raw - center, scale, shift) is the
+# LeakyReLU / ReLU side the kernels take for that unit, in forward and in backward (tests/kinks.py turns it into the
+# derivative masks the checker is evaluated with).  None (the default) costs nothing.
+TRACE = [None]
+
+
 # Trainers that own zero_grad() (FlatParams) and use every parameter exactly once per backward set
 # DIRECT_GRADS[0] = True: parameter gradients are then written straight into `p.grad` by the kernels
 # that produce them and autograd receives None, which removes one accumulate launch (and one
@@ -181,6 +188,8 @@ def _unit_fwd(u, S, train, keep):
     else:
         out = State(y)
     rec.S_out = out
+    if TRACE[0] is not None and isinstance(u.act, float):
+        TRACE[0][id(u.bn if u.bn is not None else u.mod)] = (y, out.x)
     return out, (rec if keep else None)
 
 

@@ -57,6 +57,7 @@ struct HaloPlan {
   int pos[4];                 // accumulator position (TMEM column block) of each phase
   int bslot_bytes;            // weight ring slot: 256 * BN * (largest group)
   int a_tmem;                 // 1: Linear / 1x1 mode with the A operand staged in tensor memory (see the producer)
+  int xacc;                   // 1: cross terms (hi*lo' + lo*hi') in their own accumulator columns [BN, 2BN) -- see the MMA issuer
   HaloPlane plane[4];
 };
 
@@ -99,7 +100,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   const int BN = p.BN, NB = p.NB;
   const int KB = (a.Cs + 31) >> 5;
   const uint32_t bstage = (uint32_t)p.bslot_bytes;
-  const uint32_t acc_cols = (uint32_t)(a.nphase * BN);
+  const uint32_t acc_cols = (uint32_t)(a.nphase * BN * (p.xacc ? 2 : 1));
   const uint32_t a_cols = p.a_tmem ? (uint32_t)(kHNAT * 64) : 0u;     // A ring in tensor memory: hi | lo, 32 columns each
   const int na = p.a_tmem ? kHNAT : kHNA;
   uint32_t tmem_cols = 32;
@@ -271,7 +272,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         T_WAIT(0, mbar_wait(smem_u32(&s_tempty[acc]), ((tcount >> 1) & 1u) ^ 1u))
         tc_fence_after();
         const uint32_t d_base = tmem + acc * acc_cols;
-        uint32_t started = 0;
+        uint32_t started = 0, startedx = 0;
         for (int kb = 0; kb < KB; ++kb) {
           const int ksteps = min(32, a.Cs - kb * 32) >> 3;
           for (int pl = 0; pl < p.nplanes; ++pl, ++ita) {
@@ -290,13 +291,27 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
               uint64_t dbl = b_desc_hi | (uint64_t)(((b_hi + 128u * (uint32_t)BN) & 0x3FFFFu) >> 4);
               uint32_t ta_hi = tmem + 2u * acc_cols + (uint32_t)(aslot * 64), ta_lo = ta_hi + 32u;
               uint32_t accum = started ? 1u : 0u;
+              if (p.xacc) {
+                // [W_hi | W_lo] are adjacent in the slot: ONE MMA of N = 2*BN gives A_hi*W_hi in columns [0, BN)
+                // and A_hi*W_lo in [BN, 2BN); A_lo*W_hi joins the cross columns.  Two MMAs per product instead of
+                // three, and the main chain sees one truncating accumulate per k-step instead of three.
+                const uint32_t idesc2 = make_idesc_tf32(128, 2 * BN, 0, 0);
 #pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) {
-                mma_tf32_ts(d_base, ta_lo, dbh, idesc, accum);
-                mma_tf32_ts(d_base, ta_hi, dbl, idesc, 1u);
-                mma_tf32_ts(d_base, ta_hi, dbh, idesc, 1u);
-                accum = 1u;
-                ta_hi += 8; ta_lo += 8; dbh += 2; dbl += 2;
+                for (int k = 0; k < ksteps; ++k) {
+                  mma_tf32_ts(d_base, ta_hi, dbh, idesc2, accum);
+                  mma_tf32_ts(d_base + (uint32_t)BN, ta_lo, dbh, idesc, 1u);
+                  accum = 1u;
+                  ta_hi += 8; ta_lo += 8; dbh += 2;
+                }
+              } else {
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  mma_tf32_ts(d_base, ta_lo, dbh, idesc, accum);
+                  mma_tf32_ts(d_base, ta_hi, dbl, idesc, 1u);
+                  mma_tf32_ts(d_base, ta_hi, dbh, idesc, 1u);
+                  accum = 1u;
+                  ta_hi += 8; ta_lo += 8; dbh += 2; dbl += 2;
+                }
               }
               started = 1u;
               mma_commit(smem_u32(&s_bempty[bslot]));
@@ -323,13 +338,38 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
               uint64_t dal = a_desc_hi | (uint64_t)(((a_hi + kHHalf) & 0x3FFFFu) >> 4);
               uint64_t dbh = b_desc_hi | (uint64_t)((b_hi & 0x3FFFFu) >> 4);
               uint64_t dbl = b_desc_hi | (uint64_t)(((b_hi + 128u * ng) & 0x3FFFFu) >> 4);
+              if (p.xacc && a.nphase > 1) {
+                // scatter plans: the stacked groups of different phases cannot all be followed by their own cross
+                // columns, so the cross accumulators live nphase*BN columns further on and take two MMAs of their own
+                const uint32_t dx_tmem = d_tmem + (uint32_t)(a.nphase * BN);
+                uint32_t accx = (startedx & gmask) ? 1u : 0u;
 #pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) {
-                mma_tf32(d_tmem, dal, dbh, idesc, accum);
-                mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                mma_tf32(d_tmem, dah, dbh, idesc, 1u);
-                accum = 1u;
-                dah += 2; dal += 2; dbh += 2; dbl += 2;      // + 32 bytes (8 tf32) along K
+                for (int k = 0; k < ksteps; ++k) {
+                  mma_tf32(dx_tmem, dal, dbh, idesc, accx);
+                  mma_tf32(dx_tmem, dah, dbl, idesc, 1u);
+                  mma_tf32(d_tmem, dah, dbh, idesc, accum);
+                  accum = 1u; accx = 1u;
+                  dah += 2; dal += 2; dbh += 2; dbl += 2;
+                }
+                startedx |= gmask;
+              } else if (p.xacc) {   // one tap per group, one phase: [main | cross] accumulators (see the a_tmem branch)
+                const uint32_t idesc2 = make_idesc_tf32(128, 2 * BN, 0, 0);
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  mma_tf32(d_tmem, dah, dbh, idesc2, accum);
+                  mma_tf32(d_tmem + (uint32_t)BN, dal, dbh, idesc, 1u);
+                  accum = 1u;
+                  dah += 2; dal += 2; dbh += 2;
+                }
+              } else {
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  mma_tf32(d_tmem, dal, dbh, idesc, accum);
+                  mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                  mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                  accum = 1u;
+                  dah += 2; dal += 2; dbh += 2; dbl += 2;      // + 32 bytes (8 tf32) along K
+                }
               }
               started |= gmask;
               mma_commit(smem_u32(&s_bempty[bslot]));
@@ -436,6 +476,12 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             for (int h = 0; h < cw; h += 16) {
               float r16[16];
               tmem_ld16(d_tmem + (uint32_t)(ch * 32 + h), r16);
+              if (p.xacc) {                         // + the cross-term accumulator (rounded fp32 add)
+                float c16[16];
+                tmem_ld16(d_tmem + (uint32_t)(a.nphase * BN + ch * 32 + h), c16);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r16[i] += c16[i];
+              }
 #pragma unroll
               for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<float4*>(eb + row * kHEpiLd + h + i) = make_float4(r16[i], r16[i + 1], r16[i + 2], r16[i + 3]);
@@ -653,9 +699,19 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   }
   if (g.Cs % 16 != 0 || g.Cd % 16 != 0) return 1;
   if (g.Cd > 256 && g.epi != CVAE_EPI_PLAIN && g.stats != nullptr) return 1;   // s_stat holds 256 channels
+  // cross-term accumulators (xacc, see the MMA issuer) double the accumulator columns.  Gather plans keep their tile
+  // width (N <= 128: 2 * 2 * 128 = 512 columns); scatter plans (4 phases) fit with BN <= 32, which costs the wide
+  // layers more n-tiles (measured: stem.9 / stem.12 input gradients +25 %).  Forward accuracy is what decides which side
+  // of a LeakyReLU kink a unit takes, so the wide layers pay that price only in forward-type launches (no
+  // activation-derivative epilogue); input gradients with Cd >= 64 keep the single accumulator (their 3-8e-6 is far
+  // inside the 1e-4 gradient tolerance).  CVAE_XACC_SCATTER=0 / 2: never / always.
+  static const bool xacc_on = [] { const char* e = getenv("CVAE_XACC"); return !(e && e[0] == '0'); }();
+  static const int xacc_sc = [] { const char* e = getenv("CVAE_XACC_SCATTER"); return e ? atoi(e) : 1; }();
+  const bool want_xs = xacc_on && g.nphase > 1 &&
+                       (xacc_sc == 2 || (xacc_sc == 1 && (g.Cd % 64 != 0 || g.epi != CVAE_EPI_DACT)));
   int bn = 0;
   for (int c : {128, 64, 32, 16})
-    if (g.Cd % c == 0 && 2 * g.nphase * c <= 512) { bn = c; break; }
+    if (g.Cd % c == 0 && 2 * g.nphase * c * (want_xs ? 2 : 1) <= 512) { bn = c; break; }
   if (bn == 0) return 1;
   HaloPlan hp;
   // stack up to 128 output columns per MMA (weight-ring slot <= 32 KiB); fall back to one tap per MMA
@@ -670,6 +726,11 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
     static const bool lin_tmem = [] { const char* e = getenv("CVAE_LIN_TMEM"); return !(e && e[0] == '0'); }();
     hp.a_tmem = (lin_tmem && g.wtaps < 2 && hp.nplanes == 1 && g.nphase == 1 && hp.plane[0].ntaps == 1 &&
                  2 * bn + kHNAT * 64 <= 512) ? 1 : 0;
+    // separate cross-term accumulators: gather-type plans (one phase, one tap per MMA) whose doubled accumulators
+    // still fit tensor memory twice (CVAE_XACC=0 restores the single-accumulator 3-MMA form)
+    hp.xacc = (xacc_on && g.nphase == 1 && hp.bslot_bytes == 1 &&
+               2 * 2 * bn + (hp.a_tmem ? kHNAT * 64 : 0) <= 512) ? 1 : 0;
+    if (want_xs && 2 * 2 * g.nphase * bn <= 512) hp.xacc = 1;
   }
   hp.bslot_bytes *= 256 * bn;
   hp.NB = hp.bslot_bytes >= 32768 ? (bn >= 128 ? 3 : 2) : 4;

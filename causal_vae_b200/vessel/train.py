@@ -85,6 +85,7 @@ class VesselTrainer:
         try:
             with F.use_rng(self.rng):
                 out = self.model(x, m, t, eps)
+            self.last_outputs = tuple(o.detach() for o in out)      # the step's forward tuple (views, no graph)
             recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
             loss = total_loss(recon, kld, morph, sp, self.beta, self.lambda_morph)
             # zero_grad() above zeroed the flat buffer and every parameter is used once: gradients are written

@@ -9,6 +9,7 @@ import os
 import pytest
 import torch
 
+import kinks as K
 from oracle import cvae_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -41,34 +42,11 @@ def req(P):
     return P
 
 
-def pert_response(oracle_grads, P, seeds=(1, 2, 3, 4, 5), eps=3e-6):
-    """Relative response of the fp32 oracle's gradients to `eps`-relative weight perturbations.
-    End-to-end gradients are discontinuous at fp32 rounding scale: ONE pre-activation that sits within
-    rounding distance of a ReLU / LeakyReLU kink (observed: cascade enc_fc.0 unit (1,19) = -6.2e-7 in
-    fp64, +1.5e-8 on the GPU) flips a derivative and moves whole gradient tensors by 1e-2..1e-1.  The
-    reference's own arithmetic shows the same response -- its fp32 gradients move by exactly that amount
-    under 3e-6-relative weight perturbations, i.e. perturbations BELOW the 1e-5 forward tolerance (and the
-    size of the 3xTF32 forward error, 2-6e-6) -- which therefore floors the tolerance per tensor."""
-    base = oracle_grads({k: v.clone() for k, v in P.items()})
-    resp = {k: 0.0 for k in base}
-    for seed in seeds:
-        gen = torch.Generator().manual_seed(seed)
-        Pp = {k: v.clone() for k, v in P.items()}
-        for k, v in Pp.items():
-            if v.is_floating_point() and "running" not in k:
-                v.mul_(1 + eps * torch.randn(v.shape, generator=gen))
-        gp = oracle_grads(Pp)
-        for k in resp:
-            if base[k] is not None:
-                resp[k] = max(resp[k], rel(gp[k], base[k]))
-    return resp
-
-
-def check_grads(model, ref64, ref32=None, floor=1e-4, skip=(), pert=None):
+def check_grads(model, ref64, ref32=None, floor=1e-4, skip=()):
     """1e-4 of each tensor's max |g| against the fp64 oracle, widened only where the reference's own
-    fp32 arithmetic does not reproduce to that level (4 x fp32-vs-fp64 discrepancy, 4 x kink response)."""
+    fp32 arithmetic does not reproduce to that level (4 x its fp32-vs-fp64 discrepancy).  The deep families
+    (cascade, latent_translator) call it with an oracle evaluated on the native run's kink sides, see tests/kinks.py."""
     worst = []
-    strict = []
     for k, p in model.named_parameters():
         if k in skip:
             continue
@@ -78,14 +56,11 @@ def check_grads(model, ref64, ref32=None, floor=1e-4, skip=(), pert=None):
             continue
         assert p.grad is not None, f"no grad for {k}"
         noise = rel(ref32[k].grad, g64) if ref32 is not None else 0.0
-        tol = max(floor, 4 * noise, 4 * (pert[k] if pert else 0.0))
+        tol = max(floor, 4 * noise)
         e = rel(p.grad, g64)
         worst.append((e / tol, k, e, noise))
-        strict.append((e / max(floor, 4 * noise), k, e, noise))
     worst.sort(reverse=True)
-    strict.sort(reverse=True)
-    print("DIAG strict (no pert) violations", sum(1 for r in strict if r[0] > 1), "of", len(strict),
-          [(round(r, 2), k, f"{e:.1e}", f"{n:.1e}") for r, k, e, n in strict[:8]])
+    print("gradient error / tolerance:", [(round(r, 2), k, f"{e:.1e}", f"{n:.1e}") for r, k, e, n in worst[:6]])
     assert worst and worst[0][0] <= 1.0, [(round(r, 2), k, f"{e:.1e}", f"{n:.1e}") for r, k, e, n in worst[:8]]
 
 
@@ -250,7 +225,8 @@ def test_cascade_forward_loss_grads(tag):
     o32 = O.cascade_forward(P32, x, m, t, eps, train=True)
     O.cascade_loss(o32[0], x, o32[1], m, o32[2], o32[3])[0].backward()
 
-    outs = model(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    with K.NativeTrace(model) as tr:
+        outs = model(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
     assert len(outs) == 4 and outs[0].shape == (B, 1, 64, 64)
     for n, a, b in zip(["recon_x", "m_hat", "mu", "logvar"], outs, outs64):
         assert rel(a, b) <= 2e-5, (n, rel(a, b))
@@ -260,12 +236,19 @@ def test_cascade_forward_loss_grads(tag):
         closef(a, b)
         closef(a, g[n], 2e-5)
 
-    def og(Pp):
+    # gradients: derivative sides may differ from the fp64 oracle's only inside the forward-tolerance band around a
+    # ReLU kink; with the same sides the gradients agree to max(1e-4, 4 x oracle fp32-vs-fp64) -- tests/kinks.py
+    pre64 = K.oracle_sides(lambda: O.cascade_forward(d64(P), x.double(), m.double(), t, eps.double(), train=True))
+    print("cascade kink sides (differing, units, worst |z|/max):", K.check_sides(tr.masks, pre64, band=2e-5))
+
+    def og(Pp, dt):
         Pp = req(Pp)
-        o = O.cascade_forward(Pp, x, m, t, eps, train=True)
-        O.cascade_loss(o[0], x, o[1], m, o[2], o[3])[0].backward()
-        return {k: (v.grad if v.is_floating_point() else None) for k, v in Pp.items()}
-    check_grads(model, P64, P32, pert=pert_response(og, P))
+        o = O.cascade_forward(Pp, x.to(dt), m.to(dt), t, eps.to(dt), train=True)
+        O.cascade_loss(o[0], x.to(dt), o[1], m.to(dt), o[2], o[3])[0].backward()
+        return Pp
+    with K.with_masks(tr.masks):
+        P64m, P32m = og(d64(P), torch.float64), og({k: w.clone() for k, w in P.items()}, torch.float32)
+    check_grads(model, P64m, P32m)
     # BatchNorm1d running statistics of mechanism_net.1 after one training forward
     sd = model.state_dict()
     for k in ("mechanism_net.1.running_mean", "mechanism_net.1.running_var"):
@@ -313,7 +296,8 @@ def test_latent_translator_forward_loss_grads(tag):
     r32, _, m32, l32 = O.lt_forward(P32, x, eps, train=True)
     O.lt_loss(r32, x, m32, l32)[0].backward()
 
-    recons, inp, mu, lv = model(x.cuda(), eps.cuda())
+    with K.NativeTrace(model, prefix="b.") as tr:
+        recons, inp, mu, lv = model(x.cuda(), eps.cuda())
     assert recons.shape == (B, 1, H, W) and mu.shape == (B, 512)
     assert rel(recons, rec64) <= 2e-5 and rel(mu, mu64) <= 2e-5 and rel(lv, lv64) <= 2e-5
     got = engine.loss_function(recons, x.cuda(), mu, lv, beta=1.0)
@@ -322,12 +306,17 @@ def test_latent_translator_forward_loss_grads(tag):
         closef(a, b)
         closef(a, g[n], 2e-5)
 
-    def og(Pp):
+    pre64 = K.oracle_sides(lambda: O.lt_forward(d64(P), x.double(), eps.double(), train=True))
+    print("latent_translator kink sides (differing, units, worst |z|/max):", K.check_sides(tr.masks, pre64, band=2e-5))
+
+    def og(Pp, dt):
         Pp = req(Pp)
-        r, _, mm, ll = O.lt_forward(Pp, x, eps, train=True)
-        O.lt_loss(r, x, mm, ll)[0].backward()
-        return {k: (v.grad if v.is_floating_point() else None) for k, v in Pp.items()}
-    check_grads(model, P64, P32, pert=pert_response(og, P))
+        r, _, mm, ll = O.lt_forward(Pp, x.to(dt), eps.to(dt), train=True)
+        O.lt_loss(r, x.to(dt), mm, ll)[0].backward()
+        return Pp
+    with K.with_masks(tr.masks):
+        P64m, P32m = og(d64(P), torch.float64), og({k: w.clone() for k, w in P.items()}, torch.float32)
+    check_grads(model, P64m, P32m)
 
     # encode-only path used by extract_vit_latents (engine.py:46-50), eval mode
     model.eval()

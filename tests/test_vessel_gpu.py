@@ -6,6 +6,7 @@ import os
 import pytest
 import torch
 
+import kinks as K
 from oracle import cvae_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -139,12 +140,15 @@ def test_train_step_matches_oracle(cfg):
     x, m, t, eps = O.vessel_inputs(B, H, W, seed=0)
     trainer = train.VesselTrainer(model, lr=1e-4)
     trainer.model.train()
-    losses = trainer._fwd_bwd(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    with K.NativeTrace(model) as tr:
+        losses = trainer._fwd_bwd(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    tr.add_sign("recon_x", trainer.last_outputs[0])
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
     trainer.opt.step()
     torch.cuda.synchronize()
 
     P64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    P64_0 = {k: v.clone() for k, v in P64.items()}
     ref64, g64, tot64 = O.vessel_train_step(P64, {}, 1, x.double(), m.double(), t.double(), eps.double())
     P32 = {k: v.clone() for k, v in sd.items()}
     ref32, g32, tot32 = O.vessel_train_step(P32, {}, 1, x, m, t, eps)
@@ -157,46 +161,30 @@ def test_train_step_matches_oracle(cfg):
         gold = json.load(f)
     assert abs(float(losses[0]) - gold["train"]["loss"]) <= 2e-5 * abs(gold["train"]["loss"])
 
-    # gradients: 1e-4 of each tensor's max |g| -- widened where the reference's own arithmetic is
-    # not reproducible to that level.  End-to-end gradients of this network are discontinuous at fp32
-    # rounding scale: a LeakyReLU(0.01) / |recon| / clamp kink flipping for ONE element changes
-    # whole-network gradients by 1e-2..1e-1 (measured: the reference's gradients move that much under a
-    # 3e-7 relative weight perturbation).  The floor is therefore max(4 x fp32-vs-fp64 discrepancy of
-    # the oracle, 4 x its response to 3e-7 weight perturbations); tight (1e-4) gradient parity is
-    # established per layer chain in test_ops_gpu.py and per segment in test_vessel_segments_gpu.py.
-    pert = {k: 0.0 for k in g64}
-    pert_tot = 0.0
-    # perturbation size 3e-6: BELOW the 1e-5 forward tolerance and the size of the 3xTF32 forward
-    # error (2-6e-6) -- the scale at which kink flips happen on the native path
-    for seed in (1, 2, 3, 4, 5):
-        Pp = {k: v.clone() for k, v in sd.items()}
-        gen = torch.Generator().manual_seed(seed)
-        for k, v in Pp.items():
-            if v.is_floating_point() and "running" not in k:
-                v.mul_(1 + 3e-6 * torch.randn(v.shape, generator=gen))
-        _, gp, totp = O.vessel_train_step(Pp, {}, 1, x, m, t, eps)
-        pert_tot = max(pert_tot, abs(float(totp) - float(tot32)) / float(tot32))
-        for k in pert:
-            pert[k] = max(pert[k], rel(gp[k], g32[k]))
-    worst = []
-    strict = []
-    for k, g in g64.items():
-        noise = rel(g32[k], g)
-        tol = max(1e-4, 4 * noise, 4 * pert[k])
-        e = rel(grads[k], g)
-        worst.append((e / tol, k, e, noise))
-        if noise < 1.0:
-            strict.append((e / max(1e-4, 4 * noise), k, e, noise))
-    worst.sort(reverse=True)
-    strict.sort(reverse=True)
-    print("DIAG strict (no pert) cfg", cfg, "violations", sum(1 for r in strict if r[0] > 1), "of", len(strict),
-          [(round(r, 2), k, f"{e:.1e}", f"{n:.1e}") for r, k, e, n in strict[:10]])
-    print("worst grad err/tol:", [(round(r, 2), k, f"{e:.1e}", f"{n:.1e}") for r, k, e, n in worst[:12]])
-    assert worst[0][0] <= 1.0, [(round(r, 2), k, f"{e:.1e}", f"{n:.1e}") for r, k, e, n in worst[:12]]
+    # gradients (north star: 1e-4 of each tensor's max |g|).  Whole-network gradients are discontinuous where a
+    # pre-activation crosses a LeakyReLU / |recon| kink, so the check is the three tight statements of tests/kinks.py:
+    # forward values at the forward tolerance (above and in test_eval_forward_*), derivative sides differing from the
+    # fp64 oracle's only INSIDE the forward-tolerance band around a kink, and gradients at
+    # max(1e-4, 4 x the oracle's own fp32-vs-fp64 discrepancy) when evaluated with the same sides.
+    pre64 = K.oracle_sides(lambda: O.vessel_loss(*(lambda o: (o[0], x.double(), o[1], m.double(), o[2], o[3], o[4], o[5]))(
+        O.vessel_forward({k: v.clone() for k, v in P64_0.items()}, x.double(), m.double(), t.double(), eps.double(), True))))
+    flips, units, worst_z = K.check_sides(tr.masks, pre64, band=2e-5)
+    print(f"cfg {cfg}: {flips} of {units} units took the other side of a kink (worst |z|/max|z| {worst_z:.1e})")
+    with K.with_masks(tr.masks):
+        P64m = {k: v.clone() for k, v in P64_0.items()}
+        _, g64m, tot64m = O.vessel_train_step(P64m, {}, 1, x.double(), m.double(), t.double(), eps.double())
+        P32m = {k: v.clone() for k, v in sd.items()}
+        _, g32m, tot32m = O.vessel_train_step(P32m, {}, 1, x, m, t, eps)
+    K.check_grads(grads, g64m, g32m, what=str(cfg))
+    # unconditioned comparison, for the record: against the fp64 oracle with ITS OWN sides (differs by the flips)
+    unc = sorted(((rel(grads[k], g) / max(1e-4, 4 * rel(g32[k], g)), k) for k, g in g64.items() if rel(g32[k], g) < 1),
+                 reverse=True)
+    print(f"cfg {cfg}: unconditioned err / max(1e-4, 4 x reference fp32 noise): worst {unc[0][0]:.2f} ({unc[0][1]}), "
+          f"{sum(1 for r, _ in unc if r > 1)} of {len(unc)} tensors above 1")
     for k in ("backbone.fc_mu.weight", "backbone.fc_var.bias"):
         assert float(grads[k].abs().max()) == 0.0                       # unused heads get no gradient
     tot = trainer.opt.grad_norm().item()
-    assert abs(tot - float(tot64)) <= max(1e-4, 4 * abs(float(tot32) - float(tot64)) / float(tot64), 4 * pert_tot) * float(tot64)
+    assert abs(tot - float(tot64m)) <= max(1e-4, 4 * abs(float(tot32m) - float(tot64m)) / float(tot64m)) * float(tot64m)
     # BN running statistics after the step (momentum 0.1, unbiased variance)
     for k, v in model.state_dict().items():
         if k.endswith(("running_mean", "running_var")):
@@ -295,12 +283,15 @@ def test_vessel_cnn_variant_matches_oracle_and_golden():
     assert img.shape == (c["B"], 1, c["H"], c["W"]) and rel(img, want_img) <= 1e-5
 
     model.train()
-    outs = model(xc, mc, tc, ec)
+    with K.NativeTrace(model) as tr:
+        outs = model(xc, mc, tc, ec)
+    tr.add_sign("recon_x", outs[0])
     parts = train.loss_function(outs[0], xc, outs[1], mc, outs[2], outs[3], outs[4], outs[5])
     loss = train.total_loss(*parts, beta=c["beta"])
     loss.backward()
     torch.cuda.synchronize()
     P64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    P64_0 = {k: v.clone() for k, v in P64.items()}
     o64, l64, g64 = O.vessel_cnn_loss_and_grads(P64, x.double(), m.double(), t.double(), eps.double(), c["beta"])
     # Training-mode BatchNorm over a batch of 4 (BatchNorm1d in enc_fc / dec_fc sees 4 values per feature) amplifies
     # rounding: the oracle's own fp32 run differs from its fp64 run by ~1e-4 on recon_x.  Tolerance on outputs and
@@ -323,22 +314,19 @@ def test_vessel_cnn_variant_matches_oracle_and_golden():
             bad["loss." + n] = (float(v), ref, tol)
     if abs(float(loss) - gold["train"]["loss"]) > 2e-5 * abs(gold["train"]["loss"]):
         bad["loss.vs_live_reference_golden"] = (float(loss), gold["train"]["loss"])
-    # gradients: 1e-4 of each tensor's max |g|, widened to (i) 4x the REFERENCE's own fp32-vs-fp64 discrepancy of that
-    # tensor (recorded in the golden: median 1.6e-3, max 2e-2) and (ii) 4x the response of the oracle's fp32 gradients
-    # to a 3e-6 relative weight perturbation — the size of the 3xTF32 forward error.  Whole-network gradients are
-    # discontinuous at that scale: a pre-activation within rounding distance of a LeakyReLU / ReLU kink flips one
-    # derivative, and with 10^7..10^8 activations per layer a few hundred do (scripts/diag_cnn_layers.py: every
-    # conv layer alone is at 1e-6..3e-5, the conv + BatchNorm + activation chains with >= 10^5 pixels per channel
-    # show 1e-3..1e-2 on weight gradients while the same chains on small maps are at 1e-6).  Biases in front of a
-    # BatchNorm have an exactly zero gradient (rounding noise in fp32): bounded against the layer's weight gradient.
-    pert = {k: 0.0 for k in g32}
-    for seed in (1, 2):
-        gen = torch.Generator().manual_seed(seed)
-        Pp = {k: (v * (1 + 3e-6 * torch.randn(v.shape, generator=gen)) if v.is_floating_point() and "running" not in k
-                  else v.clone()) for k, v in sd.items()}
-        _, _, gp = O.vessel_cnn_loss_and_grads(Pp, x, m, t, eps, c["beta"])
-        for k in pert:
-            pert[k] = max(pert[k], rel(gp[k], g32[k]))
+    # gradients: the three statements of tests/kinks.py -- derivative sides differing from the fp64 oracle's only inside
+    # the forward-tolerance band around a LeakyReLU / ReLU kink (with 10^8 activations a few hundred sit that close),
+    # and, evaluated with the SAME sides, gradients at max(1e-4, 4 x the oracle's own fp32-vs-fp64 discrepancy) of each
+    # tensor's max |g|.  Biases in front of a BatchNorm have an exactly zero gradient (rounding noise in fp32):
+    # bounded against the layer's weight gradient.
+    pre64 = K.oracle_sides(lambda: O.vessel_loss(*(lambda o: (o[0], x.double(), o[1], m.double(), o[2], o[3], o[4], o[5]))(
+        O.vessel_cnn_forward({k: v.clone() for k, v in P64_0.items()}, x.double(), m.double(), t.double(), eps.double(), True))))
+    # band: the K = 8192 layers' forward tolerance (see the outputs above)
+    print("CNN variant kink sides (differing, units, worst |z|/max):", K.check_sides(tr.masks, pre64, band=1e-4))
+    with K.with_masks(tr.masks):
+        _, _, g64m = O.vessel_cnn_loss_and_grads({k: v.clone() for k, v in P64_0.items()}, x.double(), m.double(), t.double(),
+                                                 eps.double(), c["beta"])
+        _, _, g32m = O.vessel_cnn_loss_and_grads({k: v.clone() for k, v in sd.items()}, x, m, t, eps, c["beta"])
     noise = gold["train"]["grad_noise_fp32_vs_fp64"]
     worst = {}
     for k, p in model.named_parameters():
@@ -348,8 +336,12 @@ def test_vessel_cnn_variant_matches_oracle_and_golden():
             if p.grad.abs().max().item() > 1e-3 * g64[wk].abs().max().item():
                 bad["grad0." + k] = p.grad.abs().max().item()
             continue
-        worst[k] = rel(p.grad, g64[k]) / max(1e-4, 4 * noise[k], 4 * pert[k])
-    bad.update({"grad." + k: (v, noise[k], pert[k]) for k, v in worst.items() if v > 1.0})
+        # floor 5e-4 here (not the 1e-4 of the BASELINE configs): this variant's BatchNorm1d layers normalise over the
+        # 4 samples of the batch behind K = 30751 / 8192 contractions, which amplifies last-bit differences of the
+        # forward values into 2-4e-4 of the adapter gradients even with identical kink sides (observed: enc_fc.3.weight
+        # 3.9e-4); the model is not a BASELINE config, the ViT variant is checked at 1e-4 in test_train_step_matches_oracle
+        worst[k] = rel(p.grad, g64m[k]) / max(5e-4, 4 * rel(g32m[k], g64m[k]))
+    bad.update({"grad." + k: v for k, v in worst.items() if v > 1.0})
     # running statistics updated as BatchNorm does (momentum 0.1, unbiased variance)
     after = model.state_dict()
     for k in after:
@@ -376,14 +368,19 @@ def test_vessel_cnn_variant_train_step():
     x, m, t, eps = O.vessel_inputs(c["B"], c["H"], c["W"], c["m_dim"], c["t_dim"], c["z_dim"], seed=0)
     lr = 1e-4
     trainer = train.VesselTrainer(model, lr=lr, max_norm=5.0, beta=c["beta"])
-    losses = trainer.step(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    with K.NativeTrace(model) as tr:
+        losses = trainer.step(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    tr.add_sign("recon_x", trainer.last_outputs[0])
     gnorm = float(trainer.flat.grad.double().norm())
     torch.cuda.synchronize()
     P64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
-    _, l64, g64 = O.vessel_cnn_loss_and_grads(P64, x.double(), m.double(), t.double(), eps.double(), c["beta"])
+    _, l64, _ = O.vessel_cnn_loss_and_grads({k: v.clone() for k, v in P64.items()}, x.double(), m.double(), t.double(),
+                                            eps.double(), c["beta"])
     assert abs(float(losses[0]) - float(l64["loss"])) <= 1e-5 * abs(float(l64["loss"]))
+    with K.with_masks(tr.masks):        # the fp64 oracle on the kink sides the native step took (tests/kinks.py)
+        _, _, g64 = O.vessel_cnn_loss_and_grads(P64, x.double(), m.double(), t.double(), eps.double(), c["beta"])
     clipped, total = O.clip_grad_norm(g64, 5.0)
-    assert abs(gnorm - float(total)) <= 2e-2 * float(total), (gnorm, float(total))     # whole-network gradient noise floor
+    assert abs(gnorm - float(total)) <= 1e-3 * float(total), (gnorm, float(total))
     # first Adam step: every weight moves by lr * gc / (|gc| + 1e-8) with gc the CLIPPED gradient (the global norm is
     # ~1e6, so gc ~ 1e-7..1e-5 and the 1e-8 matters): just under lr, against the sign of its gradient
     after = model.state_dict()
@@ -394,9 +391,8 @@ def test_vessel_cnn_variant_train_step():
         strong = g.abs() > 1e-2 * g.abs().max()                 # elements whose gradient is far above the noise
         agree = (torch.sign(d[strong]) == -torch.sign(g[strong])).double().mean().item()
         assert agree >= 0.99, (k, agree)
-        # magnitude: sensitivity to the ~1-2 % whole-network gradient noise is eps / (|gc| + eps) of it -> 5 % bound
         want = -lr * clipped[k] / (clipped[k].abs() + 1e-8)
-        assert torch.allclose(d[strong], want[strong], rtol=5e-2, atol=1e-9), (k, float((d - want)[strong].abs().max()))
+        assert torch.allclose(d[strong], want[strong], rtol=1e-2, atol=1e-9), (k, float((d - want)[strong].abs().max()))
     l2 = trainer.step(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
     assert float(l2[0]) < float(losses[0])
 
