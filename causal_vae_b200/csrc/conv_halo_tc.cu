@@ -428,7 +428,6 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
     const bool want_stats = a.epi != CVAE_EPI_PLAIN && a.stats != nullptr;
     const bool reg_stats = want_stats && nchunks == 1 && p.tiles_n == 1;
     const int nbuf = BN <= 64 ? 2 : 1;
-    int* s_out2 = reinterpret_cast<int*>(ebuf + nbuf * 128 * kHEpiLd);     // [nbuf][128] row -> output pixel
     double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
     auto reduce_stats = [&](int chan0) {            // all 128 epilogue threads; sums -> s_stat[chan0 + ...]
 #pragma unroll
@@ -452,6 +451,44 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 4; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
     };
+    // The activation-derivative epilogue (CVAE_EPI_DACT) re-reads the producer's raw output for every element it
+    // writes.  Those addresses depend only on the tile index, so the rows of the NEXT chunk are requested one chunk
+    // ahead (8 x 128-bit registers per thread): their DRAM latency then overlaps the TMEM drain, the barrier and the
+    // stores of the current chunk -- and, across tiles, the wait for the next accumulator.  Before, each batch of four
+    // rows was a dependent round trip (profiles/r1_ncu_halo_stem3_raw.txt: the 4 epilogue warps were the limiter of
+    // the stride-2 input gradients; role timers: 327 of 345 kclk busy).
+    const bool dact = a.epi == CVAE_EPI_DACT;
+    // A thread's rows of a chunk are r0, r0 + rstep, ...: same column of the patch, (rstep / 8) patch rows apart, so
+    // their output pixels are obase + u * ostep for u < nval (rows past the image bottom / an invalid column: nval = 0)
+    const int ostep = (rstep >> 3) * a.os * a.Wd;
+    struct Rows { int obase, nval, col; };
+    auto rows_of = [&](int t, int phs, int ch) -> Rows {
+      Rows r{0, 0, 0};
+      if (t >= total) return r;
+      const HTile tl = h_decode(p, t);
+      r.col = tl.n0 + ch * 32 + cg * 4;
+      const int qh = tl.h0 + (r0 >> 3), qw = tl.w0 + (r0 & 7);
+      const int oh = qh * a.os + p.ph[phs], ow = qw * a.os + p.pw[phs];
+      if (qw >= p.Wq || ow >= a.Wd) return r;
+      r.obase = (tl.n * a.Hd + oh) * a.Wd + ow;
+      const int dq = rstep >> 3;
+      // rows u with qh + u*dq < Hq and oh + u*dq*os < Hd
+      const int lim_q = p.Hq - qh, lim_o = a.Hd - oh;
+      int n = lim_q > 0 ? (lim_q + dq - 1) / dq : 0;
+      const int n2 = lim_o > 0 ? (lim_o + dq * a.os - 1) / (dq * a.os) : 0;
+      n = min(min(n, n2), cgs);
+      r.nval = n;
+      return r;
+    };
+    float4 pre[8];                                  // reference rows of the chunk about to be processed
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    Rows cur = rows_of(blockIdx.x, 0, 0);
+    if (dact) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u < cur.nval) pre[u] = __ldg(reinterpret_cast<const float4*>(a.epi_ref + (size_t)(cur.obase + u * ostep) * a.Cd + cur.col));
+    }
     uint32_t tcount = 0, cidx = 0;
     T_DECL
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
@@ -463,16 +500,8 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         const uint32_t d_tmem = tmem + acc * acc_cols + (uint32_t)(p.pos[phs] * BN) + ((uint32_t)(q * 32) << 16);
         for (int ch = 0; ch < nchunks; ++ch, ++cidx) {
           float* eb = ebuf + (cidx % nbuf) * 128 * kHEpiLd;
-          int* so = s_out2 + (cidx % nbuf) * 128;
-          {  // TMEM -> padded shared tile (thread = accumulator row) + this row's output pixel
+          {  // TMEM -> padded shared tile (thread = accumulator row)
             const int row = q * 32 + lane;
-            const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
-            int o = -1;
-            if (qh < p.Hq && qw < p.Wq) {
-              const int oh = qh * a.os + p.ph[phs], ow = qw * a.os + p.pw[phs];
-              if (oh < a.Hd && ow < a.Wd) o = (tl.n * a.Hd + oh) * a.Wd + ow;
-            }
-            so[row] = o;
             for (int h = 0; h < cw; h += 16) {
               float r16[16];
               tmem_ld16(d_tmem + (uint32_t)(ch * 32 + h), r16);
@@ -492,8 +521,16 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));
           }
+          // rows of the NEXT chunk: as soon as a reference row of this chunk has been consumed, the same register
+          // is re-used for the request of the next chunk's row (in flight for one whole chunk period)
+          Rows nxt;
+          {
+            int nt = t, nphs = phs, nch = ch + 1;
+            if (nch == nchunks) { nch = 0; if (++nphs == a.nphase) { nphs = 0; nt = t + gridDim.x; } }
+            nxt = rows_of(nt, nphs, nch);
+          }
           hbar_sync(1, 128);
-          const int col = tl.n0 + ch * 32 + cg * 4;
+          const int col = cur.col;
           float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), esc = make_float4(1.f, 1.f, 1.f, 1.f), esh = bias, ece = bias;
           if (a.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(a.bias + col));
           if (a.e_affine) {
@@ -502,41 +539,44 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             if (a.e_center != nullptr) ece = __ldg(reinterpret_cast<const float4*>(a.e_center + col));
           }
           float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};   // fp32 partial sums of this chunk's <= 8 rows
-          for (int p0 = 0; p0 < cgs; p0 += 4) {     // 4 rows per batch: their global loads overlap
-            int o[4];
-            float4 r4[4], d4[4];
+#pragma unroll
+          for (int p0 = 0; p0 < 8; p0 += 4) {       // 4 rows per batch: the skip-gradient loads of a batch overlap
+            if (p0 >= cgs) break;
+            float4 d4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              o[u] = so[r0 + (p0 + u) * rstep];
-              r4[u] = make_float4(0.f, 0.f, 0.f, 0.f); d4[u] = r4[u];
-              if (a.epi == CVAE_EPI_DACT && o[u] >= 0) {
-                const size_t goff = (size_t)o[u] * a.Cd + col;
-                r4[u] = __ldg(reinterpret_cast<const float4*>(a.epi_ref + goff));
-                if (a.epi_add != nullptr) d4[u] = __ldg(reinterpret_cast<const float4*>(a.epi_add + goff));
-              }
+              d4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (dact && a.epi_add != nullptr && p0 + u < cur.nval)
+                d4[u] = __ldg(reinterpret_cast<const float4*>(a.epi_add + (size_t)(cur.obase + (p0 + u) * ostep) * a.Cd + col));
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (o[u] < 0) continue;
-              const float4 t4 = *reinterpret_cast<const float4*>(eb + (r0 + (p0 + u) * rstep) * kHEpiLd + cg * 4);
-              float x[4] = {t4.x + bias.x, t4.y + bias.y, t4.z + bias.z, t4.w + bias.w};
-              if (a.epi == CVAE_EPI_STATS) {
+              const int ru = p0 + u;
+              if (ru < cur.nval) {
+                const float4 r4 = pre[ru];
+                const float4 t4 = *reinterpret_cast<const float4*>(eb + (r0 + ru * rstep) * kHEpiLd + cg * 4);
+                float x[4] = {t4.x + bias.x, t4.y + bias.y, t4.z + bias.z, t4.w + bias.w};
+                if (a.epi == CVAE_EPI_STATS) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { f1[j] += x[j]; f2[j] = fmaf(x[j], x[j], f2[j]); }
-              } else if (a.epi == CVAE_EPI_DACT) {
-                const float refc[4] = {r4[u].x - ece.x, r4[u].y - ece.y, r4[u].z - ece.z, r4[u].w - ece.w};
-                x[0] += d4[u].x; x[1] += d4[u].y; x[2] += d4[u].z; x[3] += d4[u].w;
-                const float z[4] = {fmaf(refc[0], esc.x, esh.x), fmaf(refc[1], esc.y, esh.y), fmaf(refc[2], esc.z, esh.z),
-                                    fmaf(refc[3], esc.w, esh.w)};
+                  for (int j = 0; j < 4; ++j) { f1[j] += x[j]; f2[j] = fmaf(x[j], x[j], f2[j]); }
+                } else if (dact) {
+                  const float refc[4] = {r4.x - ece.x, r4.y - ece.y, r4.z - ece.z, r4.w - ece.w};
+                  x[0] += d4[u].x; x[1] += d4[u].y; x[2] += d4[u].z; x[3] += d4[u].w;
+                  const float z[4] = {fmaf(refc[0], esc.x, esh.x), fmaf(refc[1], esc.y, esh.y), fmaf(refc[2], esc.z, esh.z),
+                                      fmaf(refc[3], esc.w, esh.w)};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  x[j] = z[j] > 0.f ? x[j] : x[j] * a.e_slope;
-                  f1[j] += x[j]; f2[j] = fmaf(x[j], refc[j], f2[j]);
+                  for (int j = 0; j < 4; ++j) {
+                    x[j] = z[j] > 0.f ? x[j] : x[j] * a.e_slope;
+                    f1[j] += x[j]; f2[j] = fmaf(x[j], refc[j], f2[j]);
+                  }
                 }
+                *reinterpret_cast<float4*>(a.dst + (size_t)(cur.obase + ru * ostep) * a.Cd + col) = make_float4(x[0], x[1], x[2], x[3]);
               }
-              *reinterpret_cast<float4*>(a.dst + (size_t)o[u] * a.Cd + col) = make_float4(x[0], x[1], x[2], x[3]);
+              if (dact && ru < nxt.nval)
+                pre[ru] = __ldg(reinterpret_cast<const float4*>(a.epi_ref + (size_t)(nxt.obase + ru * ostep) * a.Cd + nxt.col));
             }
           }
+          cur = nxt;
           if (want_stats) {                         // fold the chunk's fp32 partials into the fp64 running sums
 #pragma unroll
             for (int j = 0; j < 4; ++j) { s1[j] += (double)f1[j]; s2[j] += (double)f2[j]; }
@@ -736,6 +776,13 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   hp.NB = hp.bslot_bytes >= 32768 ? (bn >= 128 ? 3 : 2) : 4;
   if (hp.bslot_bytes == 32768 && bn < 128) hp.NB = 2;
   hp.tiles_h = (hp.Hq + kHTH - 1) / kHTH; hp.tiles_w = (hp.Wq + kHTW - 1) / kHTW; hp.tiles_n = g.Cd / bn;
+  {
+    // A tile is a 16 x 8 patch of ONE image: feature maps much smaller than that (4 x 4 in the causal_cascade stack:
+    // 16 of 128 MMA rows in use, its ConvTranspose2d 256->128 ran 631 us) go to the per-tap gather kernel, whose
+    // 128-row tiles run across images (CVAE_HALO_MIN_UTIL: least percentage of tile rows in use, default 40)
+    static const int min_util = [] { const char* e = getenv("CVAE_HALO_MIN_UTIL"); return e ? atoi(e) : 40; }();
+    if (g.wtaps >= 2 && 100ll * hp.Hq * hp.Wq < (long long)min_util * hp.tiles_h * hp.tiles_w * kHTH * kHTW) return 1;
+  }
   const long long total = (long long)g.N * hp.tiles_h * hp.tiles_w * hp.tiles_n;
   if (total >= (1ll << 31)) return 1;
   const size_t smem = (size_t)kHNA * kHAStage + (size_t)hp.NB * hp.bslot_bytes + (bn <= 64 ? 2 : 1) * kHEpiBytes + 1024;

@@ -234,20 +234,51 @@ class VesselTrainer:
 
 
 # ---- epoch loops with the reference's names (vessel_analysis/01_train/train.py:62-133) ------------------------------
-def train_one_epoch(vae, train_loader, optimizer, epoch=0, device=None):
-    """train.py:62-98.  `optimizer` is a VesselTrainer (fused step); returns the epoch loss per sample.  Unlike the
-    reference the running totals stay on the device: one host synchronisation per epoch, not one per batch."""
-    trainer = optimizer
-    if not isinstance(trainer, VesselTrainer):
-        raise RuntimeError("train_one_epoch needs a VesselTrainer (fused clip + Adam); wrap the model with VesselTrainer(vae)")
-    dev = trainer.flat.data.device if device is None else device
+_TRAINERS = {}          # id(torch optimizer) -> VesselTrainer built for it (reference-signature calls)
+
+
+def _trainer_for(vae, opt):
+    """The fused trainer behind a stock `torch.optim.Adam(vae.parameters(), lr=...)` (train.py:152): same lr / betas /
+    eps, clip_grad_norm_(5.0) as train.py:85.  Built once per optimizer object."""
+    if isinstance(opt, VesselTrainer):
+        return opt
+    tr = _TRAINERS.get(id(opt))
+    if tr is None or tr.model is not vae:
+        if not isinstance(opt, torch.optim.Adam):
+            raise RuntimeError("train_one_epoch takes a VesselTrainer or the torch.optim.Adam the reference builds "
+                               f"(train.py:152); got {type(opt).__name__}")
+        g = opt.param_groups[0]
+        if len(opt.param_groups) != 1 or g.get("weight_decay", 0) != 0 or g.get("amsgrad", False):
+            raise RuntimeError("only the reference's optimizer form is fused: one group, no weight decay, no amsgrad")
+        tr = VesselTrainer(vae, lr=g["lr"], max_norm=5.0)
+        tr.opt.betas, tr.opt.eps = tuple(g["betas"]), g["eps"]
+        _TRAINERS[id(opt)] = tr
+    return tr
+
+
+def train_one_epoch(*args, **kw):
+    """train.py:62-98.  Accepts the reference's call `train_one_epoch(epoch, vae, train_loader, opt_vae)` (opt_vae: the
+    stock Adam of train.py:152 or a VesselTrainer) and the keyword form `train_one_epoch(vae, train_loader, trainer,
+    epoch=0)`.  Returns the epoch loss per sample.  Unlike the reference the running totals stay on the device: one
+    host synchronisation per epoch, not four per batch."""
+    if args and isinstance(args[0], int):
+        epoch, vae, train_loader, optimizer = args[:4]
+    else:
+        vae, train_loader, optimizer = args[:3]
+    trainer = _trainer_for(vae, optimizer)
+    dev = kw.get("device") or trainer.flat.data.device
     total = torch.zeros((), device=dev)
+    parts = torch.zeros(2, device=dev)
     n = 0
     for x, m, t in train_loader:
         losses = trainer.step(x.to(dev, non_blocking=True), m.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
         total += losses[0].detach()
+        parts += torch.stack([losses[1].detach(), losses[2].detach()])
         n += x.shape[0]
-    return float(total) / max(n, 1)
+    size = len(train_loader.dataset) if hasattr(train_loader, "dataset") else max(n, 1)
+    recon, kld = (parts / size).tolist()
+    print(f"   [Train Breakdown] Recon: {recon:.1f} | KLD: {kld:.1f}")
+    return float(total) / size
 
 
 @torch.no_grad()
@@ -265,6 +296,8 @@ def validate(vae, val_loader, device=None):
         recon, kld, morph, sp = loss_function(out[0], x, out[1], m, out[2], out[3], out[4], out[5])
         tot += torch.stack([total_loss(recon, kld, morph, sp), recon, kld, morph])
         n += x.shape[0]
-    vals = (tot / max(n, 1)).tolist()
+    size = len(val_loader.dataset) if hasattr(val_loader, "dataset") else max(n, 1)
+    vals = (tot / size).tolist()
     validate.breakdown = {"recon": vals[1], "kld": vals[2], "morph": vals[3]}
+    print(f"   [Val Breakdown] Recon: {vals[1]:.1f} | KLD: {vals[2]:.1f} | Morph: {vals[3]:.1f}")
     return vals[0]

@@ -325,3 +325,40 @@ def test_latent_translator_forward_loss_grads(tag):
     Pe = {k: v.detach().cpu().double() if v.is_floating_point() else v.cpu() for k, v in model.state_dict().items()}
     mu_ref, _ = O.lt_encode(Pe, x.double(), train=False)
     assert rel(mu_e, mu_ref) <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# latent translator Ridge + LOOCV on the device
+# ------------------------------------------------------------------------------------------------
+def test_translator_ridge_loocv_on_device():
+    """latent_translator/analysis.py:11-82 with Z, M resident on the GPU: the N + 1 ridge problems as one batched fp64
+    solve on the device, against the golden generated from the live reference function (sklearn Ridge under
+    LeaveOneOut, tests/golden/make_ridge_golden.py)."""
+    import numpy as np
+    from causal_vae_b200.latent_translator import analysis
+    gold = load("ridge_loocv")
+    rng = np.random.default_rng(gold["seed"])
+    N, D, Fm = gold["N"], gold["D"], gold["F"]
+    Z = rng.standard_normal((N, D)).astype(np.float32)
+    Wtrue = rng.standard_normal((D, Fm)) * 0.05
+    M = (Z @ Wtrue + 0.1 * rng.standard_normal((N, Fm)) + np.array([1.0, -2.0, 0.5, 0.0, 3.0, -1.0])).astype(np.float32)
+    names = [f"f{j}" for j in range(Fm)]
+    Zd, Md = torch.from_numpy(Z).cuda(), torch.from_numpy(M).cuda()
+    model, metrics, Mhat, W = analysis.fit_translator_ridge(Zd, Md, feature_names=names, alpha=gold["alpha"])
+    assert model._w.is_cuda                                              # solved where the latents live
+    want = {r["feature"]: r for r in gold["metrics"]}
+    for r in metrics.to_dict(orient="records"):
+        assert abs(r["r2"] - want[r["feature"]]["r2"]) <= 1e-4, r
+        assert abs(r["corr"] - want[r["feature"]]["corr"]) <= 1e-4, r
+    assert list(metrics["feature"]) == [r["feature"] for r in gold["metrics"]]
+    assert np.abs(Mhat - np.array(gold["Mhat"])).max() <= 1e-4 * np.abs(np.array(gold["Mhat"])).max()
+    assert np.abs(W[:, ::37] - np.array(gold["W_sample"])).max() <= 1e-4 * gold["W_absmax"]
+    assert np.abs(model.intercept_ - np.array(gold["intercept"])).max() <= 1e-4
+    # the encode -> translate chain of latent_translator/main.py: latents straight from the device model
+    from causal_vae_b200.latent_translator import engine, models
+    vit = models.ViTVAE(img_size=(64, 64)).cuda()
+    loader = [{"x": torch.rand(4, 1, 64, 64)} for _ in range(4)]
+    Zl = engine.extract_vit_latents(vit, loader, "cuda")
+    assert Zl.shape == (16, 512)
+    _, met, Mh, _ = analysis.fit_translator_ridge(Zl, M, feature_names=names, device="cuda")
+    assert Mh.shape == (16, Fm) and len(met) == Fm
