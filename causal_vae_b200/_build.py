@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcvae_b200.so")
-SOURCES = ["conv.cu", "conv_tc.cu", "conv_halo_tc.cu", "wgrad_tc.cu", "wgrad_tile.cu", "skinny.cu", "conv_few.cu", "pack_batch.cu", "linear_small.cu", "head_bwd.cu", "norm.cu", "attention.cu", "elementwise.cu", "loss_optim.cu", "classify.cu", "input_pipeline.cu"]
+SOURCES = ["conv.cu", "conv_tc.cu", "conv_halo_tc.cu", "wgrad_tc.cu", "wgrad_tile.cu", "skinny.cu", "conv_few.cu", "pack_batch.cu", "linear_small.cu", "head_bwd.cu", "norm.cu", "attention.cu", "elementwise.cu", "loss_optim.cu", "classify.cu", "input_pipeline.cu", "attention_long.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -26,16 +26,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, timing=False):
+    """timing=True: the role-timer build (-DCVAE_TIMING) as libcvae_b200_timing.so beside the product library
+    (loaded only through CVAE_LIB by scripts/bench_layers.py)."""
+    timing = timing or os.environ.get("CVAE_TIMING") == "1"
+    lib_out = LIB.replace(".so", "_timing.so") if timing else LIB
+    if not force and not timing and not needs_build():
         return LIB
     objs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    if os.environ.get("CVAE_TIMING") == "1":       # role-level wait accounting in the tensor-core kernels (debug)
+    if timing:       # role-level wait accounting in the tensor-core kernels (debug)
         flags.append("-DCVAE_TIMING")
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", "_t.o" if timing else ".o"))
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -47,10 +51,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", lib_out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, timing="--timing" in sys.argv))

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvae_b200.so")
+# CVAE_LIB: a differently-built copy of the SAME library (scripts/: the -DCVAE_TIMING role-timer build); never a fallback
+LIB_PATH = os.environ.get("CVAE_LIB") or os.path.join(_HERE, "libcvae_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -85,6 +86,8 @@ _SIGS = {
     "cvae_layernorm_bwd_add": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "cvae_attention_fwd": [vp, vp, vp, i32, i32, i32, i32, f32, u64, u64, vp, vp],
     "cvae_attention_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, u64, vp, vp],
+    "cvae_attention_ws_bytes": [i32, i32, i32, i32],
+    "cvae_attention_bwd_ws": [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp],
     "cvae_act_fwd": [vp, vp, i64, i32, f32, vp],
     "cvae_act_bwd": [vp, vp, vp, i64, i32, f32, vp],
     "cvae_add": [vp, vp, vp, i64, vp],
@@ -137,7 +140,7 @@ EXPORTS = tuple(_SIGS)
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here = header / library drift: fail loudly
     _fn.argtypes = _args
-    _fn.restype = C.c_int64 if _name == "cvae_tc_pack_floats" else C.c_int
+    _fn.restype = C.c_int64 if _name in ("cvae_tc_pack_floats", "cvae_attention_ws_bytes") else C.c_int
 
 _ERR = {-1: "bad argument", -2: "unsupported shape", -3: "alignment", -4: "CUDA launch error"}
 

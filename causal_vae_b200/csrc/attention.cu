@@ -248,6 +248,12 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
 
 static inline int att_threads(int S) { return S <= 20 ? 64 : S <= 40 ? 128 : 256; }
 
+// attention_long.cu: strips of 32 rows with the other operand streamed through shared memory (S > 128)
+int attention_long_fwd(const float* qkv, float* out, float* probs, int B, int S, int H, int d, float dropout_p, uint64_t seed,
+                       uint64_t offset, const int64_t* counter, cudaStream_t st);
+int attention_long_bwd(const float* qkv, const float* probs, const float* dout, float* dqkv, float* ws, int B, int S, int H, int d,
+                       float dropout_p, cudaStream_t st);
+
 }  // namespace cvae
 using namespace cvae;
 
@@ -255,7 +261,8 @@ extern "C" int cvae_attention_fwd(const float* qkv, float* out, float* probs, in
                                   float dropout_p, uint64_t seed, uint64_t offset, const int64_t* counter,
                                   cvae_stream_t s) {
   if (!qkv || !out || !probs || B <= 0 || S <= 0 || H <= 0 || d <= 0) return CVAE_ERR_BAD_ARG;
-  if (S > 128 || d > 64 || (d & 3)) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  if (S > 128) return attention_long_fwd(qkv, out, probs, B, S, H, d, dropout_p, seed, offset, counter, as_stream(s));
+  if (d > 64 || (d & 3)) return CVAE_ERR_UNSUPPORTED_SHAPE;
   const int Sp = (S + kAT - 1) / kAT * kAT, lp = (Sp & 1) ? Sp : Sp + 1;
   const size_t smem = (size_t)(3 * Sp * (d + 1) + Sp * lp) * sizeof(float);
   static size_t attr = 48 * 1024;
@@ -269,8 +276,24 @@ extern "C" int cvae_attention_fwd(const float* qkv, float* out, float* probs, in
   return CVAE_OK;
 }
 
+// Workspace of cvae_attention_bwd_ws: 0 for S <= 128 (everything lives in shared memory), B*H*S floats above
+// (delta_i = sum_j dP_ij P_ij per query row, written by the dQ kernel and read by the dK / dV kernel).
+extern "C" int64_t cvae_attention_ws_bytes(int B, int S, int H, int d) {
+  (void)d;
+  return S > 128 ? (int64_t)B * H * S * (int64_t)sizeof(float) : 0;
+}
+
+extern "C" int cvae_attention_bwd_ws(const float* qkv, const float* probs, const float* dout, float* dqkv, float* ws,
+                                     int64_t ws_bytes, int B, int S, int H, int d, float dropout_p, cvae_stream_t s) {
+  if (!qkv || !probs || !dout || !dqkv || B <= 0 || S <= 0 || H <= 0 || d <= 0) return CVAE_ERR_BAD_ARG;
+  if (S <= 128) return cvae_attention_bwd(qkv, probs, dout, dqkv, B, S, H, d, dropout_p, 0, 0, nullptr, s);
+  if (!ws || ws_bytes < cvae_attention_ws_bytes(B, S, H, d)) return CVAE_ERR_BAD_ARG;
+  return attention_long_bwd(qkv, probs, dout, dqkv, ws, B, S, H, d, dropout_p, as_stream(s));
+}
+
 // `seed`, `offset`, `counter` are accepted for ABI stability and ignored: the mask is read from the
-// sign bits of `probs` (written by cvae_attention_fwd).
+// sign bits of `probs` (written by cvae_attention_fwd).  S <= 128 only: longer sequences need the workspace
+// of cvae_attention_bwd_ws.
 extern "C" int cvae_attention_bwd(const float* qkv, const float* probs, const float* dout, float* dqkv, int B,
                                   int S, int H, int d, float dropout_p, uint64_t seed, uint64_t offset,
                                   const int64_t* counter, cvae_stream_t s) {

@@ -35,13 +35,13 @@ constexpr int kHTH = 16, kHTW = 8;                 // q-space tile: 16 rows x 8 
 constexpr int kHMaxSlots = 184;                    // (16+2)*(8+2) = 180, rounded so a half is 23 KiB
 constexpr int kHHalf = kHMaxSlots * 128;           // bytes of one tf32 plane (hi or lo) of an A stage
 constexpr int kHAStage = 2 * kHHalf;
-constexpr int kHNA = 2;                            // A ring depth (shared memory)
+constexpr int kHNA = 3;                            // largest A ring depth in shared memory (plan: HaloPlan::na)
+constexpr size_t kHMaxDyn = 220 * 1024;            // dynamic shared memory cap: 227 KB per CTA minus the static arrays (~4.3 KB)
 constexpr int kHNAT = 4;                           // A ring depth in tensor-memory mode (64 columns per stage)
 constexpr int kHProdWarps = 8;
-constexpr int kHThreads = (kHProdWarps + 2 + 4) * 32;   // + MMA warp + weight-loader warp + 4 epilogue warps
+constexpr int kHEpiWarps = 8;                      // two groups of four (a warp reads only its own TMEM lane quarter)
+constexpr int kHThreads = (kHProdWarps + 2 + kHEpiWarps) * 32;   // + MMA warp + weight-loader warp + epilogue warps
 constexpr int kHItems = (kHMaxSlots * 8 + kHProdWarps * 32 - 1) / (kHProdWarps * 32);   // 16-byte vectors per producer thread
-constexpr int kHEpiLd = 36;
-constexpr int kHEpiBytes = 128 * kHEpiLd * 4 + 128 * 4;   // one staging tile + its row -> pixel table
 
 // A tap GROUP: the taps (of different output phases) that read the same staged window.  They run as ONE
 // MMA whose B operand stacks their weight tiles along N and whose D spans their (adjacent) accumulators:
@@ -57,6 +57,7 @@ struct HaloPlan {
   int pos[4];                 // accumulator position (TMEM column block) of each phase
   int bslot_bytes;            // weight ring slot: 256 * BN * (largest group)
   int a_tmem;                 // 1: Linear / 1x1 mode with the A operand staged in tensor memory (see the producer)
+  int na;                     // A ring depth (stages of kHAStage bytes in shared memory, or 64-column stages in tensor memory)
   int xacc;                   // 1: cross terms (hi*lo' + lo*hi') in their own accumulator columns [BN, 2BN) -- see the MMA issuer
   HaloPlane plane[4];
 };
@@ -93,7 +94,6 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   __shared__ __align__(8) uint64_t s_bfull[4], s_bempty[4];
   __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ double s_part[4][64];
   __shared__ double s_stat[512];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -102,20 +102,19 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   const uint32_t bstage = (uint32_t)p.bslot_bytes;
   const uint32_t acc_cols = (uint32_t)(a.nphase * BN * (p.xacc ? 2 : 1));
   const uint32_t a_cols = p.a_tmem ? (uint32_t)(kHNAT * 64) : 0u;     // A ring in tensor memory: hi | lo, 32 columns each
-  const int na = p.a_tmem ? kHNAT : kHNA;
+  const int na = p.na;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_cols + a_cols) tmem_cols <<= 1;
   uint8_t* dsm_gen = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
   const uint32_t dsm = smem_u32(dsm_gen);
-  const uint32_t b_base = dsm + kHNA * kHAStage;
-  float* ebuf = reinterpret_cast<float*>(dsm_gen + kHNA * kHAStage + NB * bstage);
+  const uint32_t b_base = dsm + (p.a_tmem ? 0u : (uint32_t)na * kHAStage);
 
   for (int i = tid; i < 512; i += kHThreads) s_stat[i] = 0.0;
   if (warp == kHProdWarps) {
     if (lane == 0) {
       for (int i = 0; i < kHNAT; ++i) { mbar_init(smem_u32(&s_afull[i]), kHProdWarps); mbar_init(smem_u32(&s_aempty[i]), 1); }
       for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&s_bfull[i]), 1); mbar_init(smem_u32(&s_bempty[i]), 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), 4); }
+      for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), kHEpiWarps); }
       mbar_fence_init();
     }
     __syncwarp();
@@ -229,8 +228,8 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
               okm |= 1u << k;
             }
           }
-          const int slot = it % kHNA;
-          T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / kHNA) & 1u) ^ 1u))
+          const int slot = it % na;
+          T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / na) & 1u) ^ 1u))
           uint8_t* sA = dsm_gen + (size_t)slot * kHAStage;
 #pragma unroll
           for (int k = 0; k < kHItems; ++k) {
@@ -411,186 +410,189 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       T_FLUSH(6, 1)
     }
   } else {
-    // ============================== epilogue warps ==============================
-    // Per 32-column chunk: TMEM -> registers -> padded shared tile (thread = accumulator row), one
-    // named barrier, then coalesced 128-bit global stores (thread = 4 channels x several rows).  The
-    // staging tile and the row -> pixel table are double-buffered when shared memory allows (BN <= 64),
-    // so a chunk costs ONE barrier.  A thread always owns the same channel group, so when the tile
-    // covers all channels in one chunk (BN <= 32, one n-tile) the BatchNorm sums stay in registers
-    // for the whole kernel; otherwise they are reduced per chunk into s_stat (absolute channel index).
-    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    // ============================== epilogue warps (two groups of four) ==============================
+    // The accumulators leave tensor memory in the 16-lane x 256-bit shape: thread t of a warp receives rows t/4 and
+    // t/4 + 8 of the 16 lanes, columns 2*(t%4), +1 of each 8-column group -- i.e. four consecutive lanes hold 32
+    // contiguous bytes of one output pixel, so every global access below is a full 32-byte sector per lane quad and
+    // NO shared-memory transposition and NO barrier is needed (the first two generations staged a 128 x 32 tile
+    // through padded shared memory behind a named barrier; with four warps that made the epilogue the limiter of
+    // the HBM-shaped launches: role timers 327 of 345 kclk busy, profiles/r1_ncu_halo_stem3_raw.txt).
+    // Work unit = 16 accumulator columns of one phase; the two groups take alternate units of the SAME tile, so a
+    // tile's drain is shared by eight warps (short tail for the layers with one or two tiles per CTA).
+    // MMA row r = 8*rh + rw is TMEM lane r: warp quarter q holds rh = 4q .. 4q+3, the two 16-lane loads give
+    // (rh, rh+1) and (rh+2, rh+3) for the fixed rw = t/4 of the thread.
     const int ew = warp - (kHProdWarps + 2);
-    const int gt = ew * 32 + lane;
-    const int nchunks = (BN + 31) >> 5;
-    const int cw = min(32, BN);                     // BN in {16, 32, 64, 128}: every chunk has this width
-    const int cgs = cw >> 2, rstep = 128 / cgs;
-    const int cg = gt % cgs, r0 = gt / cgs;
+    const int grp = ew >> 2, q = warp & 3;
+    const int rw = lane >> 2, cpair = (lane & 3) << 1;
+    const int upp = BN >> 4;                          // units per phase
+    const int nunits = a.nphase * upp;
     const bool want_stats = a.epi != CVAE_EPI_PLAIN && a.stats != nullptr;
-    const bool reg_stats = want_stats && nchunks == 1 && p.tiles_n == 1;
-    const int nbuf = BN <= 64 ? 2 : 1;
-    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
-    auto reduce_stats = [&](int chan0) {            // all 128 epilogue threads; sums -> s_stat[chan0 + ...]
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        for (int off = 16; off >= cgs; off >>= 1) {   // lanes sharing a channel group: lane, lane + cgs, ...
-          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
-        }
-      }
-      if (lane < cgs) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { s_part[ew][cg * 4 + j] = s1[j]; s_part[ew][32 + cg * 4 + j] = s2[j]; }
-      }
-      hbar_sync(1, 128);
-      if (gt < 2 * cw) {
-        const int which = gt / cw, cc = gt % cw;
-        s_stat[which * 256 + chan0 + cc] += s_part[0][which * 32 + cc] + s_part[1][which * 32 + cc] +
-                                            s_part[2][which * 32 + cc] + s_part[3][which * 32 + cc];
-      }
-      hbar_sync(1, 128);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
-    };
-    // The activation-derivative epilogue (CVAE_EPI_DACT) re-reads the producer's raw output for every element it
-    // writes.  Those addresses depend only on the tile index, so the rows of the NEXT chunk are requested one chunk
-    // ahead (8 x 128-bit registers per thread): their DRAM latency then overlaps the TMEM drain, the barrier and the
-    // stores of the current chunk -- and, across tiles, the wait for the next accumulator.  Before, each batch of four
-    // rows was a dependent round trip (profiles/r1_ncu_halo_stem3_raw.txt: the 4 epilogue warps were the limiter of
-    // the stride-2 input gradients; role timers: 327 of 345 kclk busy).
+    // a thread sees the same four channels in every unit when the tile spans all channels and a group always gets
+    // the same column half: the sums then stay in registers for the whole kernel
+    const bool reg_stats = want_stats && BN <= 32 && p.tiles_n == 1;
     const bool dact = a.epi == CVAE_EPI_DACT;
-    // A thread's rows of a chunk are r0, r0 + rstep, ...: same column of the patch, (rstep / 8) patch rows apart, so
-    // their output pixels are obase + u * ostep for u < nval (rows past the image bottom / an invalid column: nval = 0)
-    const int ostep = (rstep >> 3) * a.os * a.Wd;
-    struct Rows { int obase, nval, col; };
-    auto rows_of = [&](int t, int phs, int ch) -> Rows {
-      Rows r{0, 0, 0};
-      if (t >= total) return r;
-      const HTile tl = h_decode(p, t);
-      r.col = tl.n0 + ch * 32 + cg * 4;
-      const int qh = tl.h0 + (r0 >> 3), qw = tl.w0 + (r0 & 7);
+    const int ostep = a.os * a.Wd;                    // pixel distance between a thread's consecutive rows
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    struct Unit { int obase, vmask, col, t, ui; };
+    HTile ctl = h_decode(p, blockIdx.x);
+    int ct = blockIdx.x;
+    auto unit_of = [&](int t, int ui) -> Unit {
+      Unit u{0, 0, 0, t, ui};
+      if (t >= total || ui >= nunits) return u;
+      if (t != ct) { ctl = h_decode(p, t); ct = t; }
+      const int phs = ui / upp, hf = ui - phs * upp;
+      u.col = ctl.n0 + hf * 16 + cpair;
+      const int qh = ctl.h0 + 4 * q, qw = ctl.w0 + rw;
       const int oh = qh * a.os + p.ph[phs], ow = qw * a.os + p.pw[phs];
-      if (qw >= p.Wq || ow >= a.Wd) return r;
-      r.obase = (tl.n * a.Hd + oh) * a.Wd + ow;
-      const int dq = rstep >> 3;
-      // rows u with qh + u*dq < Hq and oh + u*dq*os < Hd
-      const int lim_q = p.Hq - qh, lim_o = a.Hd - oh;
-      int n = lim_q > 0 ? (lim_q + dq - 1) / dq : 0;
-      const int n2 = lim_o > 0 ? (lim_o + dq * a.os - 1) / (dq * a.os) : 0;
-      n = min(min(n, n2), cgs);
-      r.nval = n;
-      return r;
+      if (qw >= p.Wq || ow >= a.Wd) return u;
+      u.obase = (ctl.n * a.Hd + oh) * a.Wd + ow;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (qh + r < p.Hq && oh + r * a.os < a.Hd) u.vmask |= 1 << r;
+      return u;
     };
-    float4 pre[8];                                  // reference rows of the chunk about to be processed
+    float2 pre[4][2];                                 // reference rows of the unit about to be processed (DACT)
+    auto prefetch = [&](const Unit& u) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    Rows cur = rows_of(blockIdx.x, 0, 0);
-    if (dact) {
+      for (int r = 0; r < 4; ++r)
+        if (dact && ((u.vmask >> r) & 1)) {
+          const float* rp = a.epi_ref + (size_t)(u.obase + r * ostep) * a.Cd + u.col;
+          pre[r][0] = __ldg(reinterpret_cast<const float2*>(rp));
+          pre[r][1] = __ldg(reinterpret_cast<const float2*>(rp + 8));
+        }
+    };
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (u < cur.nval) pre[u] = __ldg(reinterpret_cast<const float4*>(a.epi_ref + (size_t)(cur.obase + u * ostep) * a.Cd + cur.col));
-    }
-    uint32_t tcount = 0, cidx = 0;
+    for (int r = 0; r < 4; ++r) pre[r][0] = pre[r][1] = make_float2(0.f, 0.f);
+    Unit cur = unit_of(blockIdx.x, grp);
+    prefetch(cur);
+    uint32_t tcount = 0;
     T_DECL
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
-      const HTile tl = h_decode(p, t);
       const uint32_t acc = tcount & 1u;
       T_WAIT(0, mbar_wait(smem_u32(&s_tfull[acc]), (tcount >> 1) & 1u))
       tc_fence_after();
-      for (int phs = 0; phs < a.nphase; ++phs) {
-        const uint32_t d_tmem = tmem + acc * acc_cols + (uint32_t)(p.pos[phs] * BN) + ((uint32_t)(q * 32) << 16);
-        for (int ch = 0; ch < nchunks; ++ch, ++cidx) {
-          float* eb = ebuf + (cidx % nbuf) * 128 * kHEpiLd;
-          {  // TMEM -> padded shared tile (thread = accumulator row)
-            const int row = q * 32 + lane;
-            for (int h = 0; h < cw; h += 16) {
-              float r16[16];
-              tmem_ld16(d_tmem + (uint32_t)(ch * 32 + h), r16);
-              if (p.xacc) {                         // + the cross-term accumulator (rounded fp32 add)
-                float c16[16];
-                tmem_ld16(d_tmem + (uint32_t)(a.nphase * BN + ch * 32 + h), c16);
+      for (int ui = grp; ui < nunits; ui += 2) {
+        const int phs = ui / upp, hf = ui - phs * upp;
+        const uint32_t taddr = tmem + acc * acc_cols + (uint32_t)(p.pos[phs] * BN + hf * 16) + ((uint32_t)(q * 32) << 16);
+        uint32_t v[2][8];
+        tmem_ld_16x256b_x2(taddr, v[0]);
+        tmem_ld_16x256b_x2(taddr + (16u << 16), v[1]);
+        if (p.xacc) {                                 // + the cross-term accumulator (rounded fp32 add)
+          uint32_t c[2][8];
+          const uint32_t xaddr = taddr + (uint32_t)(a.nphase * BN);
+          tmem_ld_16x256b_x2(xaddr, c[0]);
+          tmem_ld_16x256b_x2(xaddr + (16u << 16), c[1]);
+          tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) r16[i] += c16[i];
-              }
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4*>(eb + row * kHEpiLd + h + i) = make_float4(r16[i], r16[i + 1], r16[i + 2], r16[i + 3]);
-            }
-          }
-          if (phs == a.nphase - 1 && ch == nchunks - 1) {   // accumulators drained: hand the TMEM buffer back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));
-          }
-          // rows of the NEXT chunk: as soon as a reference row of this chunk has been consumed, the same register
-          // is re-used for the request of the next chunk's row (in flight for one whole chunk period)
-          Rows nxt;
-          {
-            int nt = t, nphs = phs, nch = ch + 1;
-            if (nch == nchunks) { nch = 0; if (++nphs == a.nphase) { nphs = 0; nt = t + gridDim.x; } }
-            nxt = rows_of(nt, nphs, nch);
-          }
-          hbar_sync(1, 128);
-          const int col = cur.col;
-          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), esc = make_float4(1.f, 1.f, 1.f, 1.f), esh = bias, ece = bias;
-          if (a.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(a.bias + col));
+            for (int i = 0; i < 8; ++i) v[h][i] = __float_as_uint(__uint_as_float(v[h][i]) + __uint_as_float(c[h][i]));
+        } else {
+          tmem_ld_wait();
+        }
+        const bool last = ui + 2 >= nunits;
+        if (last) {                                   // this warp's share of the accumulator is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));
+        }
+        const Unit nxt = last ? unit_of(t + gridDim.x, grp) : unit_of(t, ui + 2);
+        const int col = cur.col;
+        float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};   // fp32 partial sums over the unit's 4 rows
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {                 // the thread's two channel pairs: col + 8g, col + 8g + 1
+          float2 bias = make_float2(0.f, 0.f), esc = make_float2(1.f, 1.f), esh = bias, ece = bias;
+          if (a.bias != nullptr) bias = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * g));
           if (a.e_affine) {
-            esc = __ldg(reinterpret_cast<const float4*>(a.e_scale + col));
-            esh = __ldg(reinterpret_cast<const float4*>(a.e_shift + col));
-            if (a.e_center != nullptr) ece = __ldg(reinterpret_cast<const float4*>(a.e_center + col));
+            esc = __ldg(reinterpret_cast<const float2*>(a.e_scale + col + 8 * g));
+            esh = __ldg(reinterpret_cast<const float2*>(a.e_shift + col + 8 * g));
+            if (a.e_center != nullptr) ece = __ldg(reinterpret_cast<const float2*>(a.e_center + col + 8 * g));
           }
-          float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};   // fp32 partial sums of this chunk's <= 8 rows
+          float2 d2[4];                               // skip-path gradient joining here (ResBlock input gradients)
 #pragma unroll
-          for (int p0 = 0; p0 < 8; p0 += 4) {       // 4 rows per batch: the skip-gradient loads of a batch overlap
-            if (p0 >= cgs) break;
-            float4 d4[4];
+          for (int r = 0; r < 4; ++r) {
+            d2[r] = make_float2(0.f, 0.f);
+            if (dact && a.epi_add != nullptr && ((cur.vmask >> r) & 1))
+              d2[r] = __ldg(reinterpret_cast<const float2*>(a.epi_add + (size_t)(cur.obase + r * ostep) * a.Cd + col + 8 * g));
+          }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              d4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (dact && a.epi_add != nullptr && p0 + u < cur.nval)
-                d4[u] = __ldg(reinterpret_cast<const float4*>(a.epi_add + (size_t)(cur.obase + (p0 + u) * ostep) * a.Cd + col));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int ru = p0 + u;
-              if (ru < cur.nval) {
-                const float4 r4 = pre[ru];
-                const float4 t4 = *reinterpret_cast<const float4*>(eb + (r0 + ru * rstep) * kHEpiLd + cg * 4);
-                float x[4] = {t4.x + bias.x, t4.y + bias.y, t4.z + bias.z, t4.w + bias.w};
-                if (a.epi == CVAE_EPI_STATS) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) { f1[j] += x[j]; f2[j] = fmaf(x[j], x[j], f2[j]); }
-                } else if (dact) {
-                  const float refc[4] = {r4.x - ece.x, r4.y - ece.y, r4.z - ece.z, r4.w - ece.w};
-                  x[0] += d4[u].x; x[1] += d4[u].y; x[2] += d4[u].z; x[3] += d4[u].w;
-                  const float z[4] = {fmaf(refc[0], esc.x, esh.x), fmaf(refc[1], esc.y, esh.y), fmaf(refc[2], esc.z, esh.z),
-                                      fmaf(refc[3], esc.w, esh.w)};
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    x[j] = z[j] > 0.f ? x[j] : x[j] * a.e_slope;
-                    f1[j] += x[j]; f2[j] = fmaf(x[j], refc[j], f2[j]);
-                  }
-                }
-                *reinterpret_cast<float4*>(a.dst + (size_t)(cur.obase + ru * ostep) * a.Cd + col) = make_float4(x[0], x[1], x[2], x[3]);
+          for (int r = 0; r < 4; ++r) {
+            if ((cur.vmask >> r) & 1) {
+              const int vi = 4 * g + 2 * (r & 1);
+              float x0 = __uint_as_float(v[r >> 1][vi]) + bias.x, x1 = __uint_as_float(v[r >> 1][vi + 1]) + bias.y;
+              if (a.epi == CVAE_EPI_STATS) {
+                f1[2 * g] += x0; f2[2 * g] = fmaf(x0, x0, f2[2 * g]);
+                f1[2 * g + 1] += x1; f2[2 * g + 1] = fmaf(x1, x1, f2[2 * g + 1]);
+              } else if (dact) {
+                const float rc0 = pre[r][g].x - ece.x, rc1 = pre[r][g].y - ece.y;
+                x0 += d2[r].x; x1 += d2[r].y;
+                const float z0 = fmaf(rc0, esc.x, esh.x), z1 = fmaf(rc1, esc.y, esh.y);
+                x0 = z0 > 0.f ? x0 : x0 * a.e_slope;
+                x1 = z1 > 0.f ? x1 : x1 * a.e_slope;
+                f1[2 * g] += x0; f2[2 * g] = fmaf(x0, rc0, f2[2 * g]);
+                f1[2 * g + 1] += x1; f2[2 * g + 1] = fmaf(x1, rc1, f2[2 * g + 1]);
               }
-              if (dact && ru < nxt.nval)
-                pre[ru] = __ldg(reinterpret_cast<const float4*>(a.epi_ref + (size_t)(nxt.obase + ru * ostep) * a.Cd + nxt.col));
+              *reinterpret_cast<float2*>(a.dst + (size_t)(cur.obase + r * ostep) * a.Cd + col + 8 * g) = make_float2(x0, x1);
             }
           }
-          cur = nxt;
-          if (want_stats) {                         // fold the chunk's fp32 partials into the fp64 running sums
+        }
+        prefetch(nxt);                                // in flight while the next accumulator is awaited / loaded
+        if (want_stats) {
+          if (reg_stats) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { s1[j] += (double)f1[j]; s2[j] += (double)f2[j]; }
+          } else {
+            // the unit's channels differ from unit to unit: reduce the 8 row-owners of each channel pair with shuffles
+            // (lanes t, t^4, t^8, t^16 share t%4) and fold the warp's 32-row sums into the fp64 totals in shared memory
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+              for (int off = 4; off < 32; off <<= 1) {
+                f1[j] += __shfl_xor_sync(0xffffffffu, f1[j], off);
+                f2[j] += __shfl_xor_sync(0xffffffffu, f2[j], off);
+              }
+            }
+            if (lane < 4) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ch = col + (j & 1) + 8 * (j >> 1);
+                atomicAdd(&s_stat[ch], (double)f1[j]);
+                atomicAdd(&s_stat[256 + ch], (double)f2[j]);
+              }
+            }
           }
-          if (want_stats && !reg_stats) reduce_stats(tl.n0 + ch * 32);   // its barriers also free the staging tile
-          else if (nbuf == 1) hbar_sync(1, 128);                         // single staging tile: free it for reuse
         }
+        cur = nxt;
+      }
+      if (grp >= nunits) {                            // a single-unit tile: the second group only keeps the barrier phase
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));
       }
     }
-    if (gt == 0) T_FLUSH(8, 1)
+    if (ew == 0 && lane == 0) T_FLUSH(8, 1)
     if (want_stats) {
-      if (reg_stats) reduce_stats(0);
-      else hbar_sync(1, 128);
-      for (int i = gt; i < 2 * a.Cd; i += 128) {
+      if (reg_stats && grp < nunits) {
+        const int c0 = (BN == 32 ? grp * 16 : 0) + cpair;       // tiles_n == 1: n0 = 0
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int off = 4; off < 32; off <<= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+          }
+        }
+        if (lane < 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = c0 + (j & 1) + 8 * (j >> 1);
+            atomicAdd(&s_stat[ch], s1[j]);
+            atomicAdd(&s_stat[256 + ch], s2[j]);
+          }
+        }
+      }
+      hbar_sync(1, 256);
+      for (int i = ew * 32 + lane; i < 2 * a.Cd; i += 256) {
         const int which = i / a.Cd, cc = i % a.Cd;
         const double sv = s_stat[which * 256 + cc];
         if (sv != 0.0) atomicAdd(a.stats + i, sv);
@@ -785,13 +787,19 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   }
   const long long total = (long long)g.N * hp.tiles_h * hp.tiles_w * hp.tiles_n;
   if (total >= (1ll << 31)) return 1;
-  const size_t smem = (size_t)kHNA * kHAStage + (size_t)hp.NB * hp.bslot_bytes + (bn <= 64 ? 2 : 1) * kHEpiBytes + 1024;
+  // A ring: tensor memory in Linear mode; else as many shared-memory stages (2 or 3) as fit beside the weight ring --
+  // the producers issue a stage's global loads before they wait for its slot, so a deeper ring is more DRAM latency hidden
+  static const int na_max = [] { const char* e = getenv("CVAE_HALO_NA"); return e ? max(2, min(kHNA, atoi(e))) : kHNA; }();
+  hp.na = hp.a_tmem ? kHNAT : 2;
+  if (!hp.a_tmem && na_max >= 3 && (size_t)3 * kHAStage + (size_t)hp.NB * hp.bslot_bytes + 1024 <= kHMaxDyn) hp.na = 3;
+  const size_t smem = (hp.a_tmem ? 0 : (size_t)hp.na * kHAStage) + (size_t)hp.NB * hp.bslot_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_halo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_halo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess)
       return CVAE_ERR_LAUNCH;
     attr_set = true;
   }
+  if (smem > kHMaxDyn) return 1;
   conv_halo_tc_kernel<<<(int)min(total, (long long)kNumSMs), kHThreads, smem, st>>>(g, hp, (int)total);
   if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); return CVAE_ERR_LAUNCH; }
   return CVAE_OK;

@@ -144,6 +144,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// TMEM -> registers, 16 lanes x 256 bits, two column repetitions: the warp reads lanes [L, L+16) (L = lane field of
+// taddr: the warp's quarter base or + 16) and 16 consecutive columns; thread t receives rows t/4 (r[0], r[1], r[4],
+// r[5]) and t/4 + 8 (r[2], r[3], r[6], r[7]), columns 2*(t%4), +1 of the first (r[0..3]) and second (r[4..7]) 8-column
+// group -- the m16n8 accumulator fragment.  No wait inside: pair with tmem_ld_wait().
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- 3xTF32 split ------------------------------------------------------------------------------
 // v = hi + lo (+ O(2^-22 |v|)): hi = rn_tf32(v), lo = rn_tf32(v - hi).  hi*hi' + lo*hi' + hi*lo'
 // recovers the fp32 product to ~2^-21 relative, accumulated in fp32 by the tensor core.

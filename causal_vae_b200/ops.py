@@ -340,6 +340,12 @@ def attention_fwd(qkv, B, S, H, d, p, seed, offset, counter=None):
 
 def attention_bwd(qkv, probs, dout, B, S, H, d, p, seed, offset, counter=None):
     dqkv = torch.empty_like(qkv)
+    nws = int(L.lib.cvae_attention_ws_bytes(B, S, H, d))
+    if nws:      # S > 128: strip kernels with a per-row workspace (csrc/attention_long.cu)
+        ws = torch.empty(nws // 4, dtype=torch.float32, device=qkv.device)
+        L.check(L.lib.cvae_attention_bwd_ws(L.ptr(qkv), L.ptr(probs), L.ptr(dout), L.ptr(dqkv), L.ptr(ws), nws, B, S, H, d, p,
+                                            L.stream()), f"attention_bwd_ws S={S}")
+        return dqkv
     L.check(L.lib.cvae_attention_bwd(L.ptr(qkv), L.ptr(probs), L.ptr(dout), L.ptr(dqkv), B, S, H, d, p, seed, offset,
                                      L.ptr(counter), L.stream()), "attention_bwd")
     return dqkv

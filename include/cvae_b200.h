@@ -235,13 +235,20 @@ int cvae_layernorm_bwd_add(const float* dy, const float* x, const float* gamma, 
  * qkv: [B, S, 3*D] packed projections; out: [B, S, D]; probs: [B, H, S, S] saved softmax.
  * dropout on the probabilities uses the counter-based generator (seed, offset); `counter`
  * (device int64, may be NULL) is mixed into the seed so a replayed CUDA graph draws fresh masks
- * every step.  S <= 128. */
+ * every step.  S <= 128: one CTA per (batch, head), everything in shared memory (csrc/attention.cu); S > 128
+ * (961 tokens at the reference's default 768x1280 image, vessel_analysis/00_core/config.py:10-11): strips of 32
+ * rows with the other operand streamed through shared memory (csrc/attention_long.cu), forward through the same
+ * entry point, backward through cvae_attention_bwd_ws with a workspace of cvae_attention_ws_bytes()
+ * (cvae_attention_bwd itself returns CVAE_ERR_UNSUPPORTED_SHAPE above 128). */
 int cvae_attention_fwd(const float* qkv, float* out, float* probs, int B, int S, int H, int d,
                        float dropout_p, uint64_t seed, uint64_t offset, const int64_t* counter,
                        cvae_stream_t s);
 int cvae_attention_bwd(const float* qkv, const float* probs, const float* dout, float* dqkv, int B,
                        int S, int H, int d, float dropout_p, uint64_t seed, uint64_t offset,
                        const int64_t* counter, cvae_stream_t s);
+int64_t cvae_attention_ws_bytes(int B, int S, int H, int d);
+int cvae_attention_bwd_ws(const float* qkv, const float* probs, const float* dout, float* dqkv, float* ws,
+                          int64_t ws_bytes, int B, int S, int H, int d, float dropout_p, cvae_stream_t s);
 
 /* ---- elementwise / layout ---------------------------------------------------------------------- */
 enum { CVAE_ACT_LRELU = 0, CVAE_ACT_GELU = 1, CVAE_ACT_SIGMOID = 2 };

@@ -229,6 +229,39 @@ def test_train_step_matches_oracle(cfg):
             assert int(v) == 1
 
 
+def test_default_768x1280_config_runs_and_matches_oracle():
+    """The reference's DEFAULT vessel config (768x1280, vessel_analysis/00_core/config.py:10-11): 24*40 + 1 = 961 tokens,
+    so the ViT blocks take the strip attention kernels (csrc/attention_long.cu) and decoder_input is 512 -> 245760.
+    Eval forward at 2e-5, train-mode losses at 1e-5, global gradient norm against the fp64 oracle."""
+    from causal_vae_b200.vessel import train
+    H, W, B = 768, 1280, 2
+    model, sd = build(H, W)
+    x, m, t, eps = O.vessel_inputs(B, H, W, seed=3)
+    model.eval()
+    with torch.no_grad():
+        outs = model(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+        ref = O.vessel_forward(sd, x, m, t, eps, train=False)
+    for n, a, b in zip(["recon_x", "m_hat", "mu", "logvar", "m_mu", "m_logvar"], outs, ref):
+        assert rel(a, b) <= 2e-5, (n, rel(a, b))
+    trainer = train.VesselTrainer(model, lr=1e-4)
+    trainer.model.train()
+    losses = trainer._fwd_bwd(x.cuda(), m.cuda(), t.cuda(), eps.cuda())
+    P64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    ref64, g64, tot64 = O.vessel_train_step(P64, {}, 1, x.double(), m.double(), t.double(), eps.double())
+    for n, v in zip(["loss", "recon", "kld", "morph", "sparsity"], losses):
+        e = abs(float(v) - float(ref64[n])) / abs(float(ref64[n]))
+        assert e <= 1e-5, (n, float(v), float(ref64[n]), e)
+    # attention-path gradients have no kinks between them and the loss other than the decoder's: compare the tensors
+    # whose gradient flows through the 961-token attention at the oracle's own fp32-vs-fp64 scale
+    P32 = {k: v.clone() for k, v in sd.items()}
+    _, g32, _ = O.vessel_train_step(P32, {}, 1, x, m, t, eps)
+    grads = {k: p.grad.detach() for k, p in model.named_parameters()}
+    tot = float(trainer.flat.grad.double().norm())
+    assert abs(tot - float(tot64)) <= 2e-2 * float(tot64), (tot, float(tot64))
+    for k in ("backbone.decoder.18.weight", "backbone.decoder.18.bias", "dec_adapter.3.bias", "morph_predictor_mu.weight"):
+        assert rel(grads[k], g64[k]) <= max(1e-4, 4 * rel(g32[k], g64[k])), (k, rel(grads[k], g64[k]))
+
+
 def test_graph_replay_equals_eager():
     from causal_vae_b200.vessel import train
     H = W = 64
