@@ -55,6 +55,9 @@ _SIGS = {
     "cvae_conv_gather": [C.POINTER(ConvParams), vp],
     "cvae_wgrad_splits": [i32, i32, i32],
     "cvae_conv_wgrad": [C.POINTER(WgradParams), vp],
+    "cvae_tc_pack_rows_floats": [i64, i32],
+    "cvae_tc_pack_rows": [vp, vp, i64, i32, vp],
+    "cvae_linear_tc_packed": [C.POINTER(ConvParams), vp, vp],
     "cvae_wgrad_reduce": [vp, i32, i32, i32, i32, i32, vp, i32, vp],
     "cvae_pack_weight": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "cvae_conv_few_eligible": [i32] * 12,
@@ -140,7 +143,7 @@ EXPORTS = tuple(_SIGS)
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here = header / library drift: fail loudly
     _fn.argtypes = _args
-    _fn.restype = C.c_int64 if _name in ("cvae_tc_pack_floats", "cvae_attention_ws_bytes") else C.c_int
+    _fn.restype = C.c_int64 if _name in ("cvae_tc_pack_floats", "cvae_attention_ws_bytes", "cvae_tc_pack_rows_floats") else C.c_int
 
 _ERR = {-1: "bad argument", -2: "unsupported shape", -3: "alignment", -4: "CUDA launch error"}
 

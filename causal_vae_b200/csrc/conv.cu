@@ -612,6 +612,7 @@ extern "C" int cvae_conv_gather(const cvae_conv_params_t* p, cvae_stream_t s) {
   if (!p || !p->src || !p->wt || !p->dst || p->N <= 0) return CVAE_ERR_BAD_ARG;
   if (p->epi == CVAE_EPI_DACT && !p->epi_ref) return CVAE_ERR_BAD_ARG;
   GatherArgs g;
+  g.a_image = nullptr;
   g.src = p->src; g.wt = p->wt; g.bias = p->bias; g.dst = p->dst;
   g.in_scale = p->in.scale; g.in_shift = p->in.shift; g.in_center = p->in.center; g.in_slope = p->in.slope;
   g.in_affine = p->in.scale != nullptr; g.in_act = p->in.slope != 1.0f;

@@ -16,6 +16,7 @@ struct GatherArgs {
   int N, Hs, Ws, Cs, Hd, Wd, Cd;
   int os, is, wtaps, nphase, ksplit;
   PhaseGeom phase[4];
+  const float* a_image;   // Linear layers only: the A operand already split and swizzled by cvae_tc_pack_rows (else nullptr)
 };
 
 struct WgradArgs {

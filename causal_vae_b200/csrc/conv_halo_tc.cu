@@ -36,12 +36,15 @@ constexpr int kHMaxSlots = 184;                    // (16+2)*(8+2) = 180, rounde
 constexpr int kHHalf = kHMaxSlots * 128;           // bytes of one tf32 plane (hi or lo) of an A stage
 constexpr int kHAStage = 2 * kHHalf;
 constexpr int kHNA = 3;                            // largest A ring depth in shared memory (plan: HaloPlan::na)
-constexpr size_t kHMaxDyn = 220 * 1024;            // dynamic shared memory cap: 227 KB per CTA minus the static arrays (~4.3 KB)
+constexpr size_t kHMaxDyn = 226 * 1024;            // dynamic shared memory cap: 227 KB per CTA minus the static barriers (~200 B)
+constexpr int kHRawStages = 4;                     // Linear mode: cp.async ring of raw row chunks (k-blocks in flight + 1)
 constexpr int kHNAT = 4;                           // A ring depth in tensor-memory mode (64 columns per stage)
-constexpr int kHProdWarps = 8;
+// Producer warps are a template parameter of the kernel (PW): 8 (18 warps -> 96 registers per thread) for forward-type
+// launches, whose operand transform is the limiter and scales with the number of warps staging it; 6 (16 warps -> 128
+// registers, software-pipelined stages) for input-gradient launches, whose activation-derivative epilogue wants the registers.
 constexpr int kHEpiWarps = 8;                      // two groups of four (a warp reads only its own TMEM lane quarter)
-constexpr int kHThreads = (kHProdWarps + 2 + kHEpiWarps) * 32;   // + MMA warp + weight-loader warp + epilogue warps
-constexpr int kHItems = (kHMaxSlots * 8 + kHProdWarps * 32 - 1) / (kHProdWarps * 32);   // 16-byte vectors per producer thread
+__host__ __device__ constexpr int h_threads(int pw) { return (pw + 2 + kHEpiWarps) * 32; }   // + MMA warp + weight-loader warp + epilogue warps
+__host__ __device__ constexpr int h_items(int pw) { return (kHMaxSlots * 8 + pw * 32 - 1) / (pw * 32); }   // 16-byte vectors per producer thread
 
 // A tap GROUP: the taps (of different output phases) that read the same staged window.  They run as ONE
 // MMA whose B operand stacks their weight tiles along N and whose D spans their (adjacent) accumulators:
@@ -56,7 +59,12 @@ struct HaloPlan {
   int ph[4], pw[4];           // output offset of each phase
   int pos[4];                 // accumulator position (TMEM column block) of each phase
   int bslot_bytes;            // weight ring slot: 256 * BN * (largest group)
+  int a_pre;                  // 1: Linear mode with a pre-packed A image (cvae_tc_pack_rows): the loader warp fetches 32 KB stages
+  int a_stage, a_half;        // A ring geometry in shared memory: bytes per stage, offset of the lo plane
   int a_tmem;                 // 1: Linear / 1x1 mode with the A operand staged in tensor memory (see the producer)
+  int stat_off;               // byte offset (dynamic shared memory) of the epilogue warps' fp64 statistic slices
+  int fence_mode;             // 0: producers fence their stores; 1: the MMA issuer fences once per stage (see the producers)
+  int prefetch;               // 1: the loader warp requests epilogue reference rows / next halo tiles into L2
   int na;                     // A ring depth (stages of kHAStage bytes in shared memory, or 64-column stages in tensor memory)
   int xacc;                   // 1: cross terms (hi*lo' + lo*hi') in their own accumulator columns [BN, 2BN) -- see the MMA issuer
   HaloPlane plane[4];
@@ -87,15 +95,17 @@ __device__ __forceinline__ HTile h_decode(const HaloPlan& p, int t) {
   return o;
 }
 
-__global__ void __launch_bounds__(kHThreads, 1)
+template <int PW>
+__global__ void __launch_bounds__(h_threads(PW), 1)
 conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ HaloPlan p, const int total) {
   extern __shared__ uint8_t dsm_raw[];
   __shared__ __align__(8) uint64_t s_afull[kHNAT], s_aempty[kHNAT];
   __shared__ __align__(8) uint64_t s_bfull[4], s_bempty[4];
   __shared__ __align__(8) uint64_t s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ double s_stat[512];
 
+  constexpr int kHProdWarps = PW, kHItems = h_items(PW);
+  constexpr bool kPipe = PW <= 6;                  // register room for a second set of stage loads
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN, NB = p.NB;
   const int KB = (a.Cs + 31) >> 5;
@@ -107,12 +117,11 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   while (tmem_cols < 2u * acc_cols + a_cols) tmem_cols <<= 1;
   uint8_t* dsm_gen = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
   const uint32_t dsm = smem_u32(dsm_gen);
-  const uint32_t b_base = dsm + (p.a_tmem ? 0u : (uint32_t)na * kHAStage);
+  const uint32_t b_base = dsm + (p.a_tmem ? 0u : (uint32_t)(na * p.a_stage));
 
-  for (int i = tid; i < 512; i += kHThreads) s_stat[i] = 0.0;
   if (warp == kHProdWarps) {
     if (lane == 0) {
-      for (int i = 0; i < kHNAT; ++i) { mbar_init(smem_u32(&s_afull[i]), kHProdWarps); mbar_init(smem_u32(&s_aempty[i]), 1); }
+      for (int i = 0; i < kHNAT; ++i) { mbar_init(smem_u32(&s_afull[i]), p.a_pre ? 1 : (p.a_tmem ? (PW >= 8 ? 8 : 4) : kHProdWarps)); mbar_init(smem_u32(&s_aempty[i]), 1); }
       for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&s_bfull[i]), 1); mbar_init(smem_u32(&s_bempty[i]), 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), kHEpiWarps); }
       mbar_fence_init();
@@ -125,142 +134,236 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  if (warp < kHProdWarps && p.a_tmem) {
+  if (warp < kHProdWarps && p.a_pre) {
+    // A operand pre-packed (cvae_tc_pack_rows): nothing to transform or split -- the loader warp streams it
+  } else if (warp < kHProdWarps && p.a_tmem) {
     // ============================== A producers, Linear / 1x1 mode: rows -> tensor memory ==============================
-    // With both operands in shared memory a kind::tf32 MMA costs ~96 clk for N <= 128 (operand fetch), with A
-    // in tensor memory 64 clk (scripts/umma_rate.cu) - and a Linear layer has no halo to share between taps,
-    // so nothing is lost by leaving shared memory out: thread = one row of the 128-row tile (TMEM lane), warps
-    // w and w + 4 take channels 0-15 / 16-31 of the k-block, hi and lo planes go to columns [0,32) / [32,64)
-    // of the stage with tcgen05.st.
-    const int q = warp & 3, half = warp >> 2;
-    const int row = q * 32 + lane;
-    const uint32_t t_a = tmem + 2u * acc_cols + ((uint32_t)(q * 32) << 16);
-    uint32_t it = 0;
-    T_DECL
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const HTile tl = h_decode(p, t);
-      const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
-      const bool rok = qh < a.Hs && qw < a.Ws;
-      const float* rp = a.src + (((size_t)tl.n * a.Hs + (rok ? qh : 0)) * a.Ws + (rok ? qw : 0)) * a.Cs;
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int c0 = kb * 32 + half * 16;
-        float4 v[4];
+    // With both operands in shared memory a kind::tf32 MMA costs ~100-120 clk whatever N <= 256 is, with A in tensor
+    // memory 51-64 clk (scripts/umma_rate*.cu) - and a Linear layer has no halo to share between taps, so nothing is
+    // lost by leaving shared memory out: thread = one row of the 128-row tile (TMEM lane; warps 0-3, the other producer
+    // warps idle), hi and lo planes of a 32-channel k-block go to columns [0,32) / [32,64) of the stage with tcgen05.st.
+    constexpr int kLinWarps = PW >= 8 ? 8 : 4;       // 8: warps w and w + 4 take channels 0-15 / 16-31 of a k-block
+    constexpr int kHpt = kLinWarps == 8 ? 1 : 2;      // 16-channel halves per thread
+    constexpr int kPitch = kHpt == 1 ? 80 : 144;      // bytes per thread and stage (+16: conflict-free 128-bit reads)
+    if (warp < kLinWarps) {
+      const int q = warp & 3, h0 = kLinWarps == 8 ? (warp >> 2) : 0;
+      const int row = q * 32 + lane;
+      const uint32_t t_a = tmem + 2u * acc_cols + ((uint32_t)(q * 32) << 16);
+      // A thread's channels of a k-block (64 or 128 bytes of its own row) travel global -> shared with cp.async,
+      // kHRawStages - 1 k-blocks ahead and across tile boundaries, into a slot only this thread reads: no barrier, no
+      // registers held while the loads fly.  (First form: load -> transform -> tcgen05.st -> next load, one dependent
+      // round trip per k-block.)
+      uint8_t* raw = dsm_gen + (size_t)NB * bstage + (size_t)tid * kPitch;
+      int ti = blockIdx.x, kbi = 0;                    // next (tile, k-block) to request
+      auto row_ptr = [&](int t) -> const float* {      // this thread's row of tile t, or nullptr past the matrix
+        if (t >= total) return nullptr;
+        const HTile tl = h_decode(p, t);
+        const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
+        if (qh >= a.Hs || qw >= a.Ws) return nullptr;
+        return a.src + (((size_t)tl.n * a.Hs + qh) * a.Ws + qw) * a.Cs;
+      };
+      const float* rpi = row_ptr(ti);
+      auto issue = [&](int slot) {
+        if (ti < total) {
+          const int c0 = kbi * 32 + h0 * 16;
+          const uint32_t dst = smem_u32(raw + (size_t)slot * (kLinWarps * 32 * kPitch));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rok && c0 + 4 * j < a.Cs) v[j] = __ldg(reinterpret_cast<const float4*>(rp + c0 + 4 * j));
-        }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 x = v[j];
-          const int c = c0 + 4 * j;
-          if (rok && c < a.Cs) {   // padding stays exactly 0
-            if (a.in_affine) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c));
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c));
-              float4 ce = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c));
-              x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
-              x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
-            }
-            if (a.in_act) {
-              x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope);
-              x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope);
-            }
+          for (int j = 0; j < 4 * kHpt; ++j) {
+            if (rpi != nullptr && c0 + 4 * j < a.Cs)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * j), "l"(rpi + c0 + 4 * j) : "memory");
+            else
+              asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst + 16u * j), "f"(0.f) : "memory");
           }
-          float4 h4, l4;
-          split4(x, h4, l4);
-          hi[4 * j] = __float_as_uint(h4.x); hi[4 * j + 1] = __float_as_uint(h4.y);
-          hi[4 * j + 2] = __float_as_uint(h4.z); hi[4 * j + 3] = __float_as_uint(h4.w);
-          lo[4 * j] = __float_as_uint(l4.x); lo[4 * j + 1] = __float_as_uint(l4.y);
-          lo[4 * j + 2] = __float_as_uint(l4.z); lo[4 * j + 3] = __float_as_uint(l4.w);
+          if (++kbi == KB) { kbi = 0; ti += gridDim.x; rpi = row_ptr(ti); }
         }
-        const int slot = it % kHNAT;
-        T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / kHNAT) & 1u) ^ 1u))
-        tc_fence_after();
-        tmem_st16(t_a + (uint32_t)(slot * 64 + half * 16), hi);
-        tmem_st16(t_a + (uint32_t)(slot * 64 + 32 + half * 16), lo);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_afull[slot]));
-      }
-    }
-    if (tid == 0) T_FLUSH(0, 1)
-  } else if (warp < kHProdWarps) {
-    // ============================== A producers: halo tile -> swizzled hi / lo planes ==============================
-    const int chunk = tid & 7;
-    const int nslots = p.R * p.C;
-    int it_i[kHItems], it_j[kHItems], it_s[kHItems];
+        asm volatile("cp.async.commit_group;" ::: "memory");     // always: one group per iteration keeps the count uniform
+      };
 #pragma unroll
-    for (int k = 0; k < kHItems; ++k) {
-      const int s = (tid >> 3) + k * (kHProdWarps * 4);
-      it_s[k] = s < nslots ? s : -1;
-      it_i[k] = s / p.C; it_j[k] = s % p.C;
-    }
-    uint32_t it = 0;
-    T_DECL
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const HTile tl = h_decode(p, t);
-      const size_t img = (size_t)tl.n * a.Hs * a.Ws;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int c = kb * 32 + chunk * 4;
-        const bool cok = c < a.Cs;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), ce = sh;
-        if (a.in_affine && cok) {
-          sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c));
-          sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c));
-          if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c));
-        }
-        for (int pl = 0; pl < p.nplanes; ++pl, ++it) {
-          const HaloPlane& P = p.plane[pl];
-          const int bh = (tl.h0 + P.imin) * a.is + P.pr, bw = (tl.w0 + P.jmin) * a.is + P.pc;
-          float4 v[kHItems];
-          uint32_t okm = 0;
+      for (int sidx = 0; sidx < kHRawStages - 1; ++sidx) issue(sidx);
+      uint32_t it = 0;
+      T_DECL
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const HTile tl = h_decode(p, t);
+        const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
+        const bool rok = qh < a.Hs && qw < a.Ws;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          issue((int)((it + kHRawStages - 1) % kHRawStages));
+          asm volatile("cp.async.wait_group %0;" ::"n"(kHRawStages - 1) : "memory");
+          const uint8_t* rs = raw + (size_t)(it % kHRawStages) * (kLinWarps * 32 * kPitch);
+          const int slot = it % kHNAT;
 #pragma unroll
-          for (int k = 0; k < kHItems; ++k) {
-            const int ih = bh + it_i[k] * a.is, iw = bw + it_j[k] * a.is;
-            const bool ok = cok && it_s[k] >= 0 && (unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws;
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-              v[k] = __ldg(reinterpret_cast<const float4*>(a.src + (img + (size_t)ih * a.Ws + iw) * a.Cs + c));
-              okm |= 1u << k;
-            }
-          }
-          const int slot = it % na;
-          T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / na) & 1u) ^ 1u))
-          uint8_t* sA = dsm_gen + (size_t)slot * kHAStage;
+          for (int hh = 0; hh < kHpt; ++hh) {
+            const int half = h0 + hh;
+            const int c0 = kb * 32 + half * 16;
+            uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int k = 0; k < kHItems; ++k) {
-            if (it_s[k] < 0) continue;
-            float4 x = v[k];
-            if ((okm >> k) & 1u) {   // padding stays exactly 0
-              if (a.in_affine) {
-                x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
-                x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+            for (int j = 0; j < 4; ++j) {
+              float4 x = *reinterpret_cast<const float4*>(rs + 64 * hh + 16 * j);
+              const int c = c0 + 4 * j;
+              if (rok && c < a.Cs) {   // padding stays exactly 0
+                if (a.in_affine) {
+                  const float4 sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c));
+                  const float4 sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c));
+                  float4 ce = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c));
+                  x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
+                  x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+                }
+                if (a.in_act) {
+                  x.x = fmaxf(x.x, x.x * a.in_slope); x.y = fmaxf(x.y, x.y * a.in_slope);
+                  x.z = fmaxf(x.z, x.z * a.in_slope); x.w = fmaxf(x.w, x.w * a.in_slope);
+                }
               }
-              if (a.in_act) {
-                x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope);
-                x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope);
-              }
+              float4 h4, l4;
+              split4(x, h4, l4);
+              hi[4 * j] = __float_as_uint(h4.x); hi[4 * j + 1] = __float_as_uint(h4.y);
+              hi[4 * j + 2] = __float_as_uint(h4.z); hi[4 * j + 3] = __float_as_uint(h4.w);
+              lo[4 * j] = __float_as_uint(l4.x); lo[4 * j + 1] = __float_as_uint(l4.y);
+              lo[4 * j + 2] = __float_as_uint(l4.z); lo[4 * j + 3] = __float_as_uint(l4.w);
             }
-            float4 hi, lo;
-            split4(x, hi, lo);
-            const uint32_t off = (uint32_t)it_s[k] * 128u + (uint32_t)(((chunk ^ it_s[k]) & 7) << 4);
-            *reinterpret_cast<float4*>(sA + off) = hi;
-            *reinterpret_cast<float4*>(sA + kHHalf + off) = lo;
+            if (hh == 0) {
+              T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / kHNAT) & 1u) ^ 1u))
+              tc_fence_after();
+            }
+            tmem_st16(t_a + (uint32_t)(slot * 64 + half * 16), hi);
+            tmem_st16(t_a + (uint32_t)(slot * 64 + 32 + half * 16), lo);
           }
-          fence_async_smem();
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&s_afull[slot]));
         }
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (tid == 0) T_FLUSH(0, 1)
+    }
+  } else if (warp < kHProdWarps) {
+    // ============================== A producers: halo tile -> swizzled hi / lo planes ==============================
+    const int chunk = tid & 7;
+    const int nslots = p.R * p.C;
+    // per item, fixed for the whole kernel: where its 16-byte vector lands in the swizzled stage (-1: no such slot) and
+    // where it comes from relative to the stage's first pixel -- an interior stage is then one 64-bit add, one load
+    // per item
+    int soff[kHItems], goff[kHItems];
+#pragma unroll
+    for (int k = 0; k < kHItems; ++k) {
+      const int s = (tid >> 3) + k * (kHProdWarps * 4);
+      const int i = s / p.C, j = s - i * p.C;
+      soff[k] = s < nslots ? s * 128 + (((chunk ^ s) & 7) << 4) : -1;
+      goff[k] = (i * a.is * a.Ws + j * a.is) * a.Cs;
+    }
+    const int span_h = (p.R - 1) * a.is, span_w = (p.C - 1) * a.is;
+    // Software pipeline over stages: the loads of stage i + 1 are issued BEFORE stage i is transformed and stored, so a
+    // stage costs max(memory latency, transform) instead of their sum (role timers: the producers were busy 90-95 %
+    // of the forward stride-2 launches at 0.12 instructions per cycle and warp -- one dependent round trip per stage).
+    struct Stage { int t, kb, pl; };
+    auto advance = [&](Stage st) -> Stage {
+      if (++st.pl == p.nplanes) { st.pl = 0; if (++st.kb == KB) { st.kb = 0; st.t += gridDim.x; } }
+      return st;
+    };
+    int ld_t = -1;
+    HTile ld_tl{0, 0, 0, 0};
+    auto load_stage = [&](const Stage& st, float4 (&v)[kHItems]) -> uint32_t {
+      uint32_t okm = 0;
+      if (st.t != ld_t) { ld_tl = h_decode(p, st.t); ld_t = st.t; }
+      const int c = st.kb * 32 + chunk * 4;
+      const bool cok = c < a.Cs;
+      const HaloPlane& P = p.plane[st.pl];
+      const int bh = (ld_tl.h0 + P.imin) * a.is + P.pr, bw = (ld_tl.w0 + P.jmin) * a.is + P.pc;
+      const long long base = (((long long)ld_tl.n * a.Hs + bh) * a.Ws + bw) * a.Cs + c;     // float index of the stage's first pixel
+      if (cok && bh >= 0 && bw >= 0 && bh + span_h < a.Hs && bw + span_w < a.Ws) {   // interior stage (block-uniform)
+#pragma unroll
+        for (int k = 0; k < kHItems; ++k) {
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (soff[k] >= 0) { v[k] = __ldg(reinterpret_cast<const float4*>(a.src + (base + goff[k]))); okm |= 1u << k; }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kHItems; ++k) {
+          const int sl = (tid >> 3) + k * (kHProdWarps * 4);
+          const int i = sl / p.C, j = sl - i * p.C;
+          const int ih = bh + i * a.is, iw = bw + j * a.is;
+          const bool ok = cok && soff[k] >= 0 && (unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws;
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) { v[k] = __ldg(reinterpret_cast<const float4*>(a.src + (base + goff[k]))); okm |= 1u << k; }
+        }
+      }
+      return okm;
+    };
+    uint32_t it = 0;
+    T_DECL
+    Stage cur{(int)blockIdx.x, 0, 0};
+    float4 v[kHItems], vn[kHItems];
+    uint32_t okm = 0, okn = 0;
+    if (cur.t < total) okm = load_stage(cur, v);
+    int tr_kb = -1;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), ce = sh;
+    while (cur.t < total) {
+      const Stage nxt = advance(cur);
+      if constexpr (kPipe) { if (nxt.t < total) okn = load_stage(nxt, vn); }
+      if (cur.kb != tr_kb) {                         // BatchNorm coefficients of this k-block's channels
+        tr_kb = cur.kb;
+        const int c = cur.kb * 32 + chunk * 4;
+        sc = make_float4(1.f, 1.f, 1.f, 1.f); sh = make_float4(0.f, 0.f, 0.f, 0.f); ce = sh;
+        if (a.in_affine && c < a.Cs) {
+          sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c));
+          sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c));
+          if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c));
+        }
+      }
+      const int slot = it % na;
+      T_WAIT(0, mbar_wait(smem_u32(&s_aempty[slot]), ((it / na) & 1u) ^ 1u))
+      uint8_t* sA = dsm_gen + (size_t)slot * p.a_stage;
+      // Straight-line transform: no per-item branches, so the compiler interleaves the 32 independent value chains of the
+      // 8 items (the per-item `if`s of the first form left one dependent chain per basic block: ncu showed the producer
+      // warps issuing one instruction per ~7.7 clk, stall reason "wait").  Without BatchNorm the coefficients are
+      // (1, 0, 0) and without activation the slope is 1: fma(x - 0, 1, 0) and max(x, x) reproduce x exactly; padding is
+      // forced back to exactly 0 by the select.
+      const float slope = a.in_act ? a.in_slope : 1.f;
+#pragma unroll
+      for (int k = 0; k < kHItems; ++k) {
+        float4 x = v[k];
+        x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
+        x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+        x.x = fmaxf(x.x, x.x * slope); x.y = fmaxf(x.y, x.y * slope);
+        x.z = fmaxf(x.z, x.z * slope); x.w = fmaxf(x.w, x.w * slope);
+        const bool real = (okm >> k) & 1u;
+        x.x = real ? x.x : 0.f; x.y = real ? x.y : 0.f; x.z = real ? x.z : 0.f; x.w = real ? x.w : 0.f;
+        float4 hi, lo;
+        split4(x, hi, lo);
+        if (soff[k] >= 0) {
+          *reinterpret_cast<float4*>(sA + soff[k]) = hi;
+          *reinterpret_cast<float4*>(sA + kHHalf + soff[k]) = lo;
+        }
+      }
+      // generic-proxy stores -> async-proxy reads (tcgen05.mma operands) need a proxy fence somewhere on the causality
+      // path.  On the writers' side (fence_mode 0) every producer thread fences with its 128-bit stores still in flight:
+      // ncu attributed 29 % of ALL stall samples of the kernel to that MEMBAR (~45 % of the producers' time).
+      // fence_mode 1: the writers only release through the mbarrier and the MMA issuer fences once per stage after
+      // its acquire (PTX memory model: the proxy fence may sit anywhere along the base causality order).
+      if (p.fence_mode == 0) fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_afull[slot]));
+      if constexpr (kPipe) {
+#pragma unroll
+        for (int k = 0; k < kHItems; ++k) v[k] = vn[k];
+        okm = okn;
+      } else {
+        if (nxt.t < total) okm = load_stage(nxt, v);
+      }
+      cur = nxt;
+      ++it;
     }
     if (tid == 0) T_FLUSH(0, 1)
   } else if (warp == kHProdWarps) {
-    // ============================== MMA issuer (one thread) ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer (one elected lane of a CONVERGED warp) ==============================
+    // The whole warp runs the loop (barrier waits, descriptor arithmetic: all warp-uniform values) and only the issue
+    // itself is predicated on the elected lane.  Inside `if (lane == 0)` the compiler must treat every operand as
+    // per-thread data and wraps each tcgen05.mma in an ELECT / BRA.U.ANY loop with predicate chains (6 dependent
+    // instructions per MMA, SASS); that loop, not the tensor core, was the "96.6 clk per kind::tf32 MMA whatever N"
+    // of scripts/umma_rate.cu -- converged, the descriptors live in uniform registers and the MMAs issue back to back.
+    {
+      const bool leader = elect_one();
       const uint32_t sbo = (uint32_t)p.C * 128u;
       const uint64_t a_desc_hi = make_smem_desc(0, 16, sbo, kLayoutSw128);     // everything but the address
       const uint64_t b_desc_hi = make_smem_desc(0, 16, 1024, kLayoutSw128);
@@ -278,8 +381,9 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             const HaloPlane& P = p.plane[pl];
             const int aslot = ita % na;
             T_WAIT(1, mbar_wait(smem_u32(&s_afull[aslot]), (ita / na) & 1u))
+            if (p.fence_mode == 1 && !p.a_tmem) fence_async_smem();
             tc_fence_after();
-            const uint32_t a_hi0 = dsm + (uint32_t)aslot * kHAStage;
+            const uint32_t a_hi0 = dsm + (uint32_t)(aslot * p.a_stage);
             if (p.a_tmem) {          // one tap, A operand in tensor memory (columns: hi [0,32), lo [32,64) of the stage)
               const int bslot = itb % NB;
               T_WAIT(2, mbar_wait(smem_u32(&s_bfull[bslot]), (itb / NB) & 1u))
@@ -297,25 +401,25 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
                 const uint32_t idesc2 = make_idesc_tf32(128, 2 * BN, 0, 0);
 #pragma unroll 4
                 for (int k = 0; k < ksteps; ++k) {
-                  mma_tf32_ts(d_base, ta_hi, dbh, idesc2, accum);
-                  mma_tf32_ts(d_base + (uint32_t)BN, ta_lo, dbh, idesc, 1u);
+                  if (leader) mma_tf32_ts(d_base, ta_hi, dbh, idesc2, accum);
+                  if (leader) mma_tf32_ts(d_base + (uint32_t)BN, ta_lo, dbh, idesc, 1u);
                   accum = 1u;
                   ta_hi += 8; ta_lo += 8; dbh += 2;
                 }
               } else {
 #pragma unroll 4
                 for (int k = 0; k < ksteps; ++k) {
-                  mma_tf32_ts(d_base, ta_lo, dbh, idesc, accum);
-                  mma_tf32_ts(d_base, ta_hi, dbl, idesc, 1u);
-                  mma_tf32_ts(d_base, ta_hi, dbh, idesc, 1u);
+                  if (leader) mma_tf32_ts(d_base, ta_lo, dbh, idesc, accum);
+                  if (leader) mma_tf32_ts(d_base, ta_hi, dbl, idesc, 1u);
+                  if (leader) mma_tf32_ts(d_base, ta_hi, dbh, idesc, 1u);
                   accum = 1u;
                   ta_hi += 8; ta_lo += 8; dbh += 2; dbl += 2;
                 }
               }
               started = 1u;
-              mma_commit(smem_u32(&s_bempty[bslot]));
+              if (leader) mma_commit(smem_u32(&s_bempty[bslot]));
               ++itb;
-              mma_commit(smem_u32(&s_aempty[aslot]));
+              if (leader) mma_commit(smem_u32(&s_aempty[aslot]));
               continue;
             }
             for (int tp = 0; tp < P.ntaps; ++tp, ++itb) {
@@ -334,7 +438,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
               // (the issuing thread is latency-bound: rebuilding four descriptors per k-step capped
               // the issue rate at ~1 MMA / 100 clk -- measured with the CVAE_TIMING build)
               uint64_t dah = a_desc_hi | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
-              uint64_t dal = a_desc_hi | (uint64_t)(((a_hi + kHHalf) & 0x3FFFFu) >> 4);
+              uint64_t dal = a_desc_hi | (uint64_t)(((a_hi + (uint32_t)p.a_half) & 0x3FFFFu) >> 4);
               uint64_t dbh = b_desc_hi | (uint64_t)((b_hi & 0x3FFFFu) >> 4);
               uint64_t dbl = b_desc_hi | (uint64_t)(((b_hi + 128u * ng) & 0x3FFFFu) >> 4);
               if (p.xacc && a.nphase > 1) {
@@ -344,9 +448,9 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
                 uint32_t accx = (startedx & gmask) ? 1u : 0u;
 #pragma unroll 4
                 for (int k = 0; k < ksteps; ++k) {
-                  mma_tf32(dx_tmem, dal, dbh, idesc, accx);
-                  mma_tf32(dx_tmem, dah, dbl, idesc, 1u);
-                  mma_tf32(d_tmem, dah, dbh, idesc, accum);
+                  if (leader) mma_tf32(dx_tmem, dal, dbh, idesc, accx);
+                  if (leader) mma_tf32(dx_tmem, dah, dbl, idesc, 1u);
+                  if (leader) mma_tf32(d_tmem, dah, dbh, idesc, accum);
                   accum = 1u; accx = 1u;
                   dah += 2; dal += 2; dbh += 2; dbl += 2;
                 }
@@ -355,41 +459,95 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
                 const uint32_t idesc2 = make_idesc_tf32(128, 2 * BN, 0, 0);
 #pragma unroll 4
                 for (int k = 0; k < ksteps; ++k) {
-                  mma_tf32(d_tmem, dah, dbh, idesc2, accum);
-                  mma_tf32(d_tmem + (uint32_t)BN, dal, dbh, idesc, 1u);
+                  if (leader) mma_tf32(d_tmem, dah, dbh, idesc2, accum);
+                  if (leader) mma_tf32(d_tmem + (uint32_t)BN, dal, dbh, idesc, 1u);
                   accum = 1u;
                   dah += 2; dal += 2; dbh += 2;
                 }
               } else {
 #pragma unroll 4
                 for (int k = 0; k < ksteps; ++k) {
-                  mma_tf32(d_tmem, dal, dbh, idesc, accum);
-                  mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                  mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                  if (leader) mma_tf32(d_tmem, dal, dbh, idesc, accum);
+                  if (leader) mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                  if (leader) mma_tf32(d_tmem, dah, dbh, idesc, 1u);
                   accum = 1u;
                   dah += 2; dal += 2; dbh += 2; dbl += 2;      // + 32 bytes (8 tf32) along K
                 }
               }
               started |= gmask;
-              mma_commit(smem_u32(&s_bempty[bslot]));
+              if (leader) mma_commit(smem_u32(&s_bempty[bslot]));
             }
-            mma_commit(smem_u32(&s_aempty[aslot]));
+            if (leader) mma_commit(smem_u32(&s_aempty[aslot]));
           }
         }
-        mma_commit(smem_u32(&s_tfull[acc]));
+        if (leader) mma_commit(smem_u32(&s_tfull[acc]));
       }
-      T_FLUSH(2, 3)
+      if (leader) T_FLUSH(2, 3)
     }
   } else if (warp == kHProdWarps + 1) {
-    // ============================== weight loader (TMA, one thread) ==============================
-    if (lane == 0) {
-      uint32_t itb = 0;
-      T_DECL
-      const uint32_t bbytes = 128u * BN;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    // ============================== weight loader (TMA, one thread) + L2 prefetcher (the warp) ==============================
+    // The warp first requests into L2 what the OTHER roles will read from global memory about one tile later: the
+    // producer's raw output rows that the activation-derivative epilogue re-reads for THIS tile (the epilogue keeps only
+    // one work unit of loads in flight -- 16 KB per SM against the ~90 KB that 44 B/ns x 2 us of DRAM latency needs;
+    // role timers before: epilogue busy 275 of 294 kclk on the stem.3 input gradient) and the input halo rows of the
+    // NEXT tile.  One lane per image row segment; the n-tile-0 CTA of a spatial tile does it.  Off by default
+    // (CVAE_HALO_PREFETCH=1): measured neutral to harmful, see DESIGN.md.
+    const bool pf_on = p.prefetch != 0;
+    const bool ld_leader = elect_one();
+    uint32_t itb = 0, ita = 0;
+    T_DECL
+    const uint32_t bbytes = 128u * BN;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      if (pf_on) {
+        __syncwarp();
+        if (a.epi == CVAE_EPI_DACT && t % p.tiles_n == 0) {
+          const HTile tl = h_decode(p, t);
+          const int oh0 = tl.h0 * a.os, ow0 = tl.w0 * a.os;
+          const int npx = min(kHTW * a.os, a.Wd - ow0);
+          const uint32_t bytes = (uint32_t)(npx * a.Cd) * 4u;
+          for (int r = lane; r < kHTH * a.os; r += 32) {
+            if (oh0 + r >= a.Hd || npx <= 0) break;
+            const size_t o = ((size_t)(tl.n * a.Hd + oh0 + r) * a.Wd + ow0) * a.Cd;
+            prefetch_l2_lines(a.epi_ref + o, bytes);
+            if (a.epi_add != nullptr) prefetch_l2_lines(a.epi_add + o, bytes);
+          }
+        }
+        const int tn = t + gridDim.x;
+        if (tn < total && !p.a_tmem && tn % p.tiles_n == 0) {
+          const HTile tl = h_decode(p, tn);
+          // union of the planes' staged windows (plane rows / columns are `is` apart)
+          int r_lo = 1 << 30, r_hi = -(1 << 30), c_lo = 1 << 30, c_hi = -(1 << 30);
+          for (int pl = 0; pl < p.nplanes; ++pl) {
+            const HaloPlane& P = p.plane[pl];
+            const int bh = (tl.h0 + P.imin) * a.is + P.pr, bw = (tl.w0 + P.jmin) * a.is + P.pc;
+            r_lo = min(r_lo, bh); r_hi = max(r_hi, bh + (p.R - 1) * a.is);
+            c_lo = min(c_lo, bw); c_hi = max(c_hi, bw + (p.C - 1) * a.is);
+          }
+          r_lo = max(r_lo, 0); r_hi = min(r_hi, a.Hs - 1); c_lo = max(c_lo, 0); c_hi = min(c_hi, a.Ws - 1);
+          if (c_hi >= c_lo) {
+            const uint32_t bytes = (uint32_t)((c_hi - c_lo + 1) * a.Cs) * 4u;
+            for (int r = r_lo + lane; r <= r_hi; r += 32)
+              prefetch_l2_lines(a.src + ((size_t)(tl.n * a.Hs + r) * a.Ws + c_lo) * a.Cs, bytes);
+          }
+        }
+        __syncwarp();
+      }
+      if (ld_leader) {
         const int n0 = (t % p.tiles_n) * BN;
+        const int mt = t / p.tiles_n;                  // a_pre: 128-row tile of the packed A image
         for (int kb = 0; kb < KB; ++kb)
           for (int pl = 0; pl < p.nplanes; ++pl) {
+            if (p.a_pre) {                             // this k-block's A stage: hi and lo planes, 16 KB each
+              const int aslot = ita % na;
+              T_WAIT(0, mbar_wait(smem_u32(&s_aempty[aslot]), ((ita / na) & 1u) ^ 1u))
+              const uint32_t afull = smem_u32(&s_afull[aslot]);
+              const uint32_t sA = dsm + (uint32_t)(aslot * p.a_stage);
+              const float* asrc = a.a_image + ((size_t)mt * KB + kb) * 8192;
+              mbar_arrive_expect_tx(afull, 32768u);
+              bulk_g2s(sA, asrc, 16384u, afull);
+              bulk_g2s(sA + (uint32_t)p.a_half, asrc + 4096, 16384u, afull);
+              ++ita;
+            }
             const HaloPlane& P = p.plane[pl];
             for (int tp = 0; tp < P.ntaps; ++tp, ++itb) {
               const int bslot = itb % NB;
@@ -407,8 +565,8 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             }
           }
       }
-      T_FLUSH(6, 1)
     }
+    if (ld_leader) T_FLUSH(6, 1)
   } else {
     // ============================== epilogue warps (two groups of four) ==============================
     // The accumulators leave tensor memory in the 16-lane x 256-bit shape: thread t of a warp receives rows t/4 and
@@ -424,13 +582,24 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
     const int ew = warp - (kHProdWarps + 2);
     const int grp = ew >> 2, q = warp & 3;
     const int rw = lane >> 2, cpair = (lane & 3) << 1;
-    const int upp = BN >> 4;                          // units per phase
+    const int upp = BN >> 4;                          // units per phase (1, 2, 4 or 8)
+    const int upp_sh = 31 - __clz(upp);
     const int nunits = a.nphase * upp;
     const bool want_stats = a.epi != CVAE_EPI_PLAIN && a.stats != nullptr;
+    // BatchNorm sums of the CTA: one private [2][256] fp64 slice per epilogue warp (its lanes 0-3 own distinct channels
+    // after the shuffle reduction), summed over the eight warps at the end.  The shared-memory fp64 atomics this replaces
+    // (a compare-and-swap loop per add) were 13 % of the kernel's stall samples on the stem.3 forward.
+    double* wstat = reinterpret_cast<double*>(dsm_gen + p.stat_off);
+    double* wst = wstat + ew * 512;
+    if (want_stats) {
+      for (int i = lane; i < 512; i += 32) wst[i] = 0.0;
+      __syncwarp();
+    }
     // a thread sees the same four channels in every unit when the tile spans all channels and a group always gets
     // the same column half: the sums then stay in registers for the whole kernel
     const bool reg_stats = want_stats && BN <= 32 && p.tiles_n == 1;
     const bool dact = a.epi == CVAE_EPI_DACT;
+    const bool has_add = dact && a.epi_add != nullptr;
     const int ostep = a.os * a.Wd;                    // pixel distance between a thread's consecutive rows
     double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
     struct Unit { int obase, vmask, col, t, ui; };
@@ -440,7 +609,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       Unit u{0, 0, 0, t, ui};
       if (t >= total || ui >= nunits) return u;
       if (t != ct) { ctl = h_decode(p, t); ct = t; }
-      const int phs = ui / upp, hf = ui - phs * upp;
+      const int phs = ui >> upp_sh, hf = ui - (phs << upp_sh);
       u.col = ctl.n0 + hf * 16 + cpair;
       const int qh = ctl.h0 + 4 * q, qw = ctl.w0 + rw;
       const int oh = qh * a.os + p.ph[phs], ow = qw * a.os + p.pw[phs];
@@ -472,7 +641,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       T_WAIT(0, mbar_wait(smem_u32(&s_tfull[acc]), (tcount >> 1) & 1u))
       tc_fence_after();
       for (int ui = grp; ui < nunits; ui += 2) {
-        const int phs = ui / upp, hf = ui - phs * upp;
+        const int phs = ui >> upp_sh, hf = ui - (phs << upp_sh);
         const uint32_t taddr = tmem + acc * acc_cols + (uint32_t)(p.pos[phs] * BN + hf * 16) + ((uint32_t)(q * 32) << 16);
         uint32_t v[2][8];
         tmem_ld_16x256b_x2(taddr, v[0]);
@@ -510,10 +679,12 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
           }
           float2 d2[4];                               // skip-path gradient joining here (ResBlock input gradients)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            d2[r] = make_float2(0.f, 0.f);
-            if (dact && a.epi_add != nullptr && ((cur.vmask >> r) & 1))
-              d2[r] = __ldg(reinterpret_cast<const float2*>(a.epi_add + (size_t)(cur.obase + r * ostep) * a.Cd + col + 8 * g));
+          for (int r = 0; r < 4; ++r) d2[r] = make_float2(0.f, 0.f);
+          if (has_add) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if ((cur.vmask >> r) & 1)
+                d2[r] = __ldg(reinterpret_cast<const float2*>(a.epi_add + (size_t)(cur.obase + r * ostep) * a.Cd + col + 8 * g));
           }
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
@@ -543,21 +714,21 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             for (int j = 0; j < 4; ++j) { s1[j] += (double)f1[j]; s2[j] += (double)f2[j]; }
           } else {
             // the unit's channels differ from unit to unit: reduce the 8 row-owners of each channel pair with shuffles
-            // (lanes t, t^4, t^8, t^16 share t%4) and fold the warp's 32-row sums into the fp64 totals in shared memory
+            // (lanes t, t^4, t^8, t^16 share t%4) and fold the warp's 32-row sums into its fp64 slice in shared memory.
+            // The sums go to fp64 BEFORE the shuffles: the gradient sums cancel heavily, and fp32 partials over 32 rows
+            // (instead of this thread's 4) showed up as 1.2 x the tolerance in the batch-of-4 CNN-variant gradient test
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+              double a1 = (double)f1[j], a2 = (double)f2[j];
 #pragma unroll
               for (int off = 4; off < 32; off <<= 1) {
-                f1[j] += __shfl_xor_sync(0xffffffffu, f1[j], off);
-                f2[j] += __shfl_xor_sync(0xffffffffu, f2[j], off);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, off);
               }
-            }
-            if (lane < 4) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              if (lane < 4) {                         // this warp's own slots: plain read-modify-write, no atomics
                 const int ch = col + (j & 1) + 8 * (j >> 1);
-                atomicAdd(&s_stat[ch], (double)f1[j]);
-                atomicAdd(&s_stat[256 + ch], (double)f2[j]);
+                wst[ch] += a1;
+                wst[256 + ch] += a2;
               }
             }
           }
@@ -586,15 +757,17 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int ch = c0 + (j & 1) + 8 * (j >> 1);
-            atomicAdd(&s_stat[ch], s1[j]);
-            atomicAdd(&s_stat[256 + ch], s2[j]);
+            wst[ch] += s1[j];
+            wst[256 + ch] += s2[j];
           }
         }
       }
-      hbar_sync(1, 256);
-      for (int i = ew * 32 + lane; i < 2 * a.Cd; i += 256) {
+      hbar_sync(1, kHEpiWarps * 32);
+      for (int i = ew * 32 + lane; i < 2 * a.Cd; i += kHEpiWarps * 32) {
         const int which = i / a.Cd, cc = i % a.Cd;
-        const double sv = s_stat[which * 256 + cc];
+        double sv = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < kHEpiWarps; ++w8) sv += wstat[w8 * 512 + which * 256 + cc];
         if (sv != 0.0) atomicAdd(a.stats + i, sv);
       }
     }
@@ -740,6 +913,7 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
     g.phase[0].Hq = g.Hs; g.phase[0].Wq = 8;
   }
   if (g.Cs % 16 != 0 || g.Cd % 16 != 0) return 1;
+  if (g.in_act && !(g.in_slope >= 0.f && g.in_slope <= 1.f)) return 1;      // the producers use max(v, slope * v)
   if (g.Cd > 256 && g.epi != CVAE_EPI_PLAIN && g.stats != nullptr) return 1;   // s_stat holds 256 channels
   // cross-term accumulators (xacc, see the MMA issuer) double the accumulator columns.  Gather plans keep their tile
   // width (N <= 128: 2 * 2 * 128 = 512 columns); scatter plans (4 phases) fit with BN <= 32, which costs the wide
@@ -766,7 +940,10 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   hp.BN = bn;
   {  // Linear / 1x1 layers: A operand through tensor memory (CVAE_LIN_TMEM=0 keeps it in shared memory)
     static const bool lin_tmem = [] { const char* e = getenv("CVAE_LIN_TMEM"); return !(e && e[0] == '0'); }();
-    hp.a_tmem = (lin_tmem && g.wtaps < 2 && hp.nplanes == 1 && g.nphase == 1 && hp.plane[0].ntaps == 1 &&
+    hp.a_pre = (g.a_image != nullptr && g.wtaps < 2 && hp.nplanes == 1 && g.nphase == 1 && hp.plane[0].ntaps == 1 &&
+                !g.in_affine && !g.in_act) ? 1 : 0;
+    if (g.a_image != nullptr && !hp.a_pre) return 1;
+    hp.a_tmem = (!hp.a_pre && lin_tmem && g.wtaps < 2 && hp.nplanes == 1 && g.nphase == 1 && hp.plane[0].ntaps == 1 &&
                  2 * bn + kHNAT * 64 <= 512) ? 1 : 0;
     // separate cross-term accumulators: gather-type plans (one phase, one tap per MMA) whose doubled accumulators
     // still fit tensor memory twice (CVAE_XACC=0 restores the single-accumulator 3-MMA form)
@@ -789,18 +966,39 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   if (total >= (1ll << 31)) return 1;
   // A ring: tensor memory in Linear mode; else as many shared-memory stages (2 or 3) as fit beside the weight ring --
   // the producers issue a stage's global loads before they wait for its slot, so a deeper ring is more DRAM latency hidden
-  static const int na_max = [] { const char* e = getenv("CVAE_HALO_NA"); return e ? max(2, min(kHNA, atoi(e))) : kHNA; }();
-  hp.na = hp.a_tmem ? kHNAT : 2;
-  if (!hp.a_tmem && na_max >= 3 && (size_t)3 * kHAStage + (size_t)hp.NB * hp.bslot_bytes + 1024 <= kHMaxDyn) hp.na = 3;
-  const size_t smem = (hp.a_tmem ? 0 : (size_t)hp.na * kHAStage) + (size_t)hp.NB * hp.bslot_bytes + 1024;
+  static const bool pf = [] { const char* e = getenv("CVAE_HALO_PREFETCH"); return e && e[0] == '1'; }();
+  hp.prefetch = pf ? 1 : 0;
+  static const int fmode = [] { const char* e = getenv("CVAE_HALO_FENCE"); return e ? atoi(e) : 1; }();
+  hp.fence_mode = fmode;
+  static const int na_max = [] { const char* e = getenv("CVAE_HALO_NA"); return e ? max(2, min(kHNA, atoi(e))) : 2; }();   // measured: 3 stages no faster
+  hp.na = hp.a_tmem ? kHNAT : (hp.a_pre ? 3 : 2);
+  hp.a_stage = hp.a_pre ? 32768 : kHAStage;
+  hp.a_half = hp.a_pre ? 16384 : kHHalf;
+  if (!hp.a_tmem && !hp.a_pre && na_max >= 3 && (size_t)3 * kHAStage + (size_t)hp.NB * hp.bslot_bytes + 1024 <= kHMaxDyn) hp.na = 3;
+  const size_t stat_bytes = (g.epi != CVAE_EPI_PLAIN && g.stats != nullptr) ? (size_t)kHEpiWarps * 512 * sizeof(double) : 0;
+  // producer warps (template parameter): 6 + pipelined stages for the activation-derivative launches, 8 otherwise
+  static const int pw_env = [] { const char* e = getenv("CVAE_HALO_PW"); return e ? atoi(e) : 0; }();
+  // measured on the vessel step (B = 64): 8 everywhere 8.23 ms, 6 for every activation-derivative launch 8.38 ms, 6 everywhere
+  // 8.69 ms -- the 6-warp form only pays on the HBM-shaped scatter launches with few channels (stem.3 input gradient
+  // 175 -> 152 us), so that is where it is used
+  const int pw = pw_env == 6 || pw_env == 8 ? pw_env
+                 : ((g.epi == CVAE_EPI_DACT && g.nphase > 1 && g.Cd <= 32 && !hp.a_tmem && !hp.a_pre) ? 6 : 8);
+  const size_t a_bytes = hp.a_tmem ? (size_t)kHRawStages * (pw >= 8 ? 256 * 80 : 128 * 144) : (size_t)hp.na * hp.a_stage;
+  while (hp.NB > 2 && a_bytes + (size_t)hp.NB * hp.bslot_bytes + stat_bytes + 1024 > kHMaxDyn) --hp.NB;   // shallower weight ring
+  size_t smem = a_bytes + (size_t)hp.NB * hp.bslot_bytes;
+  hp.stat_off = (int)smem;
+  smem += stat_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_halo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_halo_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_halo_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess)
       return CVAE_ERR_LAUNCH;
     attr_set = true;
   }
   if (smem > kHMaxDyn) return 1;
-  conv_halo_tc_kernel<<<(int)min(total, (long long)kNumSMs), kHThreads, smem, st>>>(g, hp, (int)total);
+  const int grid = (int)min(total, (long long)kNumSMs);
+  if (pw == 6) conv_halo_tc_kernel<6><<<grid, h_threads(6), smem, st>>>(g, hp, (int)total);
+  else conv_halo_tc_kernel<8><<<grid, h_threads(8), smem, st>>>(g, hp, (int)total);
   if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); return CVAE_ERR_LAUNCH; }
   return CVAE_OK;
 }

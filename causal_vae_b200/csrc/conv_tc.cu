@@ -63,7 +63,11 @@ igemm_tc_kernel(const __grid_constant__ GatherArgs a, const int BN, const int NS
   const int total = tiles_m * tiles_n * a.nphase;
   const uint32_t stage_bytes = kTcAStage + 256u * BN;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * BN) tmem_cols <<= 1;
+  // cross terms (lo*hi' + hi*lo') in their own accumulator columns [BN, 2BN) of each buffer, added to the main chain in
+  // the epilogue: the tensor core truncates on accumulate, so the 2^-11-scaled terms must not ride the long main chain
+  // (as in conv_halo_tc.cu / wgrad_tc.cu; the launcher keeps BN <= 128 so that 2 buffers x 2 BN columns fit)
+  const uint32_t accw = 2u * BN;
+  while (tmem_cols < 2u * accw) tmem_cols <<= 1;
   uint8_t* dsm_gen = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
   const uint32_t dsm = smem_u32(dsm_gen);
 
@@ -203,8 +207,9 @@ igemm_tc_kernel(const __grid_constant__ GatherArgs a, const int BN, const int NS
       it += 2;
     }
   } else if (warp == kTcProdWarps) {
-    // ============================== MMA issuer (one thread) ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer: converged warp, one elected lane issues (see conv_halo_tc.cu) ==============================
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
       uint32_t it = 0, tcount = 0;
       TcTile tl;
@@ -213,7 +218,7 @@ igemm_tc_kernel(const __grid_constant__ GatherArgs a, const int BN, const int NS
         const uint32_t acc = tcount & 1u;
         mbar_wait(smem_u32(&s_tempty[acc]), ((tcount >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem + acc * (uint32_t)BN;
+        const uint32_t d_tmem = tmem + acc * accw;
         uint32_t accumulate = 0;
         for (int kb = 0; kb < tl.T; ++kb, ++it) {
           const int slot = it % NS;
@@ -228,14 +233,14 @@ igemm_tc_kernel(const __grid_constant__ GatherArgs a, const int BN, const int NS
             const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 1024, kLayoutSw128);
             const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 1024, kLayoutSw128);
             const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 1024, kLayoutSw128);
-            mma_tf32(d_tmem, dal, dbh, idesc, accumulate);
-            mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-            mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            if (leader) mma_tf32(d_tmem + (uint32_t)BN, dal, dbh, idesc, accumulate);
+            if (leader) mma_tf32(d_tmem + (uint32_t)BN, dah, dbl, idesc, 1u);
+            if (leader) mma_tf32(d_tmem, dah, dbh, idesc, accumulate);
             accumulate = 1u;
           }
-          mma_commit(smem_u32(&s_empty[slot]));
+          if (leader) mma_commit(smem_u32(&s_empty[slot]));
         }
-        mma_commit(smem_u32(&s_tfull[acc]));
+        if (leader) mma_commit(smem_u32(&s_tfull[acc]));
         ++tcount;
       }
     }
@@ -276,14 +281,17 @@ igemm_tc_kernel(const __grid_constant__ GatherArgs a, const int BN, const int NS
       const uint32_t acc = tcount & 1u;
       mbar_wait(smem_u32(&s_tfull[acc]), (tcount >> 1) & 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem + acc * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t d_tmem = tmem + acc * accw + ((uint32_t)(q * 32) << 16);
       for (int ch = 0; ch < nchunks; ++ch) {
         const int cw = min(32, BN - ch * 32);
         {  // TMEM -> padded shared tile (thread = accumulator row)
           const int row = q * 32 + lane;
           for (int h = 0; h < cw; h += 16) {
-            float r16[16];
+            float r16[16], c16[16];
             tmem_ld16(d_tmem + (uint32_t)(ch * 32 + h), r16);
+            tmem_ld16(d_tmem + (uint32_t)(BN + ch * 32 + h), c16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r16[i] += c16[i];
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
               *reinterpret_cast<float4*>(ebuf + row * kEpiLd + h + i) = make_float4(r16[i], r16[i + 1], r16[i + 2], r16[i + 3]);
@@ -397,11 +405,33 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ src, float* __re
   }
 }
 
+// Rows of a plain [M][K] matrix -> the tensor-core A-operand image: per (128-row tile, 32-channel k-block) one 32 KB
+// block = tf32 hi plane then lo plane, each 128 rows x 128 bytes in the 128B swizzle -- exactly what a stage of the
+// halo kernel's A ring holds, so the kernel fetches it with two bulk copies and needs no producer warps.
+__global__ void __launch_bounds__(256) tc_pack_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long M,
+                                                           int K, int KB) {
+  const int mt = blockIdx.x / KB, kb = blockIdx.x - mt * KB;
+  uint8_t* tile = reinterpret_cast<uint8_t*>(dst) + ((size_t)mt * KB + kb) * 32768;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int item = threadIdx.x + i * 256, r = item >> 3, chunk = item & 7;
+    const long long row = (long long)mt * 128 + r;
+    const int c = kb * 32 + chunk * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < M && c < K) v = __ldg(reinterpret_cast<const float4*>(src + row * K + c));
+    float4 hi, lo;
+    tc::split4(v, hi, lo);
+    const uint32_t off = tc::sw128_off(r, chunk);
+    *reinterpret_cast<float4*>(tile + off) = hi;
+    *reinterpret_cast<float4*>(tile + 16384 + off) = lo;
+  }
+}
+
 int build_geom(const cvae_conv_params_t* p, GatherArgs& g);  // conv.cu
 int launch_conv_halo_tc(const GatherArgs& g, cudaStream_t st);   // conv_halo_tc.cu (conv-shaped layers, k > 1)
 
 static int tc_pick_bn(int Cd) {
-  for (int bn = 256; bn >= 16; bn >>= 1)
+  for (int bn = 128; bn >= 16; bn >>= 1)
     if (Cd % bn == 0) return bn;
   return 0;
 }
@@ -428,11 +458,26 @@ extern "C" int cvae_tc_pack_weight(const float* src, float* dst, int A, int A_pa
   return CVAE_OK;
 }
 
-extern "C" int cvae_conv_gather_tc(const cvae_conv_params_t* p, cvae_stream_t s) {
+extern "C" int64_t cvae_tc_pack_rows_floats(int64_t M, int K) {
+  return ((M + 127) / 128) * ((K + 31) / 32) * 8192;
+}
+
+extern "C" int cvae_tc_pack_rows(const float* src, float* dst, int64_t M, int K, cvae_stream_t s) {
+  if (!src || !dst || M < 1 || K < 4 || (K & 3)) return CVAE_ERR_BAD_ARG;
+  const int KB = (K + 31) / 32;
+  const long long blocks = ((M + 127) / 128) * KB;
+  if (blocks >= (1ll << 31)) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  tc_pack_rows_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(src, dst, M, K, KB);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+
+static int conv_gather_tc_impl(const cvae_conv_params_t* p, const float* a_image, cvae_stream_t s) {
   if (!p || !p->src || !p->wt || !p->dst || p->N <= 0) return CVAE_ERR_BAD_ARG;
   if (p->epi == CVAE_EPI_DACT && !p->epi_ref) return CVAE_ERR_BAD_ARG;
   if (p->Cs % 16 != 0 || p->Cd % 16 != 0) return CVAE_ERR_UNSUPPORTED_SHAPE;
   GatherArgs g;
+  g.a_image = a_image;
   g.src = p->src; g.wt = p->wt; g.bias = p->bias; g.dst = p->dst;
   g.in_scale = p->in.scale; g.in_shift = p->in.shift; g.in_center = p->in.center; g.in_slope = p->in.slope;
   g.in_affine = p->in.scale != nullptr; g.in_act = p->in.slope != 1.0f;
@@ -456,10 +501,11 @@ extern "C" int cvae_conv_gather_tc(const cvae_conv_params_t* p, cvae_stream_t s)
     // conv-shaped layers: the halo-tile kernel stages the input once for all taps (CVAE_HALO=0 forces
     // the per-tap gather kernel below, kept for 1x1 / Linear layers and shapes the halo plan rejects)
     static const bool halo_on = [] { const char* e = getenv("CVAE_HALO"); return !(e && e[0] == '0'); }();
-    if (halo_on) {
+    if (halo_on || a_image != nullptr) {
       const int hr = launch_conv_halo_tc(g, as_stream(s));
       if (hr <= 0) return hr;
     }
+    if (a_image != nullptr) return CVAE_ERR_UNSUPPORTED_SHAPE;     // the packed operand exists for the halo kernel only
   }
   const int BN = tc_pick_bn(p->Cd);
   if (BN == 0) return CVAE_ERR_UNSUPPORTED_SHAPE;
@@ -478,4 +524,15 @@ extern "C" int cvae_conv_gather_tc(const cvae_conv_params_t* p, cvae_stream_t s)
   igemm_tc_kernel<<<min(total, kNumSMs), kTcThreads, smem, as_stream(s)>>>(g, BN, NS, tiles_m, tiles_n);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
+}
+
+extern "C" int cvae_conv_gather_tc(const cvae_conv_params_t* p, cvae_stream_t s) { return conv_gather_tc_impl(p, nullptr, s); }
+
+// Linear layer (kh = kw = 1, identity input transform) whose A operand was packed by cvae_tc_pack_rows: p->src is the
+// plain matrix the image was made from (kept for the argument checks), a_image the packed copy the kernel reads.
+extern "C" int cvae_linear_tc_packed(const cvae_conv_params_t* p, const float* a_image, cvae_stream_t s) {
+  if (!p || !a_image) return CVAE_ERR_BAD_ARG;
+  if (p->kh != 1 || p->kw != 1 || p->stride != 1 || p->pad != 0 || p->in.scale != nullptr || p->in.slope != 1.0f)
+    return CVAE_ERR_UNSUPPORTED_SHAPE;
+  return conv_gather_tc_impl(p, a_image, s);
 }

@@ -21,10 +21,21 @@ constexpr int kLsKC = 64;        // K chunk per CTA
 constexpr int kLsMaxM = 128;
 
 template <int R>   // rows per warp; M <= 4 R
-__global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant__ GatherArgs a, const int M) {
+__global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant__ GatherArgs a, const int M, const int cpc) {
   __shared__ __align__(16) float xs[4 * R * kLsKC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = blockIdx.x * 32 + lane, k0 = blockIdx.y * kLsKC;
+  const int n = blockIdx.x * 32 + lane;
+  const bool nok = n < a.Cd;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  // `cpc` consecutive K chunks per CTA (launch_linear_small: as many as still leave ~4 CTAs per SM), so a wide layer
+  // (decoder_input, 512 -> 16384: 512 column blocks) runs without K split -- no pre-zeroing, no atomics: its 8.4 M
+  // fp32 atomics were ~30 us of a 105 us launch -- and the 16384 -> 512 input gradient meets in 43 instead of 256 adds
+  for (int kc = 0; kc < cpc; ++kc) {
+  const int k0 = (blockIdx.y * cpc + kc) * kLsKC;
+  if (k0 >= a.Cs) break;
+  if (kc > 0) __syncthreads();
   // ---- stage x[:, k0 : k0 + 64] with the producer's BatchNorm + activation applied ----
   // (unrolled: a CTA's whole life is a few dependent global round trips, so every loop keeps several loads in flight)
 #pragma unroll 8
@@ -46,13 +57,12 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant
     *reinterpret_cast<float4*>(xs + m * kLsKC + c4 * 4) = v;
   }
   __syncthreads();
-  float acc[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
-  const bool nok = n < a.Cd;
   const float* wp = a.wt + (size_t)k0 * a.Cd + (nok ? n : 0);
   const float* xr = xs + warp * R * kLsKC;
   const int kmax = min(kLsKC, a.Cs - k0);            // Cs % 4 == 0
+  float part[R];                                     // this chunk's sums: chains stay 64 long whatever cpc is
+#pragma unroll
+  for (int r = 0; r < R; ++r) part[r] = 0.f;
 #pragma unroll 4
   for (int kk = 0; kk < kmax; kk += 4) {
     float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
@@ -63,8 +73,11 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float4 xv = *reinterpret_cast<const float4*>(xr + r * kLsKC + kk);
-      acc[r] = fmaf(xv.x, w0, fmaf(xv.y, w1, fmaf(xv.z, w2, fmaf(xv.w, w3, acc[r]))));
+      part[r] = fmaf(xv.x, w0, fmaf(xv.y, w1, fmaf(xv.z, w2, fmaf(xv.w, w3, part[r]))));
     }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] += part[r];
   }
   if (!nok) return;
   const float b = (blockIdx.y == 0 && a.bias != nullptr) ? __ldg(a.bias + n) : 0.f;
@@ -121,12 +134,14 @@ int launch_linear_small(const GatherArgs& g, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(g.src) & 15) != 0) return 0;
   if (g.in_affine && (((reinterpret_cast<uintptr_t>(g.in_scale) | reinterpret_cast<uintptr_t>(g.in_shift)) & 15) != 0 ||
                       (g.in_center && (reinterpret_cast<uintptr_t>(g.in_center) & 15) != 0))) return 0;
-  const dim3 grid((g.Cd + 31) / 32, (g.Cs + kLsKC - 1) / kLsKC);
+  const int ncol = (g.Cd + 31) / 32, nk = (g.Cs + kLsKC - 1) / kLsKC;
+  const int cpc = max(1, min(nk, (ncol * nk) / (4 * kNumSMs)));
+  const dim3 grid(ncol, (nk + cpc - 1) / cpc);
   if (grid.y > 1 && cudaMemsetAsync(g.dst, 0, sizeof(float) * (size_t)M * g.Cd, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
-  if (M <= 16) linear_small_kernel<4><<<grid, 128, 0, st>>>(g, (int)M);
-  else if (M <= 32) linear_small_kernel<8><<<grid, 128, 0, st>>>(g, (int)M);
-  else if (M <= 64) linear_small_kernel<16><<<grid, 128, 0, st>>>(g, (int)M);
-  else linear_small_kernel<32><<<grid, 128, 0, st>>>(g, (int)M);
+  if (M <= 16) linear_small_kernel<4><<<grid, 128, 0, st>>>(g, (int)M, cpc);
+  else if (M <= 32) linear_small_kernel<8><<<grid, 128, 0, st>>>(g, (int)M, cpc);
+  else if (M <= 64) linear_small_kernel<16><<<grid, 128, 0, st>>>(g, (int)M, cpc);
+  else linear_small_kernel<32><<<grid, 128, 0, st>>>(g, (int)M, cpc);
   if (g.epi != CVAE_EPI_PLAIN) linear_small_epi_kernel<<<(g.Cd + 31) / 32, 128, 0, st>>>(g, (int)M);
   return 1;
 }
@@ -134,8 +149,9 @@ int launch_linear_small(const GatherArgs& g, cudaStream_t st) {
 // ---- weight gradient: P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb]),  m < M <= 128 ----------------------
 // CTA tile 32 (ca) x 64 (cb); thread = 2 ca x 4 cb.
 __global__ void __launch_bounds__(256) wgrad_small_kernel(const __grid_constant__ WgradArgs a, const int M) {
-  __shared__ __align__(16) float As[kLsMaxM * 32];
-  __shared__ __align__(16) float Bs[kLsMaxM * 64];
+  extern __shared__ __align__(16) float ws_sm[];      // M x (32 + 64) floats: sized by the launch, so M = 64 leaves 9 CTAs per SM
+  float* As = ws_sm;
+  float* Bs = ws_sm + M * 32;
   const int tid = threadIdx.x;
   const int ca0 = blockIdx.x * 32, cb0 = blockIdx.y * 64;
 #pragma unroll 8
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const __grid_constant_
 // 1: launched, 0: not covered.  Requires splits == 1 (the caller's partial buffer is [rows][Cb]).
 int launch_wgrad_small(const WgradArgs& a, int taps, int splits, cudaStream_t st) {
   if (taps != 1 || splits != 1 || a.K > kLsMaxM || a.K < 1) return 0;
-  wgrad_small_kernel<<<dim3((a.Ca + 31) / 32, (a.Cb + 63) / 64), 256, 0, st>>>(a, a.K);
+  wgrad_small_kernel<<<dim3((a.Ca + 31) / 32, (a.Cb + 63) / 64), 256, (size_t)a.K * 96 * sizeof(float), st>>>(a, a.K);
   return 1;
 }
 

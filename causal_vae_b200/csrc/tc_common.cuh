@@ -25,23 +25,42 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~the hint elapses,
+// instead of spinning through the issue slots the working warps need (ncu on the halo kernel: the spin loop was 14 %
+// of all executed warp instructions).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails loudly) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps after ~4 s of wall clock (the launch fails loudly) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins >= 256u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+      spins = 0;
+    }
   }
+}
+
+// one lane of the (fully converged) warp: the predicate for uniform-datapath instructions (tcgen05.mma / commit, bulk
+// copies) issued from warp-uniform code
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- proxies / fences ------------------------------------------------------------------------
@@ -55,6 +74,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// L2 prefetch of `bytes` starting at a 128-byte aligned global address, one line per request, through the LSU: the bulk
+// form (cp.async.bulk.prefetch.L2) shares the TMA queue with the weight loads and delayed them (measured: the MMA
+// issuer's wait for weights went 33 -> 163 kclk on the stem.3 input gradient)
+__device__ __forceinline__ void prefetch_l2_lines(const void* src, uint32_t bytes) {
+  const char* p = reinterpret_cast<const char*>(src);
+  for (uint32_t o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o) : "memory");
 }
 
 // ---- TMEM ------------------------------------------------------------------------------------

@@ -324,8 +324,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_full[slot]));
     }
-  } else if (lane == 0) {
-    // ============================== MMA issuer ==============================
+  } else {
+    // ============================== MMA issuer: converged warp, one elected lane issues (see conv_halo_tc.cu) ==============================
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc_tf32(128, BN, 0, 1);   // A: TMEM (K along columns); B: MN-major shared
     const uint32_t blk_stride = kWgKPix * 128;               // bytes between 32-channel blocks of B
     uint32_t acc_m = 0, acc_c = 0;
@@ -341,14 +342,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         // offset = stride between 4-pixel swizzle atoms; one MMA consumes 8 pixel rows (1024 B)
         const uint64_t dbh = make_smem_desc(b_hi + k * 1024, blk_stride, 512, kLayoutSw128Base32);
         const uint64_t dbl = make_smem_desc(b_lo + k * 1024, blk_stride, 512, kLayoutSw128Base32);
-        mma_tf32_ts(t_cross, a_lo + k * 8, dbh, idesc, acc_c);
-        mma_tf32_ts(t_cross, a_hi + k * 8, dbl, idesc, 1u);
-        mma_tf32_ts(t_main, a_hi + k * 8, dbh, idesc, acc_m);
+        if (leader) mma_tf32_ts(t_cross, a_lo + k * 8, dbh, idesc, acc_c);
+        if (leader) mma_tf32_ts(t_cross, a_hi + k * 8, dbl, idesc, 1u);
+        if (leader) mma_tf32_ts(t_main, a_hi + k * 8, dbh, idesc, acc_m);
         acc_m = 1u; acc_c = 1u;
       }
-      mma_commit(smem_u32(&s_empty[slot]));
+      if (leader) mma_commit(smem_u32(&s_empty[slot]));
     }
-    mma_commit(smem_u32(&s_accum));
+    if (leader) mma_commit(smem_u32(&s_accum));
   }
 
   tc_fence_before();

@@ -84,6 +84,13 @@ def tc_eligible(Cs, Cd, M):
     return _TC and M >= _TC_MIN_ROWS and bool(L.lib.cvae_tc_eligible(int(Cs), int(Cd), int(M)))
 
 
+# Linear layers without an input transform: A operand pre-packed by cvae_tc_pack_rows and streamed by bulk copies (no
+# producer warps).  Off by default: measured on the vessel step it neither gains nor loses (8.65 vs 8.66 ms) -- those
+# launches are bound by the MMA's shared-memory operand traffic, not by staging; CVAE_APRE=1 enables it, the parity test
+# tests/test_tc_gpu.py::test_linear_packed_operand always exercises it.
+_APRE = os.environ.get("CVAE_APRE", "0") == "1"
+FORCE_APRE = [False]
+_APRE_MIN_ROWS = int(os.environ.get("CVAE_APRE_MIN_ROWS", "1024"))
 _FEW = os.environ.get("CVAE_FEW", "1") != "0"   # fp32 tile kernels for image-sized 16 -> 16 stride-2 layers
 
 
@@ -178,6 +185,15 @@ def conv_gather(src, wt, bias, out_hw_c, k, stride, pad, mode, in_x=IDENT, epi=L
     dst = out if out is not None else empty(N, Hd, Wd, Cd, like=src)
     p = L.ConvParams(L.ptr(src), L.ptr(wt), L.ptr(bias), L.ptr(dst), in_x.c(), epi, L.ptr(epi_ref),
                      L.ptr(epi_add), epi_x.c(), L.ptr(stats), N, Hs, Ws, Cs, Hd, Wd, Cd, k, k, stride, pad, mode)
+    M = N * Hs * Ws
+    if tc and (_APRE or FORCE_APRE[0]) and k == 1 and stride == 1 and pad == 0 and in_x.identity and (Hd, Wd) == (Hs, Ws) and M % 8 == 0 \
+            and M >= _APRE_MIN_ROWS and (epi == L.EPI_PLAIN or Cd <= 256) and mode == L.MODE_GATHER:
+        # Linear layer on a plain matrix: split + swizzle the rows once (one small launch), then both GEMM operands are
+        # streamed by bulk copies and no warp stages the A operand (csrc/conv_halo_tc.cu, a_pre mode)
+        img = empty(int(L.lib.cvae_tc_pack_rows_floats(M, Cs)), like=src)
+        L.check(L.lib.cvae_tc_pack_rows(L.ptr(src), L.ptr(img), M, Cs, L.stream()), "tc_pack_rows")
+        L.check(L.lib.cvae_linear_tc_packed(p, L.ptr(img), L.stream()), f"linear_tc_packed M={M} K={Cs} N={Cd}")
+        return dst
     fn = L.lib.cvae_conv_gather_tc if tc else L.lib.cvae_conv_gather
     L.check(fn(p, L.stream()), f"conv_gather tc={int(tc)} N={N} {Hs}x{Ws}x{Cs}->{Hd}x{Wd}x{Cd} k{k}s{stride} mode{mode}")
     return dst

@@ -157,6 +157,14 @@ int64_t cvae_tc_pack_floats(int A_pad, int B, int taps);  /* size of the packed 
 int cvae_tc_pack_weight(const float* src, float* dst, int A, int A_pad, int B, int taps, int src_bat,
                         int src_ld, cvae_stream_t s);     /* arguments as cvae_pack_weight */
 int cvae_conv_gather_tc(const cvae_conv_params_t* p, cvae_stream_t s);
+/* Linear layers whose input needs no transform (the ViT blocks' Linears, nn.MultiheadAttention's projections and their
+ * input gradients; vit_backbone.py:13-41): cvae_tc_pack_rows splits the [M][K] matrix into tf32 hi / lo planes in the
+ * tensor core's swizzled shared-memory tile order (cvae_tc_pack_rows_floats floats), and cvae_linear_tc_packed runs the
+ * GEMM with BOTH operands streamed by bulk copies -- no thread touches the A operand.  p as for cvae_conv_gather_tc with
+ * kh = kw = 1 and an identity input transform; p->src is the matrix the image was packed from. */
+int64_t cvae_tc_pack_rows_floats(int64_t M, int K);
+int cvae_tc_pack_rows(const float* src, float* dst, int64_t M, int K, cvae_stream_t s);
+int cvae_linear_tc_packed(const cvae_conv_params_t* p, const float* a_image, cvae_stream_t s);
 /* Tensor-core weight gradient: same contract, parameter block and partial layout as cvae_conv_wgrad
  * (followed by cvae_wgrad_reduce), for Cb % 16 == 0.  The gathered operand is staged straight into
  * tensor memory (lane = (tap, ca) row, columns = pixels); the split count must come from

