@@ -125,6 +125,192 @@ __global__ void __launch_bounds__(128) linear_small_epi_kernel(const __grid_cons
   }
 }
 
+// ---- wide layers with a handful of rows: decoder_input (Linear 512 -> 16384 at M = batch, vit_backbone.py:186-188), its
+// input gradient (K = 16384) and weight gradient (512 x 16384 outputs) ----------------------------------------------
+// The 32-column / 64-deep CTAs above make 4096 CTAs with 8.4 M fp32 atomics out of such a layer (105 / 110 / 102 us for
+// 0.5 GFMA and 33.5 MB of weights).  Here a CTA owns a 64 x 128 output tile, a thread a 4 x 8 register block, and the
+// reduction dimension streams through shared memory in chunks of 16 (weights by cp.async, double-buffered):
+// 32 FMA per 3 shared-memory loads.  Split K (grid.y) only where the output has too few tiles to fill the GPU.
+constexpr int kLrK = 16;
+
+__device__ __forceinline__ void lr_fma_chunk(const float (*xs)[68], const float (*ws)[128], int ty, int tx, float (&acc)[4][8]) {
+#pragma unroll
+  for (int kk = 0; kk < kLrK; ++kk) {
+    const float4 x4 = *reinterpret_cast<const float4*>(&xs[kk][4 * ty]);
+    const float4 w0 = *reinterpret_cast<const float4*>(&ws[kk][4 * tx]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&ws[kk][64 + 4 * tx]);
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+  }
+}
+
+// rows [r0, r0 + 16) x columns [n0, n0 + 128) of a row-major [R][ld] matrix -> ws[16][128] (16-byte cp.async, zero fill)
+__device__ __forceinline__ void lr_load_w(float (*ws)[128], const float* __restrict__ src, int r0, int R, int n0, int ld, int tid) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int idx = tid + u * 256, kk = idx >> 5, c4 = (idx & 31) << 2;
+    float* d = &ws[kk][c4];
+    if (r0 + kk < R && n0 + c4 < ld) {
+      const uint32_t da = static_cast<uint32_t>(__cvta_generic_to_shared(d));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + (size_t)(r0 + kk) * ld + n0 + c4) : "memory");
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// y[m][n] (+)= sum_k xf(x[m][k]) * w[k][n];  grid (Cd / 128, K splits, row blocks of 64)
+__global__ void __launch_bounds__(256) linear_rows_kernel(const __grid_constant__ GatherArgs a, const int M, const int kper) {
+  __shared__ __align__(16) float xs[2][kLrK][68];
+  __shared__ __align__(16) float ws[2][kLrK][128];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int n0 = blockIdx.x * 128, m0 = blockIdx.z * 64;
+  const int kbeg = blockIdx.y * kper, kend = min(a.Cs, kbeg + kper);
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int xm = tid >> 2, xk = (tid & 3) << 2;           // this thread's x vector of a chunk: row xm, k offset xk
+  auto load_x = [&](int k0) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k = k0 + xk;
+    if (m0 + xm < M && k < kend) {
+      v = __ldg(reinterpret_cast<const float4*>(a.src + (size_t)(m0 + xm) * a.Cs + k));
+      if (a.in_affine) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + k));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + k));
+        float4 ce = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + k));
+        v.x = fmaf(v.x - ce.x, sc.x, sh.x); v.y = fmaf(v.y - ce.y, sc.y, sh.y);
+        v.z = fmaf(v.z - ce.z, sc.z, sh.z); v.w = fmaf(v.w - ce.w, sc.w, sh.w);
+      }
+      if (a.in_act) { v.x = lrelu(v.x, a.in_slope); v.y = lrelu(v.y, a.in_slope); v.z = lrelu(v.z, a.in_slope); v.w = lrelu(v.w, a.in_slope); }
+    }
+    return v;
+  };
+  auto store_x = [&](int b, const float4 v) { xs[b][xk][xm] = v.x; xs[b][xk + 1][xm] = v.y; xs[b][xk + 2][xm] = v.z; xs[b][xk + 3][xm] = v.w; };
+  const int nch = (kend - kbeg + kLrK - 1) / kLrK;
+  if (nch > 0) {
+    store_x(0, load_x(kbeg));
+    lr_load_w(ws[0], a.wt, kbeg, kend, n0, a.Cd, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int c = 0; c < nch; ++c) {
+    const int b = c & 1;
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + 1 < nch) {
+      xn = load_x(kbeg + (c + 1) * kLrK);
+      lr_load_w(ws[b ^ 1], a.wt, kbeg + (c + 1) * kLrK, kend, n0, a.Cd, tid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    lr_fma_chunk(xs[b], ws[b], ty, tx, acc);
+    if (c + 1 < nch) store_x(b ^ 1, xn);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + 4 * ty + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + 64 * h + 4 * tx;
+      if (n >= a.Cd) continue;
+      float4 o = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+      if (blockIdx.y == 0 && a.bias != nullptr) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+      }
+      float* d = a.dst + (size_t)m * a.Cd + n;
+      if (gridDim.y == 1) *reinterpret_cast<float4*>(d) = o;
+      else { atomicAdd(d, o.x); atomicAdd(d + 1, o.y); atomicAdd(d + 2, o.z); atomicAdd(d + 3, o.w); }
+    }
+  }
+}
+
+// 1: launched, 0: not covered
+int launch_linear_rows(const GatherArgs& g, int M, cudaStream_t st) {
+  if (M > 128 || (g.Cs & 3) || (g.Cd & 3) || (long long)g.Cs * g.Cd < (1ll << 21)) return 0;
+  if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.wt) | reinterpret_cast<uintptr_t>(g.dst)) & 15) != 0) return 0;
+  if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15) != 0) return 0;
+  if (g.in_affine && (((reinterpret_cast<uintptr_t>(g.in_scale) | reinterpret_cast<uintptr_t>(g.in_shift)) & 15) != 0 ||
+                      (g.in_center && (reinterpret_cast<uintptr_t>(g.in_center) & 15) != 0))) return 0;
+  const int tiles = ((g.Cd + 127) / 128) * ((M + 63) / 64);
+  int splits = max(1, min((g.Cs + 255) / 256, (2 * kNumSMs) / max(tiles, 1)));    // >= 256 deep per CTA, ~2 CTAs per SM
+  if (4 * tiles >= 3 * kNumSMs) splits = 1;                                      // enough tiles: plain stores, no atomics
+  int kper = (g.Cs + splits - 1) / splits;
+  kper = ((kper + kLrK - 1) / kLrK) * kLrK;
+  splits = (g.Cs + kper - 1) / kper;
+  if (splits > 1 && cudaMemsetAsync(g.dst, 0, sizeof(float) * (size_t)M * g.Cd, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
+  linear_rows_kernel<<<dim3((g.Cd + 127) / 128, splits, (M + 63) / 64), 256, 0, st>>>(g, M, kper);
+  if (g.epi != CVAE_EPI_PLAIN) linear_small_epi_kernel<<<(g.Cd + 31) / 32, 128, 0, st>>>(g, M);
+  return 1;
+}
+
+// weight gradient of such a layer: P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb]), m < M <= 128: the same 64 x 128 tile with
+// the batch as the streamed dimension (both operands are read row-wise as they lie: no transposition)
+__global__ void __launch_bounds__(256) wgrad_rows_kernel(const __grid_constant__ WgradArgs a, const int M) {
+  __shared__ __align__(16) float as[2][kLrK][68];
+  __shared__ __align__(16) float bs[2][kLrK][128];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int ca0 = blockIdx.y * 64, cb0 = blockIdx.x * 128;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  auto load_a = [&](int b, int m0) {        // 16 rows x 64 channels of ga (transform applied): one float4 per thread
+    const int kk = tid >> 4, c = ca0 + ((tid & 15) << 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + kk < M && c < a.Ca) {
+      v = __ldg(reinterpret_cast<const float4*>(a.ga + (size_t)(m0 + kk) * a.Ca + c));
+      if (a.a_affine) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.a_scale + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.a_shift + c));
+        float4 ce = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.a_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.a_center + c));
+        v.x = fmaf(v.x - ce.x, sc.x, sh.x); v.y = fmaf(v.y - ce.y, sc.y, sh.y);
+        v.z = fmaf(v.z - ce.z, sc.z, sh.z); v.w = fmaf(v.w - ce.w, sc.w, sh.w);
+      }
+      if (a.a_act) { v.x = lrelu(v.x, a.a_slope); v.y = lrelu(v.y, a.a_slope); v.z = lrelu(v.z, a.a_slope); v.w = lrelu(v.w, a.a_slope); }
+    }
+    *reinterpret_cast<float4*>(&as[b][kk][(tid & 15) << 2]) = v;
+  };
+  const int nch = (M + kLrK - 1) / kLrK;
+  load_a(0, 0);
+  lr_load_w(bs[0], a.db, 0, M, cb0, a.Cb, tid);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int c = 0; c < nch; ++c) {
+    const int b = c & 1;
+    if (c + 1 < nch) {
+      load_a(b ^ 1, (c + 1) * kLrK);
+      lr_load_w(bs[b ^ 1], a.db, (c + 1) * kLrK, M, cb0, a.Cb, tid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    lr_fma_chunk(as[b], bs[b], ty, tx, acc);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ca = ca0 + 4 * ty + i;
+    if (ca >= a.Ca) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cb = cb0 + 64 * h + 4 * tx;
+      if (cb < a.Cb)
+        *reinterpret_cast<float4*>(a.partial + (size_t)ca * a.Cb + cb) = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+    }
+  }
+}
+
 // 1: launched, 0: not covered
 int launch_linear_small(const GatherArgs& g, cudaStream_t st) {
   if (g.wtaps != 1 || g.nphase != 1 || g.is != 1 || g.os != 1 || g.Hs != g.Hd || g.Ws != g.Wd) return 0;
@@ -134,8 +320,9 @@ int launch_linear_small(const GatherArgs& g, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(g.src) & 15) != 0) return 0;
   if (g.in_affine && (((reinterpret_cast<uintptr_t>(g.in_scale) | reinterpret_cast<uintptr_t>(g.in_shift)) & 15) != 0 ||
                       (g.in_center && (reinterpret_cast<uintptr_t>(g.in_center) & 15) != 0))) return 0;
+  if (launch_linear_rows(g, (int)M, st)) return 1;      // wide layers (decoder_input): register-blocked tile kernel below
   const int ncol = (g.Cd + 31) / 32, nk = (g.Cs + kLsKC - 1) / kLsKC;
-  const int cpc = max(1, min(nk, (ncol * nk) / (4 * kNumSMs)));
+  const int cpc = 1;     // K chunks per CTA: > 1 measured slower (a CTA's life is latency; serial chunks add to it)
   const dim3 grid(ncol, (nk + cpc - 1) / cpc);
   if (grid.y > 1 && cudaMemsetAsync(g.dst, 0, sizeof(float) * (size_t)M * g.Cd, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
   if (M <= 16) linear_small_kernel<4><<<grid, 128, 0, st>>>(g, (int)M, cpc);
@@ -203,6 +390,11 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const __grid_constant_
 // 1: launched, 0: not covered.  Requires splits == 1 (the caller's partial buffer is [rows][Cb]).
 int launch_wgrad_small(const WgradArgs& a, int taps, int splits, cudaStream_t st) {
   if (taps != 1 || splits != 1 || a.K > kLsMaxM || a.K < 1) return 0;
+  if ((long long)a.Ca * a.Cb >= (1ll << 21) && (a.Ca & 3) == 0 && (a.Cb & 3) == 0 && !a.b_affine && !a.b_act &&
+      ((reinterpret_cast<uintptr_t>(a.ga) | reinterpret_cast<uintptr_t>(a.db) | reinterpret_cast<uintptr_t>(a.partial)) & 15) == 0) {
+    wgrad_rows_kernel<<<dim3((a.Cb + 127) / 128, (a.Ca + 63) / 64), 256, 0, st>>>(a, a.K);
+    return 1;
+  }
   wgrad_small_kernel<<<dim3((a.Ca + 31) / 32, (a.Cb + 63) / 64), 256, (size_t)a.K * 96 * sizeof(float), st>>>(a, a.K);
   return 1;
 }

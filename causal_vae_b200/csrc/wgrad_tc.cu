@@ -210,14 +210,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll
         for (int p = 0; p < kH; ++p) {
           if (a.a_affine) b0[p] = fmaf(b0[p] - ce, sc, sh);
-          if (a.a_act) b0[p] = lrelu(b0[p], a.a_slope);
+          if (a.a_act) b0[p] = fmaxf(b0[p], b0[p] * a.a_slope);      // slope in [0, 1] (launcher)
         }
       } else if (m0 != 0u) {
 #pragma unroll
         for (int p = 0; p < kH; ++p) {
           if ((m0 >> p) & 1u) {                  // padding stays exactly 0
             if (a.a_affine) b0[p] = fmaf(b0[p] - ce, sc, sh);
-            if (a.a_act) b0[p] = lrelu(b0[p], a.a_slope);
+            if (a.a_act) b0[p] = fmaxf(b0[p], b0[p] * a.a_slope);
           }
         }
       }
@@ -271,11 +271,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int bt = tid - 256;                    // 0..127
     const int chunk = bt & 7, prow = bt >> 3;    // 16-byte chunk of a 128-byte row; pixel rows prow, prow + 16
     const int nblk = (BN + 31) >> 5;
-    for (int st = 0; st < nst; ++st) {
-      const int slot = st % kWgStages;
+    // nblk * 2 float4 per thread and stage (BN = 128 -> 8).  The loads of stage st + 1 are issued before stage st is
+    // transformed and stored: with one stage of loads in flight the four B warps paid a full DRAM round trip per stage
+    // and were the critical path of the kernel (ncu, profiles/r2_ncu_wgrad_tc_raw.txt: the first use of the loaded vectors
+    // carried the stall samples; 3.2 kclk per 32-pixel stage against 0.8 kclk of MMA time).
+    auto load_stage = [&](int st, float4 (&v)[8]) {
       const int kb = kbeg + st * kWgKPix;
-      float4 v[8];
-      // nblk * 2 float4 per thread (BN = 128 -> 8)
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
 #pragma unroll
@@ -286,6 +287,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             v[b * 2 + i] = __ldg(reinterpret_cast<const float4*>(a.db + (size_t)pix * a.Cb + col));
         }
       }
+    };
+    float4 v[8], vn[8];
+    if (nst > 0) load_stage(0, v);
+    for (int st = 0; st < nst; ++st) {
+      const int slot = st % kWgStages;
+      const int kb = kbeg + st * kWgKPix;
+      if (st + 1 < nst) load_stage(st + 1, vn);
       mbar_wait(smem_u32(&s_empty[slot]), (uint32_t)(((st / kWgStages) & 1) ^ 1));
       uint8_t* sB = dsm_gen + (size_t)slot * stage_bytes;
 #pragma unroll
@@ -309,8 +317,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
               x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
             }
             if (a.b_act) {
-              x.x = lrelu(x.x, a.b_slope); x.y = lrelu(x.y, a.b_slope);
-              x.z = lrelu(x.z, a.b_slope); x.w = lrelu(x.w, a.b_slope);
+              x.x = fmaxf(x.x, x.x * a.b_slope); x.y = fmaxf(x.y, x.y * a.b_slope);      // slope in [0, 1] (launcher)
+              x.z = fmaxf(x.z, x.z * a.b_slope); x.w = fmaxf(x.w, x.w * a.b_slope);
             }
           }
           float4 hi, lo;
@@ -323,6 +331,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_full[slot]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = vn[i];
     }
   } else {
     // ============================== MMA issuer: converged warp, one elected lane issues (see conv_halo_tc.cu) ==============================
@@ -402,6 +412,9 @@ extern "C" int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s)
     return CVAE_ERR_BAD_ARG;
   const int BN = wg_pick_bn(p->Cb);
   if (BN == 0) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  if ((p->xa.slope != 1.0f && !(p->xa.slope >= 0.f && p->xa.slope <= 1.f)) ||
+      (p->xb.slope != 1.0f && !(p->xb.slope >= 0.f && p->xb.slope <= 1.f)))
+    return CVAE_ERR_UNSUPPORTED_SHAPE;          // the producers evaluate the leaky ReLU as max(v, slope * v)
   WgradArgs a;
   a.ga = p->ga; a.db = p->db;
   a.a_scale = p->xa.scale; a.a_shift = p->xa.shift; a.a_center = p->xa.center; a.a_slope = p->xa.slope;

@@ -148,6 +148,17 @@ def test_tc_linear_module(shape):
     run_pair(nn.Linear(K, N), sd, lambda P, xx: O._lin({"l.weight": P["weight"], "l.bias": P["bias"]}, "l", xx), x)
 
 
+@pytest.mark.parametrize("shape", [(64, 512, 16384), (64, 16384, 512), (16, 2048, 1024), (128, 1024, 2048), (37, 516, 4100)])
+def test_wide_linear_with_few_rows(shape):
+    """decoder_input-sized Linear layers at M = batch rows (vit_backbone.py:186-188): the register-blocked 64 x 128 tile
+    kernels of csrc/linear_small.cu (forward, split-K input gradient, weight gradient) against the fp64 oracle."""
+    from causal_vae_b200 import nn
+    B, K, N = shape
+    sd = O.fill_state_dict({"weight": (N, K), "bias": (N,)}, seed=5)
+    x = gen(B, K, seed=6)
+    run_pair(nn.Linear(K, N), sd, lambda P, xx: O._lin({"l.weight": P["weight"], "l.bias": P["bias"]}, "l", xx), x)
+
+
 @pytest.mark.parametrize("shape", [(2048, 256, 768), (1304, 512, 256), (4160, 256, 256)])
 def test_linear_packed_operand(shape):
     """Linear layers through cvae_tc_pack_rows + cvae_linear_tc_packed (A operand pre-split and pre-swizzled, both
