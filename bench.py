@@ -25,12 +25,14 @@ H = W = 256
 B_PER_GPU = 64
 FLOP_PER_SAMPLE = 5.057e9          # fwd+bwd matmul/conv FLOPs (2*MAC), measured on the reference
 BYTES_PER_SAMPLE = 77e6 + 8.8e6    # irreducible fp32 activation + parameter/optimizer traffic
-# dram__bytes_read.sum + dram__bytes_write.sum of the probed launch (stem.3 input gradient, B = 64) from the
-# `ncu --set full` capture summarised in profiles/r1_ncu_halo_stem3_raw.txt (launch 1: 201.6 MB read + 98.5 MB
-# written); algorithmic bytes of that launch: 335.5e6 (part of the re-read reference tensor is served by L2)
-NCU_TRAFFIC_BYTES = 300.1e6
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_halo_stem3_raw.txt launch 1 (dram__bytes_read.sum + dram__bytes_write.sum)"
-
+# dram__bytes_read.sum + dram__bytes_write.sum of the probed launch (stem.3 input gradient, B = 64) from the ncu launch
+# list of the whole step, profiles/r2_step_traffic.csv (launch id 381: 201.7 MB read + 95.8 MB written); algorithmic bytes
+# of that launch: 335.5e6 (part of the re-read reference tensor is served by L2)
+NCU_TRAFFIC_BYTES = 297.5e6
+NCU_TRAFFIC_SOURCE = "profiles/r2_step_traffic.csv id 381 (dram__bytes_read.sum + dram__bytes_write.sum, conv_halo_tc_kernel<6>)"
+# whole-step DRAM traffic of the same capture (389 launches, one eager step at B = 64): 7.711 GB read + 1.362 GB written
+STEP_TRAFFIC_BYTES = 9.073e9
+STEP_TRAFFIC_SOURCE = "profiles/r2_step_traffic_summary.txt (sum over the 389 launches of one step; cold-cache, serialised)"
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -521,7 +523,9 @@ def run_native(args):
     dist = world > 1
     if dist:
         import torch.distributed as td
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line (no "NCCL version" banner)
+        # stdout carries ONE JSON line: NCCL prints its version banner there from level VERSION up (WARN included), so the
+        # level is left unset unless the caller set one, and whatever it logs goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
     from causal_vae_b200 import _lib as L
     from causal_vae_b200 import ops
@@ -657,18 +661,18 @@ def run_native(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
                      "traffic": NCU_TRAFFIC_BYTES,
-                     "kernel": "conv_halo_tc_kernel (tcgen05 3xTF32, halo-tile staging) on its longest launch of the step: "
+                     "kernel": "conv_halo_tc_kernel<6> (tcgen05 3xTF32, halo-tile staging) on its longest launch of the step: "
                                "stem.3 Conv2d(32->64, s2) input gradient, 64^2 -> 128^2, B=64",
                      "bytes_per_launch": probe["hbm_bytes"], "ms_per_launch": probe["hbm_ms"],
                      "peak_source": f"{how} copy bandwidth (burst: kernel timed alone)",
                      "traffic_source": NCU_TRAFFIC_SOURCE},
         "roofline_stream": {"bound": "hbm", "achieved": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9, "peak": hbm,
                             "unit": "GB/s", "frac": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9 / hbm,
-                            "traffic": 286.5e6,
+                            "traffic": 281.9e6,
                             "kernel": "convt16_up_kernel (fp32 SIMT tile kernel, csrc/conv_few.cu) on decoder.12 forward, "
                                       "ConvTranspose2d(16->16) 128^2 -> 256^2, B=64: the largest tensors of the step",
                             "bytes_per_launch": probe["few_bytes"], "ms_per_launch": probe["few_ms"],
-                            "traffic_source": "profiles/r1_ncu_few_raw.txt launch 0"},
+                            "traffic_source": "profiles/r2_step_traffic.csv (convt16_up_kernel: 67.3 MB read + 214.6 MB written)"},
         "roofline_tensor": {"bound": "tensor", "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s",
                             "frac": ach_tf / bf16_burst, "tf32_gemm_peak_tflops": tf32_peak,
                             "frac_of_tf32_gemm_peak": (ach_tf / tf32_peak) if tf32_peak else None,
@@ -681,7 +685,10 @@ def run_native(args):
         "step_roofline": {"bound": "hbm", "bytes_per_sample": bytes_per_sample, "peak_gbs": hbm,
                           "roofline_samples_per_s_per_gpu": hbm * 1e9 / bytes_per_sample,
                           "frac": (value / world) / (hbm * 1e9 / bytes_per_sample),
-                          "achieved_tflops": value / world * FLOP_PER_SAMPLE / 1e12},
+                          "achieved_tflops": value / world * FLOP_PER_SAMPLE / 1e12,
+                          "traffic_per_step": STEP_TRAFFIC_BYTES, "algorithmic_bytes_per_step": bytes_per_sample * B,
+                          "traffic_over_algorithmic": STEP_TRAFFIC_BYTES / (BYTES_PER_SAMPLE * B_PER_GPU),
+                          "traffic_source": STEP_TRAFFIC_SOURCE},
         "counterfactual": {"metric": "counterfactuals/sec (do(M_k += 5) over all 12 concepts, decode 256x256, "
                                      "per-image L2 effect reduced on device)",
                            "value": cf_rate * world, "unit": "images/s", "n_gpus": world,

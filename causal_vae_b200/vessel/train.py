@@ -50,11 +50,15 @@ class VesselTrainer:
         self.pack_plan = ops.PackPlan()
         self.side = torch.cuda.Stream() if overlap_wgrad else None
         self._early_done, self._seg, self.comm = False, None, None
+        self._mid, self._mid_done = None, False
         if distributed and os.environ.get("CVAE_DP_OVERLAP", "1") != "0":
             self._seg = self._decoder_segment()
             if self._seg is not None:
                 self.comm = torch.cuda.Stream()
                 model._decoder_grad_hook = self._early_allreduce
+                self._mid = self._transformer_start()
+                if self._mid is not None and hasattr(model, "backbone"):
+                    model.backbone._tokens_grad_hook = self._mid_allreduce
         rank = 0
         if distributed:
             import torch.distributed as dist
@@ -114,6 +118,42 @@ class VesselTrainer:
         hi = self.flat.offsets[idx[-1] + 1] if idx[-1] + 1 < len(self.flat.params) else self.flat.numel
         return lo, hi
 
+    def _transformer_start(self):
+        """offset of the first transformer parameter when [transformer .. fc_var] directly precedes the decoder segment"""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        lo = self._seg[0]
+        start = None
+        for i, p in enumerate(self.flat.params):
+            n = names[id(p)]
+            if self.flat.offsets[i] >= lo:
+                break
+            inside = n.startswith(("backbone.transformer.", "backbone.to_latent.", "backbone.fc_mu.", "backbone.fc_var."))
+            if inside and start is None:
+                start = self.flat.offsets[i]
+            if not inside and start is not None:
+                return None                      # something else sits between the transformer and the decoder
+        return start
+
+    def _mid_allreduce(self, _grad):
+        """Second bucket: fires when the transformer's backward has been enqueued (gradient of the token sequence), i.e.
+        before the stem's.  Transformer / to_latent gradients and everything behind the decoder segment (adapters,
+        morphology head: complete long before) are reduced while the stem backward runs; only the stem + embeddings
+        (4 MB) remain for after the join."""
+        import torch.distributed as dist
+        if not self._early_done:
+            return None
+        cur = torch.cuda.current_stream()
+        self.comm.wait_stream(cur)
+        if self.side is not None:
+            self.comm.wait_stream(self.side)
+        lo, hi = self._seg
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.flat.grad[self._mid:lo], op=dist.ReduceOp.SUM, group=self.pg)
+            if hi < self.flat.numel:
+                dist.all_reduce(self.flat.grad[hi:], op=dist.ReduceOp.SUM, group=self.pg)
+        self._mid_done = True
+        return None
+
     def _early_allreduce(self, _grad):
         import torch.distributed as dist
         cur = torch.cuda.current_stream()
@@ -132,12 +172,14 @@ class VesselTrainer:
         if self._early_done:
             import torch.distributed as dist
             lo, hi = self._seg
+            if self._mid_done:
+                lo, hi = self._mid, self.flat.numel          # only the stem + embeddings are left
             if lo > 0:
                 dist.all_reduce(self.flat.grad[:lo], op=dist.ReduceOp.SUM, group=self.pg)
             if hi < self.flat.numel:
                 dist.all_reduce(self.flat.grad[hi:], op=dist.ReduceOp.SUM, group=self.pg)
             torch.cuda.current_stream().wait_stream(self.comm)
-            self._early_done = False
+            self._early_done = self._mid_done = False
         else:
             allreduce_gradients(self.flat.grad, group=self.pg)
 

@@ -79,7 +79,11 @@ class ViTVAE(tnn.Module):
         return self.dropout(tok)
 
     def encode_cls(self, x):
-        tok = self.transformer(self.tokens(x))
+        tok = self.tokens(x)
+        hook = getattr(self, "_tokens_grad_hook", None)
+        if hook is not None and tok.requires_grad:
+            tok.register_hook(hook)        # fires when the transformer's backward has been enqueued (data-parallel bucket)
+        tok = self.transformer(tok)
         return self.to_latent(tok[:, 0])
 
     def encode(self, x):

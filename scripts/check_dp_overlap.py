@@ -1,5 +1,5 @@
 """torchrun --nproc-per-node 2 scripts/check_dp_overlap.py: the flat gradient after one data-parallel step with the
-overlapped (decoder-first) all-reduce equals the single-collective result, and both equal the sum of the two ranks'
+overlapped (decoder-first, then transformer, then stem) all-reduce equals the single-collective result, and both equal the sum of the two ranks'
 local gradients."""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,6 +26,7 @@ for mode in ("local", "single", "overlap"):
     torch.cuda.synchronize()
     res[mode] = tr.flat.grad.clone()
     assert (mode == "overlap") == (tr.comm is not None), (mode, tr.comm)
+    assert (mode == "overlap") == (tr._mid is not None), (mode, tr._mid)      # second bucket (transformer) armed
 summed = res["local"].clone()
 dist.all_reduce(summed)
 mx = summed.abs().max().item()
