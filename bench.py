@@ -266,15 +266,17 @@ def input_pipeline_probe(torch, hbm):
 
 
 CF_SOURCES = 65536      # BASELINE configs[4]: 65536 source samples, do() on every one of the 12 concepts
+CF_CHUNK = int(os.environ.get("CVAE_CF_CHUNK", "64"))   # sources per graph replay (measured: 16 / 32 / 64 / 128 -> 63 / 69 / 75 / 74 k images/s)
 
 
-def counterfactual_rate(torch, model, sources, chunk=32):
+def counterfactual_rate(torch, model, sources, chunk=None):
     """BASELINE configs[4]: do(M_k += 5) on every concept k of every source, decode, reduce each image to
     ||x_cf - x_base||_2 on device (vessel_analysis/04_generate_counterfactual/generate_counterfactual.py:83-99,
     analyze_vessel.py:101-115).  `sources` = this rank's shard of the 65536-source job (sources shard across ranks
     with no collective), streamed in chunks; inputs resident in HBM, eval mode."""
     from causal_vae_b200 import counterfactual as CF
     from causal_vae_b200.vessel import models
+    chunk = CF_CHUNK if chunk is None else chunk
     model.eval()
     K, Z = models.CONFIG["M_DIM"], models.CONFIG["Z_DIM"]
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -287,7 +289,7 @@ def counterfactual_rate(torch, model, sources, chunk=32):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        acc = eng.sweep_all(m, z).sum()                  # one graph replay per chunk of 32 sources
+        acc = eng.sweep_all(m, z).sum()                  # one graph replay per chunk of sources
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -598,7 +600,7 @@ def run_native(args):
     h2d = sum(a.numel() * a.element_size() for a in pin)
 
     # ---- counterfactual generation: the full 65536-source job, sources sharded over the ranks, no collective ----
-    cf_sources = max(32, (args.cf_sources // world) // 32 * 32)
+    cf_sources = max(CF_CHUNK, (args.cf_sources // world) // CF_CHUNK * CF_CHUNK)
     barrier()
     cf_rate, cf_ms, _ = counterfactual_rate(torch, model, cf_sources)
     barrier()
@@ -693,7 +695,7 @@ def run_native(args):
                                      "per-image L2 effect reduced on device)",
                            "value": cf_rate * world, "unit": "images/s", "n_gpus": world,
                            "sample": f"{cf_sources * world} sources x 12 concepts = {cf_sources * world * 12} decoded images "
-                                     f"({cf_sources} sources per GPU in chunks of 32; BASELINE configs[4] is 65536 sources; "
+                                     f"({cf_sources} sources per GPU in chunks of {CF_CHUNK}; BASELINE configs[4] is 65536 sources; "
                                      "sources shard across GPUs with no collective)",
                            "ms": cf_ms,
                            "roofline": {"bound": "hbm", "bytes_per_image": 16.5e6, "peak": hbm, "unit": "GB/s",

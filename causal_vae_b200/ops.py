@@ -81,7 +81,10 @@ _TC_MIN_ROWS = int(os.environ.get("CVAE_TC_MIN_ROWS", "1024"))   # below this a 
 
 
 def tc_eligible(Cs, Cd, M):
-    return _TC and M >= _TC_MIN_ROWS and bool(L.lib.cvae_tc_eligible(int(Cs), int(Cd), int(M)))
+    # few rows but a very wide output still make a full grid of tiles: decoder_input (512 -> 16384) at the 416 rows of a
+    # counterfactual chunk ran 211 us on the fp32 gather kernel
+    enough = M >= _TC_MIN_ROWS or (M >= 128 and M % 8 == 0 and M * Cd >= (1 << 21))
+    return _TC and enough and bool(L.lib.cvae_tc_eligible(int(Cs), int(Cd), int(M)))
 
 
 # Linear layers without an input transform: A operand pre-packed by cvae_tc_pack_rows and streamed by bulk copies (no
