@@ -129,6 +129,8 @@ _SIGS = {
     "cvae_debug_read": [vp, i32],
     "cvae_do_expand": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
     "cvae_rowdiff_l2": [vp, vp, vp, i64, i64, i32, vp],
+    "cvae_pair_expand": [vp, vp, vp, i32, i32, i32, f32, vp],
+    "cvae_ensemble_mean_std": [vp, i32, vp, vp, i64, vp],
     "cvae_sumsq": [vp, i64, vp, vp],
     "cvae_clip_adam": [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp, vp],
     "cvae_upsample2x_fwd": [vp, vp, i32, i32, i32, i32, vp],

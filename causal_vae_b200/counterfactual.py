@@ -92,6 +92,56 @@ def mediation_decomposition(model, m_a, z_a, m_b, z_b):
             "feature_pct": 100.0 * d[:, 3:] / total.unsqueeze(1)}
 
 
+def ensemble_mean_std(preds, with_std=True):
+    """torch.stack(preds).mean(0), .std(0) of up to 8 same-shaped CUDA tensors in one pass
+    (ensemble_reconstruction.py:80-86)."""
+    import ctypes as C
+    preds = [p.contiguous() for p in preds]
+    mean = torch.empty_like(preds[0])
+    std = torch.empty_like(preds[0]) if with_std else None
+    arr = (C.c_void_p * len(preds))(*[p.data_ptr() for p in preds])
+    L.check(L.lib.cvae_ensemble_mean_std(C.cast(arr, C.c_void_p), len(preds), L.ptr(mean), L.ptr(std), mean.numel(),
+                                         L.stream()), "ensemble_mean_std")
+    return mean, std
+
+
+@torch.no_grad()
+def ensemble_reconstruction(models, x, m, t):
+    """Mean and unbiased std of the eval-mode reconstructions of the fold models
+    (vessel_analysis/04_generate_counterfactual/ensemble_reconstruction.py:58-89).  Returns (mean, std), [B,1,H,W]."""
+    recons = []
+    for model in models:
+        model.eval()
+        recons.append(model(x, m, t)[0])
+    return ensemble_mean_std(recons)
+
+
+@torch.no_grad()
+def z_permutation_grid(models, x, m, t, scale=1.0):
+    """The M x Z cross-product of vessel_analysis/03_evaluate_vessel/check_mechanism_z_perm.py:100-131: row i takes the
+    measured concepts M of sample i, column j the style code z_j = mu(x_j, m_j, t_j) * scale of sample j; every cell is
+    decoded by every fold model and the cells are averaged over the models.  All N*N rows of a model go through ONE
+    decode.  Returns [N, N, 1, H, W] (cell (i, i) at scale 1 is the reconstruction of sample i)."""
+    N, K = m.shape
+    cells = []
+    for model in models:
+        model.eval()
+        if hasattr(model, "encode"):
+            mu = model.encode(x, m, t, torch.zeros(N, model.my_z_dim, device=x.device))[0]    # z = mu, no decode needed
+        else:
+            mu = model(x, m, t)[2]                                                             # the reference's own call
+        Z = mu.shape[1]
+        rows = ops.empty(N * N, K + Z, like=m)
+        L.check(L.lib.cvae_pair_expand(L.ptr(m.contiguous()), L.ptr(mu.contiguous()), L.ptr(rows), N, K, Z, float(scale),
+                                       L.stream()), "pair_expand")
+        if hasattr(model, "dec_adapter"):                      # the ViT / CNN switch of check_mechanism_z_perm.py:119-124
+            cells.append(model.backbone.decode(model.dec_adapter(rows)))
+        else:
+            cells.append(model.dec_conv(model.dec_fc(rows).view(-1, 512, *model.GRID)))
+    mean = cells[0] if len(cells) == 1 else ensemble_mean_std(cells, with_std=False)[0]
+    return mean.view(N, N, *mean.shape[1:])
+
+
 class CounterfactualEngine:
     """High-throughput form of counterfactual_sweep for a frozen model: the whole sweep of one chunk of
     sources (base decode, do() scatter, decode of chunk*K rows, per-image L2) is captured once in a CUDA

@@ -333,6 +333,40 @@ __global__ void rowdiff_l2_kernel(const float* __restrict__ a, const float* __re
   if (threadIdx.x == 0) out[row] = (float)sqrt(t);
 }
 
+// torch.stack(preds).mean(0) and .std(0) (unbiased) over the reconstructions of up to 8 fold models
+// (vessel_analysis/04_generate_counterfactual/ensemble_reconstruction.py:80-86; check_mechanism_z_perm.py:129): one pass,
+// two-pass-in-registers variance (mean first, then squared deviations) so that nearly equal folds do not cancel.
+struct EnsemblePtrs { const float* p[8]; };
+__global__ void ensemble_mean_std_kernel(const __grid_constant__ EnsemblePtrs e, int n_models, float* __restrict__ mean,
+                                         float* __restrict__ stdv, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = k < n_models ? __ldg(e.p[k] + i) : 0.f; s += v[k]; }
+    const float mu = s / (float)n_models;
+    mean[i] = mu;
+    if (stdv != nullptr) {
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[k] - mu; q = k < n_models ? fmaf(d, d, q) : q; }
+      stdv[i] = n_models > 1 ? sqrtf(q / (float)(n_models - 1)) : nanf("");
+    }
+  }
+}
+
+// rows (i*N + j) = cat(m[i], scale * z[j]): every M source against every Z source (check_mechanism_z_perm.py:100-118)
+__global__ void pair_expand_kernel(const float* __restrict__ m, const float* __restrict__ z, float* __restrict__ out, int N,
+                                   int K, int Z, float scale) {
+  const int64_t total = (int64_t)N * N * (K + Z);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % (K + Z));
+    const int64_t r = idx / (K + Z);
+    const int i = (int)(r / N), j = (int)(r % N);
+    out[idx] = c < K ? m[(int64_t)i * K + c] : z[(int64_t)j * Z + (c - K)] * scale;
+  }
+}
+
 // nn.Upsample(scale_factor=2, mode='nearest') on NHWC (vessel_analysis/00_core/models.py:123-145, the CNN decoder):
 // y[n, 2h+a, 2w+b, :] = x[n, h, w, :]; backward sums each 2x2 block.  V = 4 (C % 4 == 0) or 1.
 template <int V>
@@ -569,6 +603,27 @@ extern "C" int cvae_do_expand(const float* m, const float* z, float* out, int S,
                               float v, cvae_stream_t s) {
   if (!m || !z || !out || S <= 0 || K <= 0 || Z <= 0) return CVAE_ERR_BAD_ARG;
   do_expand_kernel<<<ew_blocks((int64_t)S * K * (K + Z)), 256, 0, ST>>>(m, z, out, S, K, Z, set_value, v);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+
+extern "C" int cvae_ensemble_mean_std(const float* const* preds, int n_models, float* mean, float* stdv, int64_t n,
+                                      cvae_stream_t s) {
+  if (!preds || !mean || n_models < 1 || n_models > 8 || n <= 0) return CVAE_ERR_BAD_ARG;
+  EnsemblePtrs e;
+  for (int k = 0; k < 8; ++k) e.p[k] = k < n_models ? preds[k] : nullptr;
+  for (int k = 0; k < n_models; ++k) if (!e.p[k]) return CVAE_ERR_BAD_ARG;
+  const int blocks = (int)min((n + 255) / 256, (int64_t)kNumSMs * 16);
+  ensemble_mean_std_kernel<<<blocks, 256, 0, ST>>>(e, n_models, mean, stdv, n);
+  CVAE_LAUNCH_CHECK();
+  return CVAE_OK;
+}
+
+extern "C" int cvae_pair_expand(const float* m, const float* z, float* out, int N, int K, int Z, float scale, cvae_stream_t s) {
+  if (!m || !z || !out || N <= 0 || K <= 0 || Z <= 0) return CVAE_ERR_BAD_ARG;
+  const int64_t total = (int64_t)N * N * (K + Z);
+  const int blocks = (int)min((total + 255) / 256, (int64_t)kNumSMs * 16);
+  pair_expand_kernel<<<blocks, 256, 0, ST>>>(m, z, out, N, K, Z, scale);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }

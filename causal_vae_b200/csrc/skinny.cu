@@ -458,7 +458,10 @@ static bool launch_wgrad_c1(const WgradArgs& a, int taps, cudaStream_t st) {
   const int C = CB1 ? a.Ca : a.Cb;
   if ((C & 3) || C > 64 || C < 4 || kThreads % (C / 4)) return false;
   if (cudaMemsetAsync(a.partial, 0, sizeof(float) * (size_t)taps * C, st) != cudaSuccess) return false;
-  const int grid = stream_grid(a.K, C / 4);
+  // every block ends with taps x C same-address atomics: 1184 blocks made 1184 serialised adds per output (the two 4x4
+  // layers of the cascade model: 217 us each); two blocks per SM keep the loads in flight with a quarter of the atomics
+  static const int bps = [] { const char* e = getenv("CVAE_WGC1_BPS"); return e ? atoi(e) : 2; }();
+  const int grid = min(stream_grid(a.K, C / 4), kNumSMs * bps);
   if (taps == 9) wgrad_c1_kernel<9, CB1><<<grid, kThreads, 0, st>>>(a);
   else if (taps == 16) wgrad_c1_kernel<16, CB1><<<grid, kThreads, 0, st>>>(a);
   else return false;

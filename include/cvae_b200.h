@@ -363,6 +363,11 @@ int cvae_uniform_kl_bwd(const float* logits, int64_t rows, int T, const float* g
  * rows [m' | z] for S sources x K concepts: row (s*K + k) = cat(do_k(m[s]), z[s]). */
 int cvae_do_expand(const float* m, const float* z, float* out, int S, int K, int Z, int set_value,
                    float v, cvae_stream_t s);
+/* rows (i*N + j) = cat(m[i], scale * z[j]): the M x Z cross-product grid of check_mechanism_z_perm.py:100-118 */
+int cvae_pair_expand(const float* m, const float* z, float* out, int N, int K, int Z, float scale, cvae_stream_t s);
+/* elementwise mean and unbiased std over the reconstructions of n_models <= 8 fold models (`preds`: HOST array of device
+ * pointers; torch.stack(..).mean(0) / .std(0), ensemble_reconstruction.py:80-86); stdv may be NULL */
+int cvae_ensemble_mean_std(const float* const* preds, int n_models, float* mean, float* stdv, int64_t n, cvae_stream_t s);
 /* per-row L2 norm of (a - b[row / group]) (analyze_vessel.py:115) */
 int cvae_rowdiff_l2(const float* a, const float* b, float* out, int64_t rows, int64_t rowlen,
                     int group, cvae_stream_t s);

@@ -123,6 +123,49 @@ def test_feature_importance_and_mediation_sweeps():
         assert rel(out["feature_pct"][:, k], 100 * nrm(dec(mk, z_a), base) / (total + 1e-9)) <= 1e-4, k
 
 
+def test_ensemble_and_z_permutation_grid():
+    """f1 remainder: the 5-fold ensemble reconstruction (ensemble_reconstruction.py:58-89: mean and unbiased std of the
+    folds' eval reconstructions) and the M x Z cross-product grid (check_mechanism_z_perm.py:100-131: M of sample i with
+    z = mu * scale of sample j, averaged over the folds) against the oracle, three "folds" = three weight seeds."""
+    from causal_vae_b200 import counterfactual as CF
+    from causal_vae_b200.vessel import models as VM
+    H, W, N = 64, 64, 4
+    VM.CONFIG["IMG_HEIGHT"], VM.CONFIG["IMG_WIDTH"] = H, W
+    x, m, t, eps = O.vessel_inputs(N, H, W, seed=2)
+    folds, sds = [], []
+    for seed in (0, 1, 2):
+        sd = O.fill_state_dict(O.vessel_shapes(H, W), seed=seed)
+        mod = VM.CausalViTVAE()
+        mod.load_state_dict(sd)
+        folds.append(mod.cuda().eval())
+        sds.append(sd)
+    # ensemble_reconstruction draws its own eps inside model(x, m, t): compare through the deterministic pieces instead --
+    # mean / std kernel on the oracle's reconstructions, and the grid (z = mu needs no eps)
+    zero = torch.zeros(N, VM.CONFIG["Z_DIM"])
+    recs = [O.vessel_forward(sd, x, m, t, zero, train=False)[0] for sd in sds]
+    mean, std = CF.ensemble_mean_std([r.cuda() for r in recs])
+    ref = torch.stack(recs).double()
+    assert rel(mean, ref.mean(dim=0)) <= 1e-6 and rel(std, ref.std(dim=0)) <= 1e-5
+    one, none = CF.ensemble_mean_std([recs[0].cuda()], with_std=False)
+    assert none is None and torch.equal(one.cpu(), recs[0])
+    got_mean, got_std = CF.ensemble_reconstruction(folds, x.cuda(), m.cuda(), t.cuda())
+    assert got_mean.shape == (N, 1, H, W) and got_std.shape == (N, 1, H, W) and torch.isfinite(got_std).all()
+    for scale in (1.0, 0.5):
+        grid = CF.z_permutation_grid(folds, x.cuda(), m.cuda(), t.cuda(), scale=scale)
+        assert grid.shape == (N, N, 1, H, W)
+        want = 0
+        for sd in sds:
+            mu = O.vessel_forward(sd, x, m, t, zero, train=False)[2]
+            mi = m.repeat_interleave(N, dim=0)                      # row i*N + j: M of sample i ...
+            zj = (mu * scale).repeat(N, 1)                          # ... with the scaled style code of sample j
+            want = want + O.vessel_decode(sd, mi, zj, (H // 32, W // 32), False).double()
+        want = (want / len(sds)).view(N, N, 1, H, W)
+        assert rel(grid, want) <= 2e-5, (scale, rel(grid, want))
+    # the diagonal at scale 1 is each sample's own (z = mu) reconstruction, averaged over the folds
+    diag = torch.stack([CF.z_permutation_grid(folds, x.cuda(), m.cuda(), t.cuda())[i, i] for i in range(N)])
+    assert rel(diag, torch.stack(recs).double().mean(dim=0)) <= 2e-5
+
+
 @pytest.mark.parametrize("cfg", [(64, 64, 4), (128, 96, 8), (256, 256, 8), (256, 256, 64)])
 def test_eval_forward_and_counterfactual(cfg):
     from causal_vae_b200 import counterfactual as CF
