@@ -72,6 +72,7 @@ _SIGS = {
     "cvae_wgrad_tc_eligible": [i32, i32, i32],
     "cvae_wgrad_tc_splits": [i32, i32, i32],
     "cvae_conv_wgrad_tc": [C.POINTER(WgradParams), vp],
+    "cvae_conv_wgrad_tc_direct": [C.POINTER(WgradParams), vp, i32, vp],
     "cvae_wgrad_tile_splits": [i32, i32, i32, i32, i32, i32],
     "cvae_conv_wgrad_tile": [C.POINTER(WgradParams), vp],
     "cvae_bn_finalize": [vp, i32, f64, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp],

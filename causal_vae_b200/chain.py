@@ -256,10 +256,10 @@ def _unit_bwd(u, rec, dz, stats, prev_entry, prev_stats, need_dx, add, grads, gr
         if bias_direct and side is not None:
             ops.col_sum(dy, Cd, out=u.mod.bias.grad)
         if u.kind == "convT":
-            ops.conv_wgrad(dy, S_in.t, IDENT, S_in.x, u.k, u.stride, u.pad, gw)
+            ops.conv_wgrad(dy, S_in.t, IDENT, S_in.x, u.k, u.stride, u.pad, gw, zeroed=w_direct)
         else:
             ca_real = w.shape[1] if u.kind == "linear" else None
-            ops.conv_wgrad(S_in.t, dy, S_in.x, IDENT, u.k, u.stride, u.pad, gw, ca_real=ca_real)
+            ops.conv_wgrad(S_in.t, dy, S_in.x, IDENT, u.k, u.stride, u.pad, gw, ca_real=ca_real, zeroed=w_direct)
     if side is not None:
         side.wait_stream(torch.cuda.current_stream())     # dy (and the statistics it depends on) are complete
         with torch.cuda.stream(side):

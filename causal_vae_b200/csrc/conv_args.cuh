@@ -27,6 +27,9 @@ struct WgradArgs {
   int N, Ha, Wa, Ca, Hq, Wq, Cb;
   int kw, stride, pad, rows, kchunk, K;
   int seg;   // wgrad_tc A-loader variant: 32 / 16 / 8 = whole output-row segments per stage, -1 = Linear, 0 = general
+  // wgrad_tc direct mode (cvae_conv_wgrad_tc_direct): split-K tiles meet in the PRE-ZEROED torch-layout gradient
+  // direct[cb][ca < ca_real][tap] through fp32 reductions (red.global.add) - no partial buffer, no reduce launch
+  float* direct = nullptr; int ca_real = 0; int taps = 0;
 };
 
 // skinny.cu: 1-channel layers as pure HBM streams.  Each returns false when the shape is not covered.

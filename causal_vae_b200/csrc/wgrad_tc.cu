@@ -255,14 +255,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         float mn[16], cr[16];
         tmem_ld16(t_main + lane_sel + (uint32_t)c, mn);
         tmem_ld16(t_cross + lane_sel + (uint32_t)c, cr);
-        if (row_ok) {
+        if (a.direct != nullptr) {
+          // direct mode: the K splits of this tile meet in the zeroed gradient (torch layout [cb][ca][tap]).  Lanes are
+          // consecutive input channels: stride taps * 4 B (Linear: one 128-byte line per warp and column)
+          if (row_ok && ca < a.ca_real) {
+            const size_t cstride = (size_t)a.ca_real * a.taps;
+            float* dst = a.direct + (size_t)(n0 + c) * cstride + (size_t)ca * a.taps + tap;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)i * cstride, mn[i] + cr[i]);
+          }
+        } else if (row_ok) {
           float* dst = a.partial + ((size_t)blockIdx.z * a.rows + row) * a.Cb + n0 + c;
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             *reinterpret_cast<float4*>(dst + i) = make_float4(mn[i] + cr[i], mn[i + 1] + cr[i + 1], mn[i + 2] + cr[i + 2], mn[i + 3] + cr[i + 3]);
         }
       }
-    } else if (row_ok && par == 0) {
+    } else if (row_ok && par == 0 && a.direct == nullptr) {
       float* dst = a.partial + ((size_t)blockIdx.z * a.rows + row) * a.Cb + n0;
       for (int c = 0; c < BN; ++c) dst[c] = 0.f;
     }
@@ -406,8 +415,9 @@ extern "C" int cvae_wgrad_tc_splits(int pixels, int rows, int Cb) {
   return best;
 }
 
-extern "C" int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s) {
-  if (!p || !p->ga || !p->db || !p->partial || p->splits < 1) return CVAE_ERR_BAD_ARG;
+static int wgrad_tc_launch(const cvae_wgrad_params_t* p, float* direct, int ca_real, cvae_stream_t s) {
+  if (!p || !p->ga || !p->db || (!p->partial && !direct) || p->splits < 1) return CVAE_ERR_BAD_ARG;
+  if (direct && (ca_real < 1 || ca_real > p->Ca)) return CVAE_ERR_BAD_ARG;
   if ((p->Ha + 2 * p->pad - p->kh) / p->stride + 1 != p->Hq || (p->Wa + 2 * p->pad - p->kw) / p->stride + 1 != p->Wq)
     return CVAE_ERR_BAD_ARG;
   const int BN = wg_pick_bn(p->Cb);
@@ -426,6 +436,7 @@ extern "C" int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s)
   a.kw = p->kw; a.stride = p->stride; a.pad = p->pad;
   a.rows = p->kh * p->kw * p->Ca;
   a.K = p->N * p->Hq * p->Wq;
+  a.direct = direct; a.ca_real = ca_real; a.taps = p->kh * p->kw;
   int chunk = (a.K + p->splits - 1) / p->splits;
   chunk = ((chunk + kWgKPix - 1) / kWgKPix) * kWgKPix;
   a.kchunk = chunk;
@@ -446,4 +457,11 @@ extern "C" int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s)
   wgrad_tc_kernel<<<grid, kWgThreads, smem, as_stream(s)>>>(a, BN);
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
+}
+
+extern "C" int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s) { return wgrad_tc_launch(p, nullptr, 0, s); }
+
+extern "C" int cvae_conv_wgrad_tc_direct(const cvae_wgrad_params_t* p, float* grad, int ca_real, cvae_stream_t s) {
+  if (!grad) return CVAE_ERR_BAD_ARG;
+  return wgrad_tc_launch(p, grad, ca_real, s);
 }

@@ -202,8 +202,13 @@ def conv_gather(src, wt, bias, out_hw_c, k, stride, pad, mode, in_x=IDENT, epi=L
     return dst
 
 
-def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulate=False, tc=None):
-    """grad_out (torch layout [Cb][Ca_real][k*k]) = sum_pix xa(ga[gather]) (x) xb(db)."""
+_WG_DIRECT = os.environ.get("CVAE_WG_DIRECT", "1") != "0"
+
+
+def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulate=False, tc=None, zeroed=False):
+    """grad_out (torch layout [Cb][Ca_real][k*k]) = sum_pix xa(ga[gather]) (x) xb(db).
+    zeroed: grad_out is known to hold zeros (the trainers' flat gradient buffer after zero_grad) - the tensor-core
+    kernel then adds its split-K tiles straight into it (no partial buffer, no reduce launch)."""
     N, Ha, Wa, Ca = ga.shape
     _, Hq, Wq, Cb = db.shape
     taps = k * k
@@ -217,6 +222,11 @@ def conv_wgrad(ga, db, xa, xb, k, stride, pad, grad_out, ca_real=None, accumulat
     else:
         splits = (L.lib.cvae_wgrad_tc_splits if tc else L.lib.cvae_wgrad_splits)(pixels, rows, Cb)
         fn = L.lib.cvae_conv_wgrad_tc if tc else L.lib.cvae_conv_wgrad
+    if tc is True and (zeroed or accumulate) and _WG_DIRECT and grad_out.is_contiguous():
+        p = L.WgradParams(L.ptr(ga), L.ptr(db), xa.c(), xb.c(), None, splits, N, Ha, Wa, Ca, Hq, Wq, Cb, k, k, stride, pad)
+        L.check(L.lib.cvae_conv_wgrad_tc_direct(p, L.ptr(grad_out), Ca if ca_real is None else ca_real, L.stream()),
+                f"conv_wgrad_tc_direct {Ha}x{Wa}x{Ca} / {Hq}x{Wq}x{Cb} k{k}s{stride}")
+        return grad_out
     partial = empty(splits, rows, Cb, like=ga)
     p = L.WgradParams(L.ptr(ga), L.ptr(db), xa.c(), xb.c(), L.ptr(partial), splits, N, Ha, Wa, Ca, Hq, Wq, Cb,
                       k, k, stride, pad)

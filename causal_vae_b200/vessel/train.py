@@ -224,11 +224,18 @@ class VesselTrainer:
         import gc
         gc.collect()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        if os.environ.get("CVAE_GRAPH_DOT"):             # diagnosis: cudaGraphDebugDotPrint of the captured step
+            self.graph.enable_debug_mode()
+        # CVAE_MAIN_PRIO=1 (experiment): capture on a high-priority stream, so that kernel nodes of the main chain
+        # (input gradients, BatchNorm backward: the critical path) are dispatched before pending side-stream CTAs
+        cap = torch.cuda.Stream(priority=-1) if os.environ.get("CVAE_MAIN_PRIO", "0") == "1" else None
+        with torch.cuda.graph(self.graph, stream=cap):
             self.static_losses = self._fwd_bwd(**self.static)
             self._allreduce()
             self.opt.step()
         # the capture pass itself does not execute; nothing to undo
+        if os.environ.get("CVAE_GRAPH_DOT"):
+            self.graph.debug_dump(os.environ["CVAE_GRAPH_DOT"])
         return self
 
     def load_batch(self, x, m, t, eps=None):

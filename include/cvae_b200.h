@@ -172,6 +172,11 @@ int cvae_linear_tc_packed(const cvae_conv_params_t* p, const float* a_image, cva
 int cvae_wgrad_tc_eligible(int pixels, int rows, int Cb);
 int cvae_wgrad_tc_splits(int pixels, int rows, int Cb);
 int cvae_conv_wgrad_tc(const cvae_wgrad_params_t* p, cvae_stream_t s);
+/* The same kernel without the partial buffer and without cvae_wgrad_reduce: every K split adds its tile into `grad`
+ * (torch layout [Cb][ca_real][kh*kw], rows ca >= ca_real of a padded operand are dropped) with fp32 reductions, so
+ * `grad` must hold zeros (or the value to accumulate onto) when the launch starts -- the state the trainers' flat
+ * gradient buffer is in after zero_grad() (train.py:78 optimizer.zero_grad() in the reference).  p->partial is unused. */
+int cvae_conv_wgrad_tc_direct(const cvae_wgrad_params_t* p, float* grad, int ca_real, cvae_stream_t s);
 
 /* Shared-memory tiled fp32 weight gradient for 3x3 (pad 1, stride 1 | 2) layers with few channels and
  * many pixels (Ca in {1,16,32}, Cb in {1,16,32,64}: vit_backbone.py:74-78 stem.0/stem.3, :136-156

@@ -393,8 +393,16 @@ def test_head_backward_fused_vs_separate_kernels_and_fp64():
 def test_batched_weight_packing_equals_per_use_packing():
     """ops.PackPlan: the one-launch re-pack reproduces every per-use layout bit for bit after the weights change."""
     from causal_vae_b200 import ops
-    ws = [gen(64, 32, 9, seed=70).cuda(), gen(48, 16, 1, seed=71).cuda(), gen(16, 16, 9, seed=72).cuda()]
-    args = [(32, 32, 64, 9, True, 32, True), (48, 48, 16, 1, False, 16, True), (16, 16, 16, 9, False, 16, False)]
+    ws = [gen(64, 32, 9, seed=70).cuda(), gen(48, 16, 1, seed=71).cuda(), gen(16, 16, 9, seed=72).cuda(),
+          gen(768, 256, 1, seed=73).cuda(), gen(128, 140, 1, seed=74).cuda(), gen(256, 64, 1, seed=75).cuda(),
+          gen(64, 128, 9, seed=76).cuda(), gen(192, 96, 1, seed=77).cuda()]
+    # (A, A_pad, B, taps, src_bat, src_ld, tc)
+    args = [(32, 32, 64, 9, True, 32, True), (48, 48, 16, 1, False, 16, True), (16, 16, 16, 9, False, 16, False),
+            (256, 256, 768, 1, True, 256, True),     # ViT Linear [out][in]: 128-bit source reads
+            (140, 144, 128, 1, True, 140, True),     # ragged K (adapter): scalar tail, rows of 140 floats are not 16-byte aligned
+            (64, 64, 256, 1, True, 64, False),       # fp32 transposition tiles (decoder_input layout)
+            (64, 64, 128, 9, False, 128, True),      # transposed-conv weight [Cin][Cout][tap] on the tensor-core image
+            (90, 96, 192, 1, True, 96, False)]       # fp32 transposition with zero-padded rows (A < A_pad)
     plan = ops.PackPlan()
     ops.set_pack_plan(plan)
     try:

@@ -267,6 +267,22 @@ def test_tc_wgrad_vs_simt_and_fp64(case):
     print(f"wgrad {case}: simt err {e0:.2e}  tc err {e1:.2e}")
     assert e0 <= 1e-5
     assert e1 <= 1e-5, f"tensor-core wgrad off by {e1:.3e} (SIMT {e0:.3e})"
+    # direct mode (cvae_conv_wgrad_tc_direct): split-K tiles reduced straight into the zeroed torch-layout gradient
+    gz = torch.zeros(Cb, Ca, k * k, device="cuda")
+    ops.conv_wgrad(ga, db, xa, xb, k, stride, pad, gz, tc=True, zeroed=True)
+    base = gen(Cb, Ca, k * k, seed=9).cuda()
+    gacc = base.clone()
+    ops.conv_wgrad(ga, db, xa, xb, k, stride, pad, gacc, tc=True, accumulate=True)
+    torch.cuda.synchronize()
+    e2, e3 = rel(gz, want), rel(gacc - base, want)
+    print(f"   direct err {e2:.2e}, accumulate-onto err {e3:.2e}")
+    assert e2 <= 1e-5 and e3 <= 1e-5
+    if Ca % 8 == 0:                               # Linear with a padded operand: rows ca >= ca_real are dropped
+        real = Ca - 3
+        gp = torch.zeros(Cb, real, k * k, device="cuda")
+        ops.conv_wgrad(ga, db, xa, xb, k, stride, pad, gp, ca_real=real, tc=True, zeroed=True)
+        torch.cuda.synchronize()
+        assert rel(gp, want[:, :real]) <= 1e-5
 
 
 TILE_WGRAD_CASES = [
