@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcvae_b200.so")
-SOURCES = ["conv.cu", "conv_tc.cu", "conv_halo_tc.cu", "wgrad_tc.cu", "wgrad_tile.cu", "skinny.cu", "conv_few.cu", "pack_batch.cu", "linear_small.cu", "head_bwd.cu", "norm.cu", "attention.cu", "elementwise.cu", "loss_optim.cu", "classify.cu", "input_pipeline.cu", "attention_long.cu"]
+SOURCES = ["conv.cu", "conv_tc.cu", "conv_halo_tc.cu", "wgrad_tc.cu", "wgrad_tile.cu", "skinny.cu", "conv_few.cu", "pack_batch.cu", "linear_small.cu", "head_bwd.cu", "norm.cu", "attention.cu", "elementwise.cu", "loss_optim.cu", "classify.cu", "input_pipeline.cu", "attention_long.cu", "graph_prio.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

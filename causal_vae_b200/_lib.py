@@ -140,6 +140,10 @@ _SIGS = {
     "cvae_aa_weights": [i32, i32, vp, vp, vp, vp],
     "cvae_vessel_preprocess": [C.POINTER(PreprocParams), vp],
     "cvae_scaler_transform": [vp, vp, vp, vp, i64, i32, vp],
+    "cvae_graph_set_priorities": [vp, i32, i32, vp],
+    "cvae_graph_instantiate_prio": [vp, vp],
+    "cvae_graph_launch": [vp, vp],
+    "cvae_graph_exec_destroy": [vp],
 }
 EXPORTS = tuple(_SIGS)
 
@@ -176,3 +180,35 @@ def stream():
 
 def xform(scale=None, shift=None, slope=1.0, center=None):
     return Xform(ptr(scale), ptr(shift), ptr(center), float(slope))
+
+
+class PriorityGraphExec:
+    """Executable form of a captured torch.cuda.CUDAGraph (keep_graph=True) whose kernel nodes carry launch priorities:
+    the weight-gradient family yields SMs to the main chain (csrc/graph_prio.cu).  launch() replays on the current stream."""
+
+    def __init__(self, graph, prio_main=-1, prio_side=0):
+        self.graph = graph                        # keeps the cudaGraph_t and its memory pool alive
+        counts = (C.c_int * 3)()
+        raw = graph.raw_cuda_graph()
+        rc = lib.cvae_graph_set_priorities(raw, prio_main, prio_side, C.cast(counts, C.c_void_p))
+        if rc != 0:
+            raise RuntimeError(f"libcvae_b200: graph_set_priorities failed: {_ERR.get(rc, rc)}")
+        self.kernel_nodes, self.side_nodes, self.unnamed = counts[0], counts[1], counts[2]
+        ex = C.c_void_p()
+        rc = lib.cvae_graph_instantiate_prio(raw, C.byref(ex))
+        if rc != 0:
+            raise RuntimeError(f"libcvae_b200: graph_instantiate_prio failed: {_ERR.get(rc, rc)}")
+        self.exec = ex
+
+    def launch(self):
+        rc = lib.cvae_graph_launch(self.exec, stream())
+        if rc != 0:
+            raise RuntimeError(f"libcvae_b200: graph_launch failed: {_ERR.get(rc, rc)}")
+
+    def __del__(self):
+        ex, self.exec = getattr(self, "exec", None), None
+        if ex:
+            try:
+                lib.cvae_graph_exec_destroy(ex)
+            except Exception:
+                pass

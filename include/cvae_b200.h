@@ -421,6 +421,19 @@ int cvae_vessel_preprocess(const cvae_preproc_t* p, cvae_stream_t s);
 int cvae_scaler_transform(const double* m, const double* mean, const double* scale, float* out, int64_t rows,
                           int cols, cvae_stream_t s);
 
+/* ---- replay of a captured step with per-node priorities ------------------------------------------------------------
+ * The reference's step (train.py:77-86) is one stream-ordered sequence; here it is captured once into a CUDA graph whose
+ * weight-gradient family runs as a parallel branch.  cvae_graph_set_priorities marks every kernel node of the captured
+ * cudaGraph_t: `prio_side` for the weight-gradient family (kernel names containing "wgrad" / "col_reduce"), `prio_main`
+ * for everything else (CUDA convention: lower value = higher priority); counts[3] = {kernel nodes, side nodes, nodes
+ * whose name could not be resolved}.  cvae_graph_instantiate_prio instantiates with
+ * cudaGraphInstantiateFlagUseNodePriority (a default instantiation ignores node priorities); cvae_graph_launch replays
+ * it on `s`.  The caller keeps the cudaGraph_t and its memory pool alive. */
+int cvae_graph_set_priorities(void* graph, int prio_main, int prio_side, int* counts);
+int cvae_graph_instantiate_prio(void* graph, void** exec_out);
+int cvae_graph_launch(void* exec, cvae_stream_t s);
+int cvae_graph_exec_destroy(void* exec);
+
 /* ---- debug: role-level wait accounting of the tensor-core kernels (builds with -DCVAE_TIMING only;
  * returns 0 and leaves out16 untouched otherwise).  Not part of the reference-facing surface. */
 int cvae_debug_read(unsigned long long* out16, int reset);
