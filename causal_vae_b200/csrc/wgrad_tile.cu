@@ -91,40 +91,81 @@ wgrad_tile_kernel(const __grid_constant__ WgradArgs a, const int patches, const 
   for (int patch = blockIdx.x; patch < patches; patch += gridDim.x) {
     const int tw = patch % tiles_w, tt = patch / tiles_w, th = tt % tiles_h, n = tt / tiles_h;
     const int h0 = th * kWtTH, w0 = tw * kWtTW;
-    // ---- stage the input halo of ga (transform applied; padding stays exactly 0) ----
+    // ---- stage the input halo of ga and the db patch (transform applied; padding stays exactly 0) ----
+    // Loads are issued in batches of up to kBatch per thread BEFORE the first shared-memory store of the batch: the
+    // plain load -> transform -> store loop cannot be reordered by the compiler across the stores, so a thread paid one
+    // full L2 / DRAM round trip per vector (nine per patch for the stride-2 halo) with nothing else in flight.
     const int gh0 = h0 * S - a.pad, gw0 = w0 * S - a.pad;
-    for (int idx = tid; idx < GR * GC * NA; idx += kWtThreads) {
-      const int pix = idx / NA, gi = pix / GC, gj = pix % GC;
-      const int ih = gh0 + gi, iw = gw0 + gj;
-      VecT<VA> v;
+    constexpr int kBatch = 6;
+    constexpr int kGaItems = GR * GC * NA, kDbItems = NPIX * NB;
+    constexpr int kGaIters = (kGaItems + kWtThreads - 1) / kWtThreads, kDbIters = (kDbItems + kWtThreads - 1) / kWtThreads;
+    {
+      // the db patch first (its loads stay in flight while the halo batches are issued)
+      VecT<VB> dv[kDbIters];
+      int dpix[kDbIters];
 #pragma unroll
-      for (int i = 0; i < VA; ++i) v.v[i] = 0.f;
-      if ((unsigned)ih < (unsigned)a.Ha && (unsigned)iw < (unsigned)a.Wa) {
-        v = ldgv<VA>(a.ga + (((size_t)n * a.Ha + ih) * a.Wa + iw) * CA + ga_grp * VA);
+      for (int u = 0; u < kDbIters; ++u) {
+        const int idx = tid + u * kWtThreads;
+        dpix[u] = -1;
 #pragma unroll
-        for (int i = 0; i < VA; ++i) {
-          if (a.a_affine) v.v[i] = fmaf(v.v[i] - ace.v[i], asc.v[i], ash.v[i]);
-          if (a.a_act) v.v[i] = lrelu(v.v[i], a.a_slope);
+        for (int i = 0; i < VB; ++i) dv[u].v[i] = 0.f;
+        if (idx < kDbItems) {
+          const int pix = idx / NB, r = pix / kWtTW, c = pix % kWtTW;
+          const int qh = h0 + r, qw = w0 + c;
+          dpix[u] = pix;
+          if (qh < a.Hq && qw < a.Wq) {
+            dv[u] = ldgv<VB>(a.db + (((size_t)n * a.Hq + qh) * a.Wq + qw) * a.Cb + cb0 + db_grp * VB);
+            dpix[u] |= 1 << 30;
+          }
         }
       }
-      stv<VA>(sG + pix * CA + ga_grp * VA, v);
-    }
-    // ---- stage the db patch ----
-    for (int idx = tid; idx < NPIX * NB; idx += kWtThreads) {
-      const int pix = idx / NB, r = pix / kWtTW, c = pix % kWtTW;
-      const int qh = h0 + r, qw = w0 + c;
-      VecT<VB> v;
 #pragma unroll
-      for (int i = 0; i < VB; ++i) v.v[i] = 0.f;
-      if (qh < a.Hq && qw < a.Wq) {
-        v = ldgv<VB>(a.db + (((size_t)n * a.Hq + qh) * a.Wq + qw) * a.Cb + cb0 + db_grp * VB);
+      for (int b0 = 0; b0 < kGaIters; b0 += kBatch) {
+        VecT<VA> gv[kBatch];
+        int gpix[kBatch];
 #pragma unroll
-        for (int i = 0; i < VB; ++i) {
-          if (a.b_affine) v.v[i] = fmaf(v.v[i] - bce.v[i], bsc.v[i], bsh.v[i]);
-          if (a.b_act) v.v[i] = lrelu(v.v[i], a.b_slope);
+        for (int u = 0; u < kBatch; ++u) {
+          gpix[u] = -1;
+#pragma unroll
+          for (int i = 0; i < VA; ++i) gv[u].v[i] = 0.f;
+          if (b0 + u < kGaIters) {
+            const int idx = tid + (b0 + u) * kWtThreads;
+            if (idx < kGaItems) {
+              const int pix = idx / NA, gi = pix / GC, gj = pix % GC;
+              const int ih = gh0 + gi, iw = gw0 + gj;
+              gpix[u] = pix;
+              if ((unsigned)ih < (unsigned)a.Ha && (unsigned)iw < (unsigned)a.Wa) {
+                gv[u] = ldgv<VA>(a.ga + (((size_t)n * a.Ha + ih) * a.Wa + iw) * CA + ga_grp * VA);
+                gpix[u] |= 1 << 30;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          if (gpix[u] < 0) continue;
+          if (gpix[u] & (1 << 30)) {
+#pragma unroll
+            for (int i = 0; i < VA; ++i) {
+              if (a.a_affine) gv[u].v[i] = fmaf(gv[u].v[i] - ace.v[i], asc.v[i], ash.v[i]);
+              if (a.a_act) gv[u].v[i] = lrelu(gv[u].v[i], a.a_slope);
+            }
+          }
+          stv<VA>(sG + (gpix[u] & ~(1 << 30)) * CA + ga_grp * VA, gv[u]);
         }
       }
-      stv<VB>(sD + pix * CB + db_grp * VB, v);
+#pragma unroll
+      for (int u = 0; u < kDbIters; ++u) {
+        if (dpix[u] < 0) continue;
+        if (dpix[u] & (1 << 30)) {
+#pragma unroll
+          for (int i = 0; i < VB; ++i) {
+            if (a.b_affine) dv[u].v[i] = fmaf(dv[u].v[i] - bce.v[i], bsc.v[i], bsh.v[i]);
+            if (a.b_act) dv[u].v[i] = lrelu(dv[u].v[i], a.b_slope);
+          }
+        }
+        stv<VB>(sD + (dpix[u] & ~(1 << 30)) * CB + db_grp * VB, dv[u]);
+      }
     }
     __syncthreads();
     // ---- accumulate ----
