@@ -18,16 +18,37 @@ constexpr int kAT = 5;   // tile edge (65 = 13 * 5 tokens at 256x256)
 
 __device__ __forceinline__ int att_lp(int Sp) { return (Sp & 1) ? Sp : Sp + 1; }
 
-// rows [0,S) of one head's [S, d] slice (row stride `stride` floats) -> smem [Sp][ld], rows >= S zeroed
-__device__ __forceinline__ void att_load(float* dst, const float* __restrict__ src, int S, int Sp, int d, int ld,
-                                         size_t stride) {
-  const int d4 = d >> 2;
-  for (int i = threadIdx.x; i < Sp * d4; i += blockDim.x) {
-    const int s = i / d4, c = (i - s * d4) << 2;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s < S) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)s * stride + c));
-    float* o = dst + s * ld + c;
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+// rows [0,S) of NT heads' [S, d] slices (row stride `stride[t]` floats) -> smem [Sp][ld] each, rows >= S zeroed.
+// All loads of a batch (2 vectors per thread and tensor) are issued before the first shared-memory store: the
+// one-tensor-at-a-time load -> store loop paid 3 dependent L2 round trips per tensor, 9 per forward launch.
+template <int NT>
+__device__ __forceinline__ void att_load_multi(float* const (&dst)[NT], const float* const (&src)[NT], const size_t (&stride)[NT],
+                                               int S, int Sp, int d, int ld) {
+  const int d4 = d >> 2, n = Sp * d4;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 2 * blockDim.x) {
+    float4 v[2][NT];
+    int so[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * blockDim.x;
+      so[u] = -1;
+      const int s = i / d4, c = (i - s * d4) << 2;
+      if (i < n) so[u] = s * ld + c;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        v[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n && s < S) v[u][t] = __ldg(reinterpret_cast<const float4*>(src[t] + (size_t)s * stride[t] + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (so[u] < 0) continue;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        float* o = dst[t] + so[u];
+        o[0] = v[u][t].x; o[1] = v[u][t].y; o[2] = v[u][t].z; o[3] = v[u][t].w;
+      }
+    }
   }
 }
 
@@ -50,7 +71,7 @@ __device__ __forceinline__ void att_tile_nt(const float* __restrict__ A, const f
   }
 }
 
-__global__ void __launch_bounds__(256) attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+__global__ void __launch_bounds__(256, 4) attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                             float* __restrict__ probs, int S, int H, int d,
                                                             float p_drop, uint64_t seed, uint64_t offset,
                                                             const int64_t* __restrict__ counter) {
@@ -60,9 +81,12 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const float* __restr
   float* Q = sm; float* K = Q + Sp * ld; float* V = K + Sp * ld; float* P = V + Sp * ld;
   const int b = blockIdx.x / H, h = blockIdx.x % H, D = H * d, tid = threadIdx.x;
   const float* base = qkv + (size_t)b * S * 3 * D + h * d;
-  att_load(Q, base, S, Sp, d, ld, 3 * D);
-  att_load(K, base + D, S, Sp, d, ld, 3 * D);
-  att_load(V, base + 2 * D, S, Sp, d, ld, 3 * D);
+  {
+    float* const dsts[3] = {Q, K, V};
+    const float* const srcs[3] = {base, base + D, base + 2 * D};
+    const size_t strides[3] = {(size_t)3 * D, (size_t)3 * D, (size_t)3 * D};
+    att_load_multi<3>(dsts, srcs, strides, S, Sp, d, ld);
+  }
   __syncthreads();
   const float scale = rsqrtf((float)d);
   for (int t = tid; t < nb * nb; t += blockDim.x) {
@@ -138,7 +162,7 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const float* __restr
   }
 }
 
-__global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
+__global__ void __launch_bounds__(256, 4) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                                                             const float* __restrict__ dout, float* __restrict__ dqkv,
                                                             int S, int H, int d, float p_drop) {
   extern __shared__ float sm[];
@@ -149,8 +173,12 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
   float* dS = Ps + Sp * lp;
   const int b = blockIdx.x / H, h = blockIdx.x % H, D = H * d, tid = threadIdx.x;
   const float* base = qkv + (size_t)b * S * 3 * D + h * d;
-  att_load(A, dout + (size_t)b * S * D + h * d, S, Sp, d, ld, D);
-  att_load(Bm, base + 2 * D, S, Sp, d, ld, 3 * D);
+  {
+    float* const dsts[2] = {A, Bm};
+    const float* const srcs[2] = {dout + (size_t)b * S * D + h * d, base + 2 * D};
+    const size_t strides[2] = {(size_t)D, (size_t)3 * D};
+    att_load_multi<2>(dsts, srcs, strides, S, Sp, d, ld);
+  }
   const float* pg = probs + (size_t)blockIdx.x * S * S;
   for (int i = tid; i < Sp * lp; i += blockDim.x) Ps[i] = 0.f;
   __syncthreads();
@@ -205,6 +233,22 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
         *reinterpret_cast<float2*>(gb + (size_t)j * 3 * D + 2 * D + c) = make_float2(acc[i][0] * keep_scale, acc[i][1] * keep_scale);
     }
   }
+  // Q and K replace dO and V in shared memory after the next barrier: their loads are issued now (three vectors per
+  // thread and tensor cover S <= 96 at 256 threads) so that the round trip overlaps the softmax-gradient pass
+  const int d4 = d >> 2, nvec = Sp * d4;
+  float4 pq[3], pk[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = tid + u * blockDim.x;
+    pq[u] = make_float4(0.f, 0.f, 0.f, 0.f); pk[u] = pq[u];
+    if (i < nvec) {
+      const int s_ = i / d4, c_ = (i - s_ * d4) << 2;
+      if (s_ < S) {
+        pq[u] = __ldg(reinterpret_cast<const float4*>(base + (size_t)s_ * 3 * D + c_));
+        pk[u] = __ldg(reinterpret_cast<const float4*>(base + D + (size_t)s_ * 3 * D + c_));
+      }
+    }
+  }
   // dS = P * (dP - rowsum(dP * P)) * scale   (rows only touch Ps / dS, which the dV pass does not write)
   const int lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const float scale = rsqrtf((float)d);
@@ -215,8 +259,29 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
     for (int j = lane; j < S; j += 32) dS[r * lp + j] = fabsf(Ps[r * lp + j]) * (dS[r * lp + j] - s) * scale;
   }
   __syncthreads();
-  att_load(A, base, S, Sp, d, ld, 3 * D);          // Q
-  att_load(Bm, base + D, S, Sp, d, ld, 3 * D);     // K
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = tid + u * blockDim.x;
+    if (i < nvec) {
+      const int s_ = i / d4, c_ = (i - s_ * d4) << 2;
+      float* oq = A + s_ * ld + c_;
+      float* ok = Bm + s_ * ld + c_;
+      oq[0] = pq[u].x; oq[1] = pq[u].y; oq[2] = pq[u].z; oq[3] = pq[u].w;
+      ok[0] = pk[u].x; ok[1] = pk[u].y; ok[2] = pk[u].z; ok[3] = pk[u].w;
+    }
+  }
+  for (int i = tid + 3 * blockDim.x; i < nvec; i += blockDim.x) {      // S > 96 at 256 threads
+    const int s_ = i / d4, c_ = (i - s_ * d4) << 2;
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f), k4 = q4;
+    if (s_ < S) {
+      q4 = __ldg(reinterpret_cast<const float4*>(base + (size_t)s_ * 3 * D + c_));
+      k4 = __ldg(reinterpret_cast<const float4*>(base + D + (size_t)s_ * 3 * D + c_));
+    }
+    float* oq = A + s_ * ld + c_;
+    float* ok = Bm + s_ * ld + c_;
+    oq[0] = q4.x; oq[1] = q4.y; oq[2] = q4.z; oq[3] = q4.w;
+    ok[0] = k4.x; ok[1] = k4.y; ok[2] = k4.z; ok[3] = k4.w;
+  }
   __syncthreads();
   // dQ[s][c] = sum_j dS[s][j] K[j][c];  dK[s][c] = sum_j dS[j][s] Q[j][c]
   for (int t = tid; t < nb * d2; t += blockDim.x) {

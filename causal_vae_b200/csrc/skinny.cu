@@ -278,15 +278,30 @@ __global__ void __launch_bounds__(kThreads) conv_cs1_tile_kernel(const __grid_co
     const int tw = patch % tiles_w, tt = patch / tiles_w, th = tt % tiles_h, n = tt / tiles_h;
     const int h0 = th * TH, w0 = tw * TW;
     const int gh0 = h0 * IS - 1, gw0 = w0 * IS - 1;
-    for (int idx = tid; idx < GR * GC; idx += kThreads) {
-      const int gi = idx / GC, gj = idx % GC, ih = gh0 + gi, iw = gw0 + gj;
-      float v = 0.f;
-      if ((unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws) {
-        v = __ldg(a.src + ((size_t)n * a.Hs + ih) * a.Ws + iw);
-        if (a.in_affine) v = fmaf(v - in_ce, in_sc, in_sh);
-        if (a.in_act) v = lrelu(v, a.in_slope);
+    {
+      // every load of the halo tile is issued before the first shared-memory store (one round trip per patch, not one
+      // per loop iteration)
+      constexpr int kIt = (GR * GC + kThreads - 1) / kThreads;
+      float hv[kIt];
+      bool hok[kIt];
+#pragma unroll
+      for (int u = 0; u < kIt; ++u) {
+        const int idx = tid + u * kThreads;
+        const int gi = idx / GC, gj = idx % GC, ih = gh0 + gi, iw = gw0 + gj;
+        hok[u] = idx < GR * GC && (unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws;
+        hv[u] = 0.f;
+        if (hok[u]) hv[u] = __ldg(a.src + ((size_t)n * a.Hs + ih) * a.Ws + iw);
       }
-      sG[idx] = v;
+#pragma unroll
+      for (int u = 0; u < kIt; ++u) {
+        const int idx = tid + u * kThreads;
+        float v = hv[u];
+        if (hok[u]) {
+          if (a.in_affine) v = fmaf(v - in_ce, in_sc, in_sh);
+          if (a.in_act) v = lrelu(v, a.in_slope);
+        }
+        if (idx < GR * GC) sG[idx] = v;
+      }
     }
     __syncthreads();
     for (int p = pp; p < TH * TW; p += PPP) {
