@@ -413,35 +413,36 @@ conv16_head_fwd_kernel(const __grid_constant__ GatherArgs a, const int tiles_h, 
       sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + s4 * 4));
       if (a.in_center) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + s4 * 4));
     }
-    for (int base = 0; base < kHdPix * 4; base += 6 * kFewThreads) {   // 4624 vectors: batches of 6 loads per thread
-      float4 v[6];
-      int pixs[6];
+    // Staging by ROWS: a window row is 34 pixels x 16 channels = 2176 contiguous bytes (NHWC), so a warp takes whole rows
+    // (warp, warp + 8, ...) and a lane the vectors lane + 32 k of the row: the channel quarter (lane & 3) is a per-thread
+    // constant, the addresses are row pointer + immediate, and the five loads of a row are issued before its stores (the
+    // flat index form spent ~50 instructions per vector on divisions by 34, bounds and 64-bit address arithmetic).
+    for (int gi = warp; gi < kHdG; gi += kFewThreads / 32) {
+      const int ih = h0 - 1 + gi;
+      const bool rok = (unsigned)ih < (unsigned)a.Hs;
+      const float* rowp = a.src + (((size_t)n * a.Hs + (rok ? ih : 0)) * a.Ws + (w0 - 1)) * 16 + lane * 4;   // dereferenced only where valid
+      float4 v[5];
+      bool ok[5];
 #pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        const int idx = base + tid + u * kFewThreads;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pixs[u] = -1;
-        if (idx < kHdPix * 4) {
-          const int pix = idx >> 2, gi = pix / kHdG, gj = pix - gi * kHdG, ih = h0 - 1 + gi, iw = w0 - 1 + gj;
-          pixs[u] = pix;
-          if ((unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws) {
-            v[u] = __ldg(reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * 16 + s4 * 4));
-            pixs[u] |= 1 << 30;
-          }
-        }
+      for (int k = 0; k < 5; ++k) {
+        const int gj = (lane >> 2) + 8 * k, iw = w0 - 1 + gj;
+        ok[k] = rok && gj < kHdG && (unsigned)iw < (unsigned)a.Ws;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[k]) v[k] = __ldg(reinterpret_cast<const float4*>(rowp + k * 128));
       }
 #pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        if (pixs[u] < 0) continue;
-        float4 x = v[u];
-        if (pixs[u] & (1 << 30)) {
+      for (int k = 0; k < 5; ++k) {
+        const int gj = (lane >> 2) + 8 * k;
+        if (gj >= kHdG) continue;
+        float4 x = v[k];
+        if (ok[k]) {
           if (a.in_affine) {
             x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
             x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
           }
           if (a.in_act) { x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope); x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope); }
         }
-        float* d = sX + (s4 * 4) * kHdPlane + (pixs[u] & ~(1 << 30));
+        float* d = sX + (s4 * 4) * kHdPlane + gi * kHdG + gj;
         d[0] = x.x; d[kHdPlane] = x.y; d[2 * kHdPlane] = x.z; d[3 * kHdPlane] = x.w;
       }
     }

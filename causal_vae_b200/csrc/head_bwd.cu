@@ -9,7 +9,8 @@
 // Both gradients need the same two things per pixel: the 16-channel vector y[q] (64 bytes) and the 3x3
 // neighbourhood of g.  As separate kernels (wgrad_tile<16,1,1> + conv_cs1_tile<16,1>) the 268 MB tensor y was
 // streamed twice (227 + 257 us at B = 64); here it is read once, dz is written once, and g lives in a
-// shared-memory tile.  The loads of a patch's four y vectors are issued before the tile barrier.
+// shared-memory tile.  The global loads of patch i + 1 (four y vectors and the g halo values per thread) are
+// issued before patch i is computed, so a block always has one patch of loads in flight.
 #include "common.cuh"
 
 namespace cvae {
@@ -21,18 +22,17 @@ __global__ void __launch_bounds__(kHbThreads, 2)
 head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ x_scale,
                 const float* __restrict__ x_shift, const float* __restrict__ x_center, const float slope,
                 const float* __restrict__ w, float* __restrict__ dz, double* __restrict__ stats, float* __restrict__ dw,
-                const int N, const int H, const int W, const int patches, const int tiles_h, const int tiles_w) {
+                const int N, const int H, const int W, const int patches, const int tiles_h, const int tiles_w,
+                const int tw_shift, const int th_shift) {
   constexpr int TH = 8, TW = 32, NB = C / 4, PPP = kHbThreads / NB, NIT = TH * TW / PPP;
-  constexpr int GR = TH + 2, GC = TW + 2;
-  __shared__ float sG[GR * GC];
-  __shared__ double s_red[kHbThreads][8];
+  constexpr int GR = TH + 2, GC = TW + 2, GN = GR * GC, GIT = (GN + kHbThreads - 1) / kHbThreads;
+  __shared__ float sG[GN];
+  __shared__ float4 sW[9 * NB];                        // [tap][channel group]: broadcast reads (the weights used to
+  __shared__ double s_red[kHbThreads][8];              // occupy 36 registers; they now pay for the patch prefetch)
   const int tid = threadIdx.x, c4 = tid % NB, c0 = c4 * 4, pp = tid / NB;
-  float4 wv[9];
-  int toff[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    wv[t] = make_float4(__ldg(w + (c0 + 0) * 9 + t), __ldg(w + (c0 + 1) * 9 + t), __ldg(w + (c0 + 2) * 9 + t), __ldg(w + (c0 + 3) * 9 + t));
-    toff[t] = (2 - t / 3) * GC + (2 - t % 3);          // G_t(q) = g[q - (kh - 1, kw - 1)] in halo-tile coordinates
+  if (tid < 9 * NB) {
+    const int t = tid / NB, cc = (tid % NB) * 4;
+    sW[tid] = make_float4(__ldg(w + (cc + 0) * 9 + t), __ldg(w + (cc + 1) * 9 + t), __ldg(w + (cc + 2) * 9 + t), __ldg(w + (cc + 3) * 9 + t));
   }
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), ce = sh;
   if (x_scale != nullptr) {
@@ -44,36 +44,58 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const 
 #pragma unroll
   for (int t = 0; t < 9; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; acc[t][2] = 0.f; acc[t][3] = 0.f; }
   float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
-  // fp64 running sums live in this thread's shared-memory slot (folded once per patch), not in registers:
-  // the FMA loop already holds 36 weights + 36 weight-gradient accumulators per thread
+  // fp64 running sums live in this thread's shared-memory slot, folded every fourth patch (16 fp32 terms per fold)
 #pragma unroll
   for (int j = 0; j < 8; ++j) s_red[tid][j] = 0.0;
 
-  for (int patch = blockIdx.x; patch < patches; patch += gridDim.x) {
-    const int tw = patch % tiles_w, tt = patch / tiles_w, th = tt % tiles_h, n = tt / tiles_h;
-    const int h0 = th * TH, w0 = tw * TW;
-    for (int idx = tid; idx < GR * GC; idx += kHbThreads) {
+  // patch -> (image, tile origin); power-of-two tile grids (256 x 256: 32 x 8 tiles) avoid the runtime divisions
+  auto decode = [&](int patch, int& n, int& h0, int& w0) {
+    int tw, tt, th;
+    if (tw_shift >= 0 && th_shift >= 0) { tw = patch & (tiles_w - 1); tt = patch >> tw_shift; th = tt & (tiles_h - 1); n = tt >> th_shift; }
+    else { tw = patch % tiles_w; tt = patch / tiles_w; th = tt % tiles_h; n = tt / tiles_h; }
+    h0 = th * TH; w0 = tw * TW;
+  };
+  // every global load of a patch (its four y vectors and its share of the g halo tile) in one batch
+  auto fetch = [&](int patch, float4 (&yv)[NIT], float (&gv)[GIT]) {
+    int n, h0, w0;
+    decode(patch, n, h0, w0);
+#pragma unroll
+    for (int u = 0; u < GIT; ++u) {
+      const int idx = tid + u * kHbThreads;
       const int gi = idx / GC, gj = idx - gi * GC, ih = h0 - 1 + gi, iw = w0 - 1 + gj;
-      float v = 0.f;
-      if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) v = __ldg(g + ((size_t)n * H + ih) * W + iw);
-      sG[idx] = v;
+      gv[u] = 0.f;
+      if (idx < GN && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) gv[u] = __ldg(g + ((size_t)n * H + ih) * W + iw);
     }
-    float4 yv[NIT];
-    int off[NIT];                                      // N*H*W*C < 2^31 (checked by the launcher)
-    bool ok[NIT];
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
       const int p = pp + i * PPP, r = p / TW, c = p - r * TW, qh = h0 + r, qw = w0 + c;
-      ok[i] = qh < H && qw < W;
-      off[i] = ((n * H + qh) * W + qw) * C + c0;
       yv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok[i]) yv[i] = __ldg(reinterpret_cast<const float4*>(y + off[i]));
+      if (qh < H && qw < W) yv[i] = __ldg(reinterpret_cast<const float4*>(y + ((n * H + qh) * W + qw) * C + c0));   // N*H*W*C < 2^31
+    }
+  };
+
+  float4 yv[NIT];
+  float gv[GIT];
+  int patch = blockIdx.x, since = 0;
+  if (patch < patches) fetch(patch, yv, gv);
+  for (; patch < patches; patch += gridDim.x) {
+    int n, h0, w0;
+    decode(patch, n, h0, w0);
+#pragma unroll
+    for (int u = 0; u < GIT; ++u) {
+      const int idx = tid + u * kHbThreads;
+      if (idx < GN) sG[idx] = gv[u];
     }
     __syncthreads();
+    // the next patch's loads are in flight while this one is computed
+    float4 yn[NIT];
+    float gn[GIT];
+    const int next = patch + gridDim.x;
+    if (next < patches) fetch(next, yn, gn);
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
-      if (!ok[i]) continue;
-      const int p = pp + i * PPP, r = p / TW, c = p - r * TW;
+      const int p = pp + i * PPP, r = p / TW, c = p - r * TW, qh = h0 + r, qw = w0 + c;
+      if (qh >= H || qw >= W) continue;
       const float* gp = sG + r * GC + c;
       const float rf[4] = {yv[i].x - ce.x, yv[i].y - ce.y, yv[i].z - ce.z, yv[i].w - ce.w};
       const float z[4] = {fmaf(rf[0], sc.x, sh.x), fmaf(rf[1], sc.y, sh.y), fmaf(rf[2], sc.z, sh.z), fmaf(rf[3], sc.w, sh.w)};
@@ -82,8 +104,9 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const 
       for (int j = 0; j < 4; ++j) av[j] = z[j] > 0.f ? z[j] : z[j] * slope;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float gt = gp[toff[t]];
-        o[0] = fmaf(gt, wv[t].x, o[0]); o[1] = fmaf(gt, wv[t].y, o[1]); o[2] = fmaf(gt, wv[t].z, o[2]); o[3] = fmaf(gt, wv[t].w, o[3]);
+        const float gt = gp[(2 - t / 3) * GC + (2 - t % 3)];      // G_t(q) = g[q - (kh - 1, kw - 1)] in halo-tile coordinates
+        const float4 wt = sW[t * NB + c4];
+        o[0] = fmaf(gt, wt.x, o[0]); o[1] = fmaf(gt, wt.y, o[1]); o[2] = fmaf(gt, wt.z, o[2]); o[3] = fmaf(gt, wt.w, o[3]);
         acc[t][0] = fmaf(av[0], gt, acc[t][0]); acc[t][1] = fmaf(av[1], gt, acc[t][1]);
         acc[t][2] = fmaf(av[2], gt, acc[t][2]); acc[t][3] = fmaf(av[3], gt, acc[t][3]);
       }
@@ -92,12 +115,21 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const 
         o[j] = z[j] > 0.f ? o[j] : o[j] * slope;
         f1[j] += o[j]; f2[j] = fmaf(o[j], rf[j], f2[j]);
       }
-      *reinterpret_cast<float4*>(dz + off[i]) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dz + ((n * H + qh) * W + qw) * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
     }
+    if (++since == 4) {
+      since = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { s_red[tid][j] += (double)f1[j]; s_red[tid][4 + j] += (double)f2[j]; f1[j] = 0.f; f2[j] = 0.f; }
+      for (int j = 0; j < 4; ++j) { s_red[tid][j] += (double)f1[j]; s_red[tid][4 + j] += (double)f2[j]; f1[j] = 0.f; f2[j] = 0.f; }
+    }
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) yv[i] = yn[i];
+#pragma unroll
+    for (int u = 0; u < GIT; ++u) gv[u] = gn[u];
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s_red[tid][j] += (double)f1[j]; s_red[tid][4 + j] += (double)f2[j]; }
   // ---- BN-backward sums: threads with the same channel group -> one atomic per sum per block ----
   if (stats != nullptr) {
     __syncthreads();
@@ -141,9 +173,11 @@ extern "C" int cvae_head_bwd(const float* g, const float* y, cvae_xform_t x, con
   if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 9, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
   const int tiles_h = (H + 7) / 8, tiles_w = (W + 31) / 32;
   const int patches = N * tiles_h * tiles_w;
-  const int grid = patches < kNumSMs * 4 ? patches : kNumSMs * 4;
+  // two resident blocks per SM (128 registers): one wave, every block walks its share of the patches
+  const int grid = patches < kNumSMs * 2 ? patches : kNumSMs * 2;
+  auto log2_or_neg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
   head_bwd_kernel<16><<<grid, kHbThreads, 0, st>>>(g, y, x.scale, x.shift, x.center, x.slope, w, dz, stats, dw, N, H, W,
-                                                   patches, tiles_h, tiles_w);
+                                                   patches, tiles_h, tiles_w, log2_or_neg(tiles_w), log2_or_neg(tiles_h));
   CVAE_LAUNCH_CHECK();
   return CVAE_OK;
 }
