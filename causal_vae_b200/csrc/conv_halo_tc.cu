@@ -150,31 +150,45 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       const int row = q * 32 + lane;
       const uint32_t t_a = tmem + 2u * acc_cols + ((uint32_t)(q * 32) << 16);
       // A thread's channels of a k-block (64 or 128 bytes of its own row) travel global -> shared with cp.async,
-      // kHRawStages - 1 k-blocks ahead and across tile boundaries, into a slot only this thread reads: no barrier, no
-      // registers held while the loads fly.  (First form: load -> transform -> tcgen05.st -> next load, one dependent
+      // kHRawStages - 1 k-blocks ahead and across tile boundaries, into a slot only this thread reads: no block barrier,
+      // no registers held while the loads fly.  The copies of a warp's 32 rows are issued COOPERATIVELY: kCh consecutive
+      // lanes fetch the kCh 16-byte chunks of one row, so one instruction touches 32 / kCh rows with full sectors.  (In the
+      // thread-per-row form every instruction touched 32 different 128-byte lines, 16 of 32 sector bytes used: 1024 tag
+      // lookups per k-block and SM - scripts/probe_linear_fixed.py: ~0.9 us per k-block whatever the MMA work, 17.6 us
+      // for ONE 128 x 256 x 256 tile.  First form of all: load -> transform -> tcgen05.st -> next load, one dependent
       // round trip per k-block.)
+      constexpr int kCh = 4 * kHpt, kRpi = 32 / kCh;   // chunks per row part, rows per instruction
       uint8_t* raw = dsm_gen + (size_t)NB * bstage + (size_t)tid * kPitch;
+      const uint32_t raw_warp = smem_u32(dsm_gen + (size_t)NB * bstage + (size_t)(tid - lane) * kPitch);
+      const int crow = lane / kCh, cch = lane % kCh;   // this lane's row (within an instruction) and chunk
+      const long long Mrows = (long long)a.Hs * 8;     // Linear view: ONE image of M / 8 x 8 positions, a tile = 128 consecutive rows
       int ti = blockIdx.x, kbi = 0;                    // next (tile, k-block) to request
-      auto row_ptr = [&](int t) -> const float* {      // this thread's row of tile t, or nullptr past the matrix
-        if (t >= total) return nullptr;
+      const float* wbase = nullptr;                    // first row of this warp quarter in tile ti
+      int nvalid = 0;                                  // rows of the quarter inside the matrix
+      auto set_tile = [&](int t) {
+        wbase = nullptr; nvalid = 0;
+        if (t >= total) return;
         const HTile tl = h_decode(p, t);
-        const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
-        if (qh >= a.Hs || qw >= a.Ws) return nullptr;
-        return a.src + (((size_t)tl.n * a.Hs + qh) * a.Ws + qw) * a.Cs;
+        const long long r0 = (long long)tl.h0 * 8 + q * 32;
+        wbase = a.src + (size_t)r0 * a.Cs;
+        const long long left = Mrows - r0;
+        nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
       };
-      const float* rpi = row_ptr(ti);
+      set_tile(ti);
       auto issue = [&](int slot) {
         if (ti < total) {
-          const int c0 = kbi * 32 + h0 * 16;
-          const uint32_t dst = smem_u32(raw + (size_t)slot * (kLinWarps * 32 * kPitch));
+          const int c = kbi * 32 + h0 * 16 + 4 * cch;
+          const uint32_t dstw = raw_warp + (uint32_t)slot * (uint32_t)(kLinWarps * 32 * kPitch) + 16u * cch;
 #pragma unroll
-          for (int j = 0; j < 4 * kHpt; ++j) {
-            if (rpi != nullptr && c0 + 4 * j < a.Cs)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * j), "l"(rpi + c0 + 4 * j) : "memory");
+          for (int j = 0; j < kCh; ++j) {
+            const int rl = j * kRpi + crow;
+            const uint32_t dst = dstw + (uint32_t)(rl * kPitch);
+            if (rl < nvalid && c < a.Cs)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(wbase + (size_t)rl * a.Cs + c) : "memory");
             else
-              asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst + 16u * j), "f"(0.f) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
           }
-          if (++kbi == KB) { kbi = 0; ti += gridDim.x; rpi = row_ptr(ti); }
+          if (++kbi == KB) { kbi = 0; ti += gridDim.x; set_tile(ti); }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");     // always: one group per iteration keeps the count uniform
       };
@@ -189,6 +203,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         for (int kb = 0; kb < KB; ++kb, ++it) {
           issue((int)((it + kHRawStages - 1) % kHRawStages));
           asm volatile("cp.async.wait_group %0;" ::"n"(kHRawStages - 1) : "memory");
+          __syncwarp();                                  // the row was copied by other lanes of this warp
           const uint8_t* rs = raw + (size_t)(it % kHRawStages) * (kLinWarps * 32 * kPitch);
           const int slot = it % kHNAT;
 #pragma unroll

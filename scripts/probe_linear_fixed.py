@@ -5,7 +5,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from causal_vae_b200 import _lib as L, ops
 NL = 50
-for M, K, N in ((128, 32, 16), (128, 256, 256), (1024, 256, 256), (4160, 256, 256), (4160, 256, 768), (4160, 512, 256), (8320, 256, 256)):
+for M, K, N in ((128, 32, 16), (4160, 32, 16), (4160, 32, 128), (4160, 32, 256), (4160, 256, 16), (4160, 512, 16), (4160, 256, 128), (128, 256, 256), (4160, 256, 256), (4160, 256, 768), (4160, 512, 256), (8320, 256, 256)):
     x = torch.randn(M, 1, 1, K, device="cuda")
     w = torch.randn(N, K, 1, device="cuda") * 0.05
     b = torch.randn(N, device="cuda")
