@@ -202,7 +202,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         const bool rok = qh < a.Hs && qw < a.Ws;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           issue((int)((it + kHRawStages - 1) % kHRawStages));
-          asm volatile("cp.async.wait_group %0;" ::"n"(kHRawStages - 1) : "memory");
+          T_WAIT(1, asm volatile("cp.async.wait_group %0;" ::"n"(kHRawStages - 1) : "memory"))
           __syncwarp();                                  // the row was copied by other lanes of this warp
           const uint8_t* rs = raw + (size_t)(it % kHRawStages) * (kLinWarps * 32 * kPitch);
           const int slot = it % kHNAT;
@@ -243,7 +243,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             tmem_st16(t_a + (uint32_t)(slot * 64 + half * 16), hi);
             tmem_st16(t_a + (uint32_t)(slot * 64 + 32 + half * 16), lo);
           }
-          tmem_st_wait();
+          T_WAIT(2, tmem_st_wait())
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&s_afull[slot]));
@@ -251,6 +251,9 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       if (tid == 0) T_FLUSH(0, 1)
+#ifdef CVAE_TIMING
+      if (tid == 0) { atomicAdd(&g_halo_dbg[10], t_acc[1]); atomicAdd(&g_halo_dbg[11], t_acc[2]); }   // Linear producer: cp.async wait, tcgen05.wait::st
+#endif
     }
   } else if (warp < kHProdWarps) {
     // ============================== A producers: halo tile -> swizzled hi / lo planes ==============================
