@@ -1,7 +1,6 @@
 """causal_cascade/train.py:5-40 on the native kernels: loss_function and the inner training step."""
 from .. import functional as F
-from ..chain import direct_grads
-from ..graph import GraphedStep, trainer_state
+from ..graph import GraphedStep, StepScope, trainer_state
 from ..optim import FlatParams, FusedClipAdam
 from ..parallel import allreduce_gradients
 
@@ -22,14 +21,16 @@ class CascadeTrainer:
         self.opt = FusedClipAdam(FlatParams(model), lr)
         self.distributed, self.pg = distributed, process_group      # SUM of shard gradients (sum-reduced loss)
         self.graphed = None
+        self.scope = StepScope(self.opt.flat.data.device)
 
     def step(self, x, m, t, eps=None):
         self.model.train()
         self.opt.zero_grad()
-        recon_x, m_hat, mu, logvar = self.model(x, m, t, eps)
-        loss, l_recon, l_m = loss_function(recon_x, x, m_hat, m, mu, logvar, self.gamma)
-        with direct_grads():
-            loss.backward()
+        with self.scope:
+            recon_x, m_hat, mu, logvar = self.model(x, m, t, eps)
+            loss, l_recon, l_m = loss_function(recon_x, x, m_hat, m, mu, logvar, self.gamma)
+            with self.scope.backward():
+                loss.backward()
         if self.distributed:
             allreduce_gradients(self.opt.flat.grad, group=self.pg)
         self.opt.step()

@@ -42,7 +42,7 @@ bool launch_wgrad_ca1(const WgradArgs& a, int taps, cudaStream_t st);   // Ca ==
 int launch_conv_few(const cvae_conv_params_t* p, const GatherArgs& g, cudaStream_t st);
 int launch_conv16_head_fwd(const GatherArgs& g, cudaStream_t st);   // Conv 16 -> 1 3x3 s1 (image head forward)
 
-// linear_small.cu: Linear layers / weight gradients with M <= 128 rows.  1: launched, 0: not covered, < 0: error.
+// linear_small.cu: Linear layers / weight gradients with M <= 512 rows.  1: launched, 0: not covered, < 0: error.
 int launch_linear_small(const GatherArgs& g, cudaStream_t st);
 int launch_wgrad_small(const WgradArgs& a, int taps, int splits, cudaStream_t st);
 

@@ -1,4 +1,4 @@
-// Linear layers with a handful of rows (M = batch <= 128): the adapters, the morphology head and
+// Linear layers with a handful of rows (M = batch <= 512; 128 rows per CTA): the adapters, the morphology head and
 // decoder_input of CausalViTVAE (vessel_analysis/00_core/models.py:225-250, vit_backbone.py:186-188), and
 // every Linear of the MNIST / cascade models.
 //
@@ -18,17 +18,19 @@
 namespace cvae {
 
 constexpr int kLsKC = 64;        // K chunk per CTA
-constexpr int kLsMaxM = 128;
+constexpr int kLsMaxM = 512;     // rows beyond 128 go to further row blocks (grid z): the cascade model trains at batch 256
 
-template <int R>   // rows per warp; M <= 4 R
+template <int R>   // rows per warp; a CTA covers rows [4 R z, 4 R (z + 1)) of the M
 __global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant__ GatherArgs a, const int M, const int cpc) {
   __shared__ __align__(16) float xs[4 * R * kLsKC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = blockIdx.z * 4 * R;                 // first row of this CTA's row block
   const int n = blockIdx.x * 32 + lane;
   const bool nok = n < a.Cd;
   float acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  const float b = (nok && blockIdx.y == 0 && a.bias != nullptr) ? __ldg(a.bias + n) : 0.f;   // requested with the weights
   // `cpc` consecutive K chunks per CTA (launch_linear_small: as many as still leave ~4 CTAs per SM), so a wide layer
   // (decoder_input, 512 -> 16384: 512 column blocks) runs without K split -- no pre-zeroing, no atomics: its 8.4 M
   // fp32 atomics were ~30 us of a 105 us launch -- and the 16384 -> 512 input gradient meets in 43 instead of 256 adds
@@ -36,54 +38,77 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const __grid_constant
   const int k0 = (blockIdx.y * cpc + kc) * kLsKC;
   if (k0 >= a.Cs) break;
   if (kc > 0) __syncthreads();
+  // ---- this lane's 64 weights of the chunk: ALL requested before anything waits on them ----
+  // (the K loop used to fetch four per iteration: 16 dependent round trips to weights that left L2 a step ago, which
+  // was the whole life of these CTAs -- 14-18 us for a 64 x 64 x 12 layer; the loads now overlap the x staging too)
+  const int kmax = min(kLsKC, a.Cs - k0);            // Cs % 4 == 0
+  float wv[kLsKC];
+  {
+    const float* wp = a.wt + (size_t)k0 * a.Cd + (nok ? n : 0);
+#pragma unroll
+    for (int kk = 0; kk < kLsKC; ++kk) wv[kk] = (nok && kk < kmax) ? __ldg(wp + (size_t)kk * a.Cd) : 0.f;
+  }
   // ---- stage x[:, k0 : k0 + 64] with the producer's BatchNorm + activation applied ----
-  // (unrolled: a CTA's whole life is a few dependent global round trips, so every loop keeps several loads in flight)
-#pragma unroll 8
-  for (int idx = tid; idx < 4 * R * (kLsKC / 4); idx += 128) {
-    const int m = idx / (kLsKC / 4), c4 = idx - m * (kLsKC / 4), k = k0 + c4 * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < M && k < a.Cs) {
-      v = __ldg(reinterpret_cast<const float4*>(a.src + (size_t)m * a.Cs + k));
-      if (a.in_affine) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + k));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + k));
-        float4 ce = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + k));
-        v.x = fmaf(v.x - ce.x, sc.x, sh.x); v.y = fmaf(v.y - ce.y, sc.y, sh.y);
-        v.z = fmaf(v.z - ce.z, sc.z, sh.z); v.w = fmaf(v.w - ce.w, sc.w, sh.w);
-      }
-      if (a.in_act) { v.x = lrelu(v.x, a.in_slope); v.y = lrelu(v.y, a.in_slope); v.z = lrelu(v.z, a.in_slope); v.w = lrelu(v.w, a.in_slope); }
+  // A thread always stages the same four channels (128 threads = 8 rows x 16 vectors per pass), so their coefficients are
+  // loaded once, and the row loads go out in batches BEFORE the first shared-memory store of the batch: the plain
+  // load -> transform -> store loop is not reordered across the stores, i.e. one dependent round trip per vector
+  // (R / 2 of them: the other half of these CTAs' 14-18 us).
+  {
+    constexpr int kIt = R / 2, kB = kIt < 8 ? kIt : 8;
+    const int c4 = tid & 15, k = k0 + c4 * 4, mrow = tid >> 4;
+    const bool kok = k < a.Cs;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), ce = sh;
+    if (a.in_affine && kok) {
+      sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + k));
+      sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + k));
+      if (a.in_center != nullptr) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + k));
     }
-    *reinterpret_cast<float4*>(xs + m * kLsKC + c4 * 4) = v;
+#pragma unroll
+    for (int b0 = 0; b0 < kIt; b0 += kB) {
+      float4 v[kB];
+      bool ok[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int m = mrow + (b0 + u) * 8;
+        ok[u] = kok && mb + m < M;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[u]) v[u] = __ldg(reinterpret_cast<const float4*>(a.src + (size_t)(mb + m) * a.Cs + k));
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int m = mrow + (b0 + u) * 8;
+        float4 x = v[u];
+        if (ok[u]) {
+          if (a.in_affine) {
+            x.x = fmaf(x.x - ce.x, sc.x, sh.x); x.y = fmaf(x.y - ce.y, sc.y, sh.y);
+            x.z = fmaf(x.z - ce.z, sc.z, sh.z); x.w = fmaf(x.w - ce.w, sc.w, sh.w);
+          }
+          if (a.in_act) { x.x = lrelu(x.x, a.in_slope); x.y = lrelu(x.y, a.in_slope); x.z = lrelu(x.z, a.in_slope); x.w = lrelu(x.w, a.in_slope); }
+        }
+        *reinterpret_cast<float4*>(xs + m * kLsKC + c4 * 4) = x;
+      }
+    }
   }
   __syncthreads();
-  const float* wp = a.wt + (size_t)k0 * a.Cd + (nok ? n : 0);
   const float* xr = xs + warp * R * kLsKC;
-  const int kmax = min(kLsKC, a.Cs - k0);            // Cs % 4 == 0
   float part[R];                                     // this chunk's sums: chains stay 64 long whatever cpc is
 #pragma unroll
   for (int r = 0; r < R; ++r) part[r] = 0.f;
-#pragma unroll 4
-  for (int kk = 0; kk < kmax; kk += 4) {
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-    if (nok) {
-      w0 = __ldg(wp + (size_t)(kk + 0) * a.Cd); w1 = __ldg(wp + (size_t)(kk + 1) * a.Cd);
-      w2 = __ldg(wp + (size_t)(kk + 2) * a.Cd); w3 = __ldg(wp + (size_t)(kk + 3) * a.Cd);
-    }
+#pragma unroll
+  for (int kk = 0; kk < kLsKC; kk += 4) {            // x beyond Cs is staged as 0 and its weights are 0: no tail case
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float4 xv = *reinterpret_cast<const float4*>(xr + r * kLsKC + kk);
-      part[r] = fmaf(xv.x, w0, fmaf(xv.y, w1, fmaf(xv.z, w2, fmaf(xv.w, w3, part[r]))));
+      part[r] = fmaf(xv.x, wv[kk], fmaf(xv.y, wv[kk + 1], fmaf(xv.z, wv[kk + 2], fmaf(xv.w, wv[kk + 3], part[r]))));
     }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] += part[r];
   }
   if (!nok) return;
-  const float b = (blockIdx.y == 0 && a.bias != nullptr) ? __ldg(a.bias + n) : 0.f;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int m = warp * R + r;
+    const int m = mb + warp * R + r;
     if (m < M) {
       if (gridDim.y == 1) a.dst[(size_t)m * a.Cd + n] = acc[r] + b;      // single K chunk: plain store, no pre-zeroing
       else atomicAdd(a.dst + (size_t)m * a.Cd + n, acc[r] + b);
@@ -101,19 +126,37 @@ __global__ void __launch_bounds__(128) linear_small_epi_kernel(const __grid_cons
   if (n < a.Cd) {
     float esc = 1.f, esh = 0.f, ece = 0.f;
     if (a.e_affine) { esc = __ldg(a.e_scale + n); esh = __ldg(a.e_shift + n); if (a.e_center) ece = __ldg(a.e_center + n); }
-#pragma unroll 8
-    for (int m = warp; m < M; m += 4) {
-      const size_t o = (size_t)m * a.Cd + n;
-      float x = a.dst[o];
-      if (a.epi == CVAE_EPI_STATS) {
-        s1 += (double)x; s2 += (double)x * (double)x;
-      } else {   // CVAE_EPI_DACT
-        const float refc = __ldg(a.epi_ref + o) - ece;
-        if (a.epi_add != nullptr) x += __ldg(a.epi_add + o);
-        const float z = fmaf(refc, esc, esh);
-        x = z > 0.f ? x : x * a.e_slope;
-        a.dst[o] = x;
-        s1 += (double)x; s2 += (double)x * (double)refc;
+    // rows in batches of 8 with every load of a batch issued before its first store: the matrix is read and (DACT)
+    // rewritten in place, so the plain loop was one dependent round trip per row (10-12 us at 64 rows, 40 us at 256)
+    const bool dact = a.epi != CVAE_EPI_STATS, has_add = dact && a.epi_add != nullptr;
+    for (int mbase = warp; mbase < M; mbase += 32) {
+      float x[8], rf[8], ad[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = mbase + 4 * u;
+        x[u] = 0.f; rf[u] = 0.f; ad[u] = 0.f;
+        if (m < M) {
+          const size_t o = (size_t)m * a.Cd + n;
+          x[u] = a.dst[o];
+          if (dact) rf[u] = __ldg(a.epi_ref + o);
+          if (has_add) ad[u] = __ldg(a.epi_add + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = mbase + 4 * u;
+        if (m >= M) continue;
+        float xv = x[u];
+        if (!dact) {
+          s1 += (double)xv; s2 += (double)xv * (double)xv;
+        } else {   // CVAE_EPI_DACT
+          const float refc = rf[u] - ece;
+          if (has_add) xv += ad[u];
+          const float z = fmaf(refc, esc, esh);
+          xv = z > 0.f ? xv : xv * a.e_slope;
+          a.dst[(size_t)m * a.Cd + n] = xv;
+          s1 += (double)xv; s2 += (double)xv * (double)refc;
+        }
       }
     }
   }
@@ -236,7 +279,7 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const __grid_constant_
 
 // 1: launched, 0: not covered
 int launch_linear_rows(const GatherArgs& g, int M, cudaStream_t st) {
-  if (M > 128 || (g.Cs & 3) || (g.Cd & 3) || (long long)g.Cs * g.Cd < (1ll << 21)) return 0;
+  if (M > kLsMaxM || (g.Cs & 3) || (g.Cd & 3) || (long long)g.Cs * g.Cd < (1ll << 21)) return 0;
   if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.wt) | reinterpret_cast<uintptr_t>(g.dst)) & 15) != 0) return 0;
   if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15) != 0) return 0;
   if (g.in_affine && (((reinterpret_cast<uintptr_t>(g.in_scale) | reinterpret_cast<uintptr_t>(g.in_shift)) & 15) != 0 ||
@@ -253,7 +296,7 @@ int launch_linear_rows(const GatherArgs& g, int M, cudaStream_t st) {
   return 1;
 }
 
-// weight gradient of such a layer: P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb]), m < M <= 128: the same 64 x 128 tile with
+// weight gradient of such a layer: P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb]), m < M: the same 64 x 128 tile with
 // the batch as the streamed dimension (both operands are read row-wise as they lie: no transposition)
 __global__ void __launch_bounds__(256) wgrad_rows_kernel(const __grid_constant__ WgradArgs a, const int M) {
   __shared__ __align__(16) float as[2][kLrK][68];
@@ -328,52 +371,90 @@ int launch_linear_small(const GatherArgs& g, cudaStream_t st) {
   if (M <= 16) linear_small_kernel<4><<<grid, 128, 0, st>>>(g, (int)M, cpc);
   else if (M <= 32) linear_small_kernel<8><<<grid, 128, 0, st>>>(g, (int)M, cpc);
   else if (M <= 64) linear_small_kernel<16><<<grid, 128, 0, st>>>(g, (int)M, cpc);
-  else linear_small_kernel<32><<<grid, 128, 0, st>>>(g, (int)M, cpc);
+  else linear_small_kernel<32><<<dim3(grid.x, grid.y, (unsigned)((M + 127) / 128)), 128, 0, st>>>(g, (int)M, cpc);
   if (g.epi != CVAE_EPI_PLAIN) linear_small_epi_kernel<<<(g.Cd + 31) / 32, 128, 0, st>>>(g, (int)M);
   return 1;
 }
 
-// ---- weight gradient: P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb]),  m < M <= 128 ----------------------
+// ---- weight gradient: P[ca][cb] = sum_m xa(ga[m][ca]) * xb(db[m][cb]),  m < M <= 512 (128 rows staged at a time) ----
 // CTA tile 32 (ca) x 64 (cb); thread = 2 ca x 4 cb.
 __global__ void __launch_bounds__(256) wgrad_small_kernel(const __grid_constant__ WgradArgs a, const int M) {
-  extern __shared__ __align__(16) float ws_sm[];      // M x (32 + 64) floats: sized by the launch, so M = 64 leaves 9 CTAs per SM
+  extern __shared__ __align__(16) float ws_sm[];      // min(M, 128) x (32 + 64) floats: sized by the launch, so M = 64 leaves 9 CTAs per SM
+  const int MC = min(M, 128);                         // rows staged at a time (M <= 128: one pass, as before)
   float* As = ws_sm;
-  float* Bs = ws_sm + M * 32;
+  float* Bs = ws_sm + MC * 32;
   const int tid = threadIdx.x;
   const int ca0 = blockIdx.x * 32, cb0 = blockIdx.y * 64;
-#pragma unroll 8
-  for (int idx = tid; idx < M * 32; idx += 256) {
-    const int m = idx >> 5, c = ca0 + (idx & 31);
-    float v = 0.f;
-    if (c < a.Ca) {
-      v = __ldg(a.ga + (size_t)m * a.Ca + c);
-      if (a.a_affine) v = fmaf(v - (a.a_center ? __ldg(a.a_center + c) : 0.f), __ldg(a.a_scale + c), __ldg(a.a_shift + c));
-      if (a.a_act) v = lrelu(v, a.a_slope);
-    }
-    As[idx] = v;
-  }
-#pragma unroll 8
-  for (int idx = tid; idx < M * 64; idx += 256) {
-    const int m = idx >> 6, c = cb0 + (idx & 63);
-    float v = 0.f;
-    if (c < a.Cb) {
-      v = __ldg(a.db + (size_t)m * a.Cb + c);
-      if (a.b_affine) v = fmaf(v - (a.b_center ? __ldg(a.b_center + c) : 0.f), __ldg(a.b_scale + c), __ldg(a.b_shift + c));
-      if (a.b_act) v = lrelu(v, a.b_slope);
-    }
-    Bs[idx] = v;
-  }
-  __syncthreads();
   const int ty = tid >> 4, tx = tid & 15;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int m0 = 0; m0 < M; m0 += MC) {
+    const int mc = min(MC, M - m0);
+    if (m0 > 0) __syncthreads();
+    // a thread always stages the same channel of each operand (256 threads = 8 rows x 32 / 4 rows x 64 per pass): the
+    // coefficients are loaded once and the rows go out in batches of 8 loads before the first shared-memory store
+    // (the plain loop paid one dependent round trip per row pass: 15 us at 64 rows, 55 us at 256)
+    {
+      const int c = ca0 + (tid & 31), mrow = tid >> 5;
+      const bool cok = c < a.Ca;
+      float sc = 1.f, sh = 0.f, ce = 0.f;
+      if (a.a_affine && cok) { sc = __ldg(a.a_scale + c); sh = __ldg(a.a_shift + c); ce = a.a_center ? __ldg(a.a_center + c) : 0.f; }
+      for (int r0 = 0; r0 < mc; r0 += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + mrow + 8 * u;
+          v[u] = 0.f;
+          if (cok && r < mc) v[u] = __ldg(a.ga + (size_t)(m0 + r) * a.Ca + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + mrow + 8 * u;
+          if (r >= mc) continue;
+          float x = v[u];
+          if (cok) {
+            if (a.a_affine) x = fmaf(x - ce, sc, sh);
+            if (a.a_act) x = lrelu(x, a.a_slope);
+          }
+          As[r * 32 + (tid & 31)] = x;
+        }
+      }
+    }
+    {
+      const int c = cb0 + (tid & 63), mrow = tid >> 6;
+      const bool cok = c < a.Cb;
+      float sc = 1.f, sh = 0.f, ce = 0.f;
+      if (a.b_affine && cok) { sc = __ldg(a.b_scale + c); sh = __ldg(a.b_shift + c); ce = a.b_center ? __ldg(a.b_center + c) : 0.f; }
+      for (int r0 = 0; r0 < mc; r0 += 32) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + mrow + 4 * u;
+          v[u] = 0.f;
+          if (cok && r < mc) v[u] = __ldg(a.db + (size_t)(m0 + r) * a.Cb + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + mrow + 4 * u;
+          if (r >= mc) continue;
+          float x = v[u];
+          if (cok) {
+            if (a.b_affine) x = fmaf(x - ce, sc, sh);
+            if (a.b_act) x = lrelu(x, a.b_slope);
+          }
+          Bs[r * 64 + (tid & 63)] = x;
+        }
+      }
+    }
+    __syncthreads();
 #pragma unroll 4
-  for (int m = 0; m < M; ++m) {
-    const float2 av = *reinterpret_cast<const float2*>(As + m * 32 + ty * 2);
-    const float4 bv = *reinterpret_cast<const float4*>(Bs + m * 64 + tx * 4);
-    acc[0][0] = fmaf(av.x, bv.x, acc[0][0]); acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
-    acc[0][2] = fmaf(av.x, bv.z, acc[0][2]); acc[0][3] = fmaf(av.x, bv.w, acc[0][3]);
-    acc[1][0] = fmaf(av.y, bv.x, acc[1][0]); acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
-    acc[1][2] = fmaf(av.y, bv.z, acc[1][2]); acc[1][3] = fmaf(av.y, bv.w, acc[1][3]);
+    for (int m = 0; m < mc; ++m) {
+      const float2 av = *reinterpret_cast<const float2*>(As + m * 32 + ty * 2);
+      const float4 bv = *reinterpret_cast<const float4*>(Bs + m * 64 + tx * 4);
+      acc[0][0] = fmaf(av.x, bv.x, acc[0][0]); acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
+      acc[0][2] = fmaf(av.x, bv.z, acc[0][2]); acc[0][3] = fmaf(av.x, bv.w, acc[0][3]);
+      acc[1][0] = fmaf(av.y, bv.x, acc[1][0]); acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
+      acc[1][2] = fmaf(av.y, bv.z, acc[1][2]); acc[1][3] = fmaf(av.y, bv.w, acc[1][3]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -395,7 +476,7 @@ int launch_wgrad_small(const WgradArgs& a, int taps, int splits, cudaStream_t st
     wgrad_rows_kernel<<<dim3((a.Cb + 127) / 128, (a.Ca + 63) / 64), 256, 0, st>>>(a, a.K);
     return 1;
   }
-  wgrad_small_kernel<<<dim3((a.Ca + 31) / 32, (a.Cb + 63) / 64), 256, (size_t)a.K * 96 * sizeof(float), st>>>(a, a.K);
+  wgrad_small_kernel<<<dim3((a.Ca + 31) / 32, (a.Cb + 63) / 64), 256, (size_t)min(a.K, 128) * 96 * sizeof(float), st>>>(a, a.K);
   return 1;
 }
 

@@ -245,20 +245,31 @@ static bool window3x3(const GatherArgs& g) {
   return true;
 }
 
+// the same for a 4x4 window with offsets in [-1, 2] at stride 2 (Conv2d k4 s2 p1 forward, ConvTranspose2d k4 s2 p1
+// input gradient: causal_cascade/models.py:9, :36)
+static bool window4x4(const GatherArgs& g) {
+  if (g.nphase != 1 || g.phase[0].ntaps != 16 || g.is != 2 || g.os != 1) return false;
+  for (int t = 0; t < 16; ++t) {
+    const TapEntry& e = g.phase[0].taps[t];
+    if (e.dh < -1 || e.dh > 2 || e.dw < -1 || e.dw > 2) return false;
+  }
+  return true;
+}
+
 // Cs == 1 -> C channels (stem.0 forward: stride 2 + statistics; image-head input gradient: DACT + statistics)
-template <int C, int IS>
+template <int C, int IS, int KW = 3>     // KW = 4: the k4 / s2 / p1 windows of causal_cascade (window4x4 below)
 __global__ void __launch_bounds__(kThreads) conv_cs1_tile_kernel(const __grid_constant__ GatherArgs a, const int patches,
                                                                  const int tiles_h, const int tiles_w) {
-  constexpr int TH = 8, TW = 32, NB = C / 4, PPP = kThreads / NB;
-  constexpr int GR = (TH - 1) * IS + 3, GC = (TW - 1) * IS + 3;
+  constexpr int TH = 8, TW = 32, NB = C / 4, PPP = kThreads / NB, NT = KW * KW;
+  constexpr int GR = (TH - 1) * IS + KW, GC = (TW - 1) * IS + KW;
   __shared__ float sG[GR * GC];
   __shared__ double s_red[kThreads][8];
   const int tid = threadIdx.x, c4 = tid % NB, c0 = c4 * 4, pp = tid / NB;
   const PhaseGeom& P = a.phase[0];
-  float4 w[9];
-  int toff[9];
+  float4 w[NT];
+  int toff[NT];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
+  for (int t = 0; t < NT; ++t) {
     w[t] = __ldg(reinterpret_cast<const float4*>(a.wt + P.taps[t].widx * C + c0));
     toff[t] = (P.taps[t].dh + 1) * GC + P.taps[t].dw + 1;
   }
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) conv_cs1_tile_kernel(const __grid_co
       const float* gp = sG + (r * IS) * GC + c * IS;
       float4 acc = bias;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
+      for (int t = 0; t < NT; ++t) {
         const float v = gp[toff[t]];
         acc.x = fmaf(v, w[t].x, acc.x); acc.y = fmaf(v, w[t].y, acc.y); acc.z = fmaf(v, w[t].z, acc.z); acc.w = fmaf(v, w[t].w, acc.w);
       }
@@ -421,6 +432,95 @@ __global__ void __launch_bounds__(kThreads) conv_cd1_tile_kernel(const __grid_co
   }
 }
 
+// ---- ConvTranspose2d(C -> 1, stride 2) forward with all four output phases in one pass ------------------
+// (causal_cascade / mnist dec_conv tail, k4 s2 p1: causal_cascade/models.py:36).  conv_cd1_kernel ran one grid
+// slice per phase, so every input vector was fetched four times by four different thread groups behind a runtime tap
+// loop (114 us at batch 256 for 33.5 MB of input).  Here C / 4 threads own one input position q: the 3 x 3
+// neighbourhood every phase draws its taps from is requested once, up front (nine 128-bit loads in flight per
+// thread), the four phase sums are reduced over the channel groups with shuffles and leave as a 2 x 2 output block.
+template <int TP>     // threads per position = C / 4 (power of two <= 16)
+__global__ void __launch_bounds__(kThreads) convt_cd1_phases_kernel(const __grid_constant__ GatherArgs a) {
+  __shared__ __align__(16) float s_w[16 * 64];         // [widx][Cs]
+  __shared__ int s_sel[4][9];                          // weight index of (phase, neighbourhood position) or -1
+  const int tid = threadIdx.x, Cs = a.Cs;
+  for (int i = tid; i < a.wtaps * Cs; i += kThreads) s_w[i] = __ldg(a.wt + i);
+  if (tid < 36) {
+    const int ph = tid / 9, pos = tid % 9;
+    int sel = -1;
+    for (int t = 0; t < a.phase[ph].ntaps; ++t)
+      if ((a.phase[ph].taps[t].dh + 1) * 3 + a.phase[ph].taps[t].dw + 1 == pos) sel = a.phase[ph].taps[t].widx;
+    s_sel[ph][pos] = sel;
+  }
+  __syncthreads();
+  const int Hq = a.phase[0].Hq, Wq = a.phase[0].Wq;
+  const int M = a.N * Hq * Wq;
+  const int cg = tid % TP, c0 = cg * 4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = zero, ce = zero;
+  if (a.in_affine) {
+    sc = __ldg(reinterpret_cast<const float4*>(a.in_scale + c0));
+    sh = __ldg(reinterpret_cast<const float4*>(a.in_shift + c0));
+    if (a.in_center) ce = __ldg(reinterpret_cast<const float4*>(a.in_center + c0));
+  }
+  const float bias = a.bias ? __ldg(a.bias) : 0.f;
+  constexpr int ppb = kThreads / TP;
+  const int Mpad = (M + ppb - 1) / ppb * ppb;           // keep whole position groups converged for the shuffles
+  for (int m = blockIdx.x * ppb + tid / TP; m < Mpad; m += gridDim.x * ppb) {
+    const bool live = m < M;
+    const int mm = live ? m : 0;
+    const int qw = mm % Wq;
+    const int t = mm / Wq;
+    const int qh = t % Hq, n = t / Hq;
+    float4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int pos = 0; pos < 9; ++pos) {
+      const int ih = qh + pos / 3 - 1, iw = qw + pos % 3 - 1;
+      ok[pos] = live && (unsigned)ih < (unsigned)a.Hs && (unsigned)iw < (unsigned)a.Ws;
+      v[pos] = zero;
+      if (ok[pos]) v[pos] = __ldg(reinterpret_cast<const float4*>(a.src + (((size_t)n * a.Hs + ih) * a.Ws + iw) * Cs + c0));
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int pos = 0; pos < 9; ++pos) {
+      float4 x = v[pos];
+      if (ok[pos]) x = xform4(x, sc, sh, ce, a.in_affine, a.in_act, a.in_slope);     // padding stays exactly 0
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph) {
+        const int sel = s_sel[ph][pos];
+        if (sel >= 0) {
+          const float4 w = *reinterpret_cast<const float4*>(&s_w[sel * Cs + c0]);
+          acc[ph] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[ph]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+      for (int o = TP >> 1; o > 0; o >>= 1) acc[ph] += __shfl_xor_sync(0xffffffffu, acc[ph], o);
+    if (live && cg < 4) {                               // lane cg of the group writes phase cg
+      const PhaseGeom& P = a.phase[cg];
+      const int oh = qh * 2 + P.ph, ow = qw * 2 + P.pw;
+      const float r = cg == 0 ? acc[0] : cg == 1 ? acc[1] : cg == 2 ? acc[2] : acc[3];
+      if (oh < a.Hd && ow < a.Wd) a.dst[((size_t)n * a.Hd + oh) * a.Wd + ow] = r + bias;
+    }
+  }
+}
+
+// the four phases of a stride-2 transposed convolution whose taps all lie in the 3 x 3 neighbourhood of the input position
+static bool convt_phases3x3(const GatherArgs& g) {
+  if (g.nphase != 4 || g.os != 2 || g.is != 1) return false;
+  for (int ph = 0; ph < 4; ++ph) {
+    const PhaseGeom& P = g.phase[ph];
+    if (P.Hq != g.phase[0].Hq || P.Wq != g.phase[0].Wq || P.Hq > g.Hs || P.Wq > g.Ws) return false;
+    for (int t = 0; t < P.ntaps; ++t)
+      if (P.taps[t].dh < -1 || P.taps[t].dh > 1 || P.taps[t].dw < -1 || P.taps[t].dw > 1) return false;
+    for (int q = 0; q < ph; ++q)
+      if (g.phase[q].ph == P.ph && g.phase[q].pw == P.pw) return false;
+  }
+  return true;
+}
+
 static inline int stream_grid(int64_t pixels, int tp) {
   const int64_t ppb = kThreads / tp;
   int64_t b = (pixels + ppb - 1) / ppb;
@@ -444,6 +544,13 @@ bool launch_conv_cs1(const GatherArgs& g, int maxM, cudaStream_t st) {
     else conv_cs1_tile_kernel<32, 2><<<grid, kThreads, 0, st>>>(g, patches, tiles_h, tiles_w);
     return true;
   }
+  if (window4x4(g) && maxM >= 65536 && g.Cd == 32) {     // causal_cascade at its training batch: 92 / 104 us on the streaming kernel
+    const PhaseGeom& P = g.phase[0];
+    const int tiles_h = (P.Hq + 7) / 8, tiles_w = (P.Wq + 31) / 32;
+    const int patches = g.N * tiles_h * tiles_w, grid = min(patches, kNumSMs * 6);
+    conv_cs1_tile_kernel<32, 2, 4><<<grid, kThreads, 0, st>>>(g, patches, tiles_h, tiles_w);
+    return true;
+  }
   conv_cs1_kernel<<<dim3(stream_grid(maxM, tp), 1, g.nphase), kThreads, 0, st>>>(g);
   return true;
 }
@@ -463,6 +570,16 @@ bool launch_conv_cd1(const GatherArgs& g, int maxM, cudaStream_t st) {
     const size_t smem = sizeof(float4) * (4 * 18 * 34 + 9 * 4);
     conv_cd1_tile_kernel<16><<<min(patches, kNumSMs * 4), kThreads, smem, st>>>(g, patches, tiles_h, tiles_w);
     return true;
+  }
+  if (convt_phases3x3(g) && tp >= 4 && tp <= 16) {
+    static const bool on = [] { const char* e = getenv("CVAE_CONVT_PHASES"); return !(e && e[0] == '0'); }();
+    if (on) {
+      const int grid = stream_grid(maxM, tp);
+      if (tp == 4) convt_cd1_phases_kernel<4><<<grid, kThreads, 0, st>>>(g);
+      else if (tp == 8) convt_cd1_phases_kernel<8><<<grid, kThreads, 0, st>>>(g);
+      else convt_cd1_phases_kernel<16><<<grid, kThreads, 0, st>>>(g);
+      return true;
+    }
   }
   conv_cd1_kernel<<<dim3(stream_grid(maxM, tp), 1, g.nphase), kThreads, 0, st>>>(g);
   return true;

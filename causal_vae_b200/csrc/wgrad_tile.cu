@@ -44,14 +44,14 @@ __device__ __forceinline__ void stv(float* p, const VecT<V>& r) {
   else *p = r.v[0];
 }
 
-template <int CA, int CB, int S>
+template <int CA, int CB, int S, int KW = 3>       // KW: window size (3, or 4 for the Conv2d / ConvTranspose2d(k4, s2, p1) layers of causal_cascade)
 __global__ void __launch_bounds__(kWtThreads, wt_ctas_per_sm(CA, CB))
 wgrad_tile_kernel(const __grid_constant__ WgradArgs a, const int patches, const int tiles_h, const int tiles_w) {
   constexpr int VA = CA >= 4 ? 4 : 1, VB = CB >= 4 ? 4 : 1;
   constexpr int NA = CA / VA, NB = CB / VB;
-  constexpr int T1 = 3 * NA * NB;                  // threads covering every (dh, ca-group, cb-group)
+  constexpr int T1 = KW * NA * NB;                 // threads covering every (dh, ca-group, cb-group)
   constexpr int PS = kWtThreads / T1;              // pixel subsets
-  constexpr int GR = (kWtTH - 1) * S + 3, GC = (kWtTW - 1) * S + 3;
+  constexpr int GR = (kWtTH - 1) * S + KW, GC = (kWtTW - 1) * S + KW;
   constexpr int NPIX = kWtTH * kWtTW;
   static_assert(T1 <= kWtThreads, "tile does not fit the block");
   extern __shared__ __align__(16) float smem[];
@@ -80,9 +80,9 @@ wgrad_tile_kernel(const __grid_constant__ WgradArgs a, const int patches, const 
   const bool active = tid < PS * T1;
   const int ps = tid / T1, t1 = tid % T1;
   const int cb_i = t1 % NB, ca_i = (t1 / NB) % NA, dh = t1 / (NB * NA);
-  float acc[3][VA][VB];
+  float acc[KW][VA][VB];
 #pragma unroll
-  for (int w = 0; w < 3; ++w)
+  for (int w = 0; w < KW; ++w)
 #pragma unroll
     for (int i = 0; i < VA; ++i)
 #pragma unroll
@@ -176,7 +176,7 @@ wgrad_tile_kernel(const __grid_constant__ WgradArgs a, const int patches, const 
         const VecT<VB> d = ldv<VB>(sD + pix * CB + cb_i * VB);
         const float* gp = sG + ((r * S + dh) * GC + c * S) * CA + ca_i * VA;
 #pragma unroll
-        for (int w = 0; w < 3; ++w) {
+        for (int w = 0; w < KW; ++w) {
           const VecT<VA> g = ldv<VA>(gp + w * CA);
 #pragma unroll
           for (int i = 0; i < VA; ++i)
@@ -192,27 +192,27 @@ wgrad_tile_kernel(const __grid_constant__ WgradArgs a, const int patches, const 
   if constexpr (PS == 1) {
     if (active) {
 #pragma unroll
-      for (int w = 0; w < 3; ++w)
+      for (int w = 0; w < KW; ++w)
 #pragma unroll
         for (int i = 0; i < VA; ++i) {
           VecT<VB> v;
 #pragma unroll
           for (int j = 0; j < VB; ++j) v.v[j] = acc[w][i][j];
-          stv<VB>(out + (size_t)((dh * 3 + w) * CA + ca_i * VA + i) * a.Cb + cb0 + cb_i * VB, v);
+          stv<VB>(out + (size_t)((dh * KW + w) * CA + ca_i * VA + i) * a.Cb + cb0 + cb_i * VB, v);
         }
     }
   } else {
-    constexpr int OUT = 9 * CA * CB;
+    constexpr int OUT = KW * KW * CA * CB;
     float* sR = smem;                              // [PS][9*CA][CB]  (the tiles are dead: last loop barrier passed)
     if (active) {
 #pragma unroll
-      for (int w = 0; w < 3; ++w)
+      for (int w = 0; w < KW; ++w)
 #pragma unroll
         for (int i = 0; i < VA; ++i) {
           VecT<VB> v;
 #pragma unroll
           for (int j = 0; j < VB; ++j) v.v[j] = acc[w][i][j];
-          stv<VB>(sR + ps * OUT + ((dh * 3 + w) * CA + ca_i * VA + i) * CB + cb_i * VB, v);
+          stv<VB>(sR + ps * OUT + ((dh * KW + w) * CA + ca_i * VA + i) * CB + cb_i * VB, v);
         }
     }
     __syncthreads();
@@ -229,22 +229,22 @@ wgrad_tile_kernel(const __grid_constant__ WgradArgs a, const int patches, const 
   }
 }
 
-template <int CA, int CB, int S>
+template <int CA, int CB, int S, int KW = 3>
 static int launch_tile(const WgradArgs& a, cudaStream_t st) {
-  constexpr int GR = (kWtTH - 1) * S + 3, GC = (kWtTW - 1) * S + 3;
-  constexpr int VA = CA >= 4 ? 4 : 1, VB = CB >= 4 ? 4 : 1, PS = kWtThreads / (3 * (CA / VA) * (CB / VB));
+  constexpr int GR = (kWtTH - 1) * S + KW, GC = (kWtTW - 1) * S + KW;
+  constexpr int VA = CA >= 4 ? 4 : 1, VB = CB >= 4 ? 4 : 1, PS = kWtThreads / (KW * (CA / VA) * (CB / VB));
   size_t floats = (size_t)((GR * GC * CA + 3) & ~3) + (size_t)kWtTH * kWtTW * CB;
-  if (PS > 1) floats = max(floats, (size_t)PS * 9 * CA * CB);
+  if (PS > 1) floats = max(floats, (size_t)PS * KW * KW * CA * CB);
   const size_t smem = sizeof(float) * floats;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_tile_kernel<CA, CB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(wgrad_tile_kernel<CA, CB, S, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
       return CVAE_ERR_LAUNCH;
     attr_set = true;
   }
   const int tiles_h = (a.Hq + kWtTH - 1) / kWtTH, tiles_w = (a.Wq + kWtTW - 1) / kWtTW;
   const int patches = a.N * tiles_h * tiles_w;
-  wgrad_tile_kernel<CA, CB, S><<<dim3(kNumSMs * wt_ctas_per_sm(CA, CB), a.Cb / CB), kWtThreads, smem, st>>>(a, patches, tiles_h, tiles_w);
+  wgrad_tile_kernel<CA, CB, S, KW><<<dim3(kNumSMs * wt_ctas_per_sm(CA, CB), a.Cb / CB), kWtThreads, smem, st>>>(a, patches, tiles_h, tiles_w);
   return CVAE_OK;
 }
 
@@ -256,6 +256,9 @@ using namespace cvae;
 
 // > 0: the K-split count the tiled kernel needs (size of the partial buffer) when it covers the shape; 0 otherwise.
 extern "C" int cvae_wgrad_tile_splits(int pixels, int Ca, int Cb, int k, int stride, int pad) {
+  // 4x4 / stride 2 / pad 1 with one channel on the image side: first Conv2d and last ConvTranspose2d of causal_cascade
+  // (causal_cascade/models.py:9, :36); were 160-176 us each on the streaming fallback at batch 256
+  if (k == 4) return (stride == 2 && pad == 1 && Ca == 1 && Cb == 32 && pixels >= 32768) ? kNumSMs * wt_ctas_per_sm(1, 32) : 0;
   if (k != 3 || pad != 1 || (stride != 1 && stride != 2)) return 0;
   if (!(Ca == 1 || Ca == 16 || Ca == 32) || !(Cb == 1 || Cb == 16 || Cb == 32 || Cb == 64)) return 0;
   if (Ca == 1 && Cb == 1) return 0;
@@ -268,7 +271,7 @@ extern "C" int cvae_wgrad_tile_splits(int pixels, int Ca, int Cb, int k, int str
 
 extern "C" int cvae_conv_wgrad_tile(const cvae_wgrad_params_t* p, cvae_stream_t s) {
   if (!p || !p->ga || !p->db || !p->partial) return CVAE_ERR_BAD_ARG;
-  if (p->kh != 3 || p->kw != 3) return CVAE_ERR_UNSUPPORTED_SHAPE;
+  if (p->kh != p->kw || (p->kh != 3 && p->kh != 4)) return CVAE_ERR_UNSUPPORTED_SHAPE;
   const int need = cvae_wgrad_tile_splits(p->N * p->Hq * p->Wq, p->Ca, p->Cb, p->kh, p->stride, p->pad);
   if (need == 0) return CVAE_ERR_UNSUPPORTED_SHAPE;
   if (p->splits != need) return CVAE_ERR_BAD_ARG;
@@ -283,11 +286,17 @@ extern "C" int cvae_conv_wgrad_tile(const cvae_wgrad_params_t* p, cvae_stream_t 
   a.partial = p->partial;
   a.N = p->N; a.Ha = p->Ha; a.Wa = p->Wa; a.Ca = p->Ca; a.Hq = p->Hq; a.Wq = p->Wq; a.Cb = p->Cb;
   a.kw = p->kw; a.stride = p->stride; a.pad = p->pad;
-  a.rows = 9 * p->Ca;
+  a.rows = p->kh * p->kw * p->Ca;
   a.K = p->N * p->Hq * p->Wq; a.kchunk = 0;
   cudaStream_t st = as_stream(s);
   const int cbs = tile_cb_slice(p->Cb);
   int rc = CVAE_ERR_UNSUPPORTED_SHAPE;
+  if (p->kh == 4) {
+    rc = launch_tile<1, 32, 2, 4>(a, st);
+    if (rc != CVAE_OK) return rc;
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+  }
 #define CVAE_WT(ca, cb)                                                                      \
   if (p->Ca == ca && cbs == cb) rc = p->stride == 1 ? launch_tile<ca, cb, 1>(a, st) : launch_tile<ca, cb, 2>(a, st);
   CVAE_WT(1, 16) CVAE_WT(1, 32) CVAE_WT(16, 1) CVAE_WT(16, 16) CVAE_WT(16, 32) CVAE_WT(32, 1) CVAE_WT(32, 16) CVAE_WT(32, 32)

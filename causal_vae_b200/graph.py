@@ -4,8 +4,12 @@ These steps are launch-bound (whole-network activations of 0.17 / 1.0
 replay per step replaces a few hundred enqueues.  VesselTrainer keeps its own capture (side streams, early
 all-reduce); this helper covers the plain single-stream steps."""
 import gc
+import os
 
 import torch
+
+from . import ops
+from .chain import direct_grads, side_wgrad
 
 
 class GraphedStep:
@@ -51,3 +55,49 @@ def trainer_state(models, opts):
     for m in models:
         out += [b for b in m.buffers()]
     return out
+
+
+class StepScope:
+    """What VesselTrainer does around its forward + backward, for the single-optimizer small trainers:
+
+    * the step's small fp64 accumulators come from one arena zeroed by one launch (ops.arena_begin);
+    * every weight re-layout of the step is recorded on the first step and replayed as ONE launch at the start of each
+      later step (ops.PackPlan; the latent_translator step spent 80 launches / 0.34 ms on per-use packs);
+    * in backward the weight-gradient kernels run on a side stream, forked per layer and joined before the optimizer
+      (chain.side_wgrad): a layer's weight and input gradients are independent, and most grids of these models leave
+      SMs idle.  The fork / join pattern is captured when the step is captured in a CUDA graph.
+
+        with scope:                      # forward + loss + backward
+            out = model(...); loss = ...
+            with scope.backward():
+                loss.backward()
+
+    CVAE_SMALL_SCOPE=0 turns the plan and the side stream off (A/B runs)."""
+
+    def __init__(self, device):
+        on = os.environ.get("CVAE_SMALL_SCOPE", "1") != "0"
+        self.device = device
+        self.plan = ops.PackPlan() if on else None
+        self.side = torch.cuda.Stream(device) if on and os.environ.get("CVAE_SMALL_SIDE", "1") != "0" else None
+
+    def __enter__(self):
+        ops.arena_begin(self.device)
+        if self.plan is not None:
+            ops.set_pack_plan(self.plan)
+            if not self.plan.recording:
+                self.plan.run()
+        return self
+
+    def __exit__(self, *exc):
+        ops.arena_end()
+        ops.set_pack_plan(None)
+        if self.plan is not None and self.plan.recording and exc[0] is None:
+            self.plan.finalize()
+        return False
+
+    def backward(self):
+        import contextlib
+        st = contextlib.ExitStack()
+        st.enter_context(direct_grads())
+        st.enter_context(side_wgrad(self.side))
+        return st

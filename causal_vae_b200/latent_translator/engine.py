@@ -4,8 +4,7 @@ import numpy as np
 import torch
 
 from .. import functional as F
-from ..chain import direct_grads
-from ..graph import GraphedStep, trainer_state
+from ..graph import GraphedStep, StepScope, trainer_state
 from ..optim import FlatParams, FusedClipAdam
 from ..parallel import allreduce_gradients
 
@@ -32,15 +31,17 @@ class ViTVAETrainer:
         self.opt = FusedClipAdam(FlatParams(model), lr, grad_scale=grad_scale)
         self.rng = F.RngState(counter=self.opt.step_count, rank=rank)         # this trainer's dropout generator
         self.graphed = None
+        self.scope = StepScope(self.opt.flat.data.device)
 
     def step(self, x, eps=None):
         self.model.train()
         self.opt.zero_grad()
-        with F.use_rng(self.rng):
-            recons, _, mu, log_var = self.model(x, eps)
-        loss, rl, kl = loss_function(recons, x, mu, log_var, self.beta)
-        with direct_grads():
-            loss.backward()
+        with self.scope:
+            with F.use_rng(self.rng):
+                recons, _, mu, log_var = self.model(x, eps)
+            loss, rl, kl = loss_function(recons, x, mu, log_var, self.beta)
+            with self.scope.backward():
+                loss.backward()
         if self.distributed:
             allreduce_gradients(self.opt.flat.grad, group=self.pg)
         self.opt.step()

@@ -92,6 +92,8 @@ CONV_CASES = [
     (128, 256, 3, 2, 1, 8, 8, 5),
     (16, 16, 3, 2, 1, 256, 256, 4),   # image-sized 16 -> 16 stride 2: fp32 tile kernel (conv_few.cu)
     (16, 16, 3, 2, 1, 200, 144, 10),  # the same with ragged tiles
+    (1, 32, 4, 2, 1, 64, 64, 70),     # causal_cascade enc_conv.0 at a training-sized batch: 4x4 tile kernels (fwd, wgrad)
+    (1, 32, 4, 2, 1, 50, 44, 130),    # the same with ragged tiles
 ]
 
 
@@ -113,6 +115,8 @@ CONVT_CASES = [
     (16, 16, 3, 2, 1, 1, 100, 72, 10),   # the same with ragged tiles
     (64, 32, 4, 2, 1, 0, 7, 7, 3),    # mnist dec_conv.0
     (32, 1, 4, 2, 1, 0, 14, 14, 3),   # mnist dec_conv.2 (Cout = 1)
+    (32, 1, 4, 2, 1, 0, 32, 32, 70),  # causal_cascade dec_conv.6 at a training-sized batch: 4x4 tile kernels (input gradient, wgrad)
+    (32, 1, 4, 2, 1, 0, 25, 22, 130), # the same with ragged tiles
 ]
 
 
@@ -126,7 +130,9 @@ def test_conv_transpose2d(case):
              lambda P, xx: O._convT({"c.weight": P["weight"], "c.bias": P["bias"]}, "c", xx, s, p, op), x)
 
 
-@pytest.mark.parametrize("shape", [(64, 287, 512), (7, 19, 64), (130, 256, 768), (5, 512, 1024), (64, 64, 12)])
+@pytest.mark.parametrize("shape", [(64, 287, 512), (7, 19, 64), (130, 256, 768), (5, 512, 1024), (64, 64, 12),
+                                   # causal_cascade trains at batch 256: row blocks of the few-row kernels (linear_small.cu)
+                                   (256, 4124, 512), (256, 64, 12), (200, 76, 4096), (300, 512, 256), (129, 20, 64)])
 def test_linear(shape):
     from causal_vae_b200 import nn
     B, K, N = shape
