@@ -208,8 +208,12 @@ __device__ __forceinline__ void lr_load_w(float (*ws)[128], const float* __restr
 
 // y[m][n] (+)= sum_k xf(x[m][k]) * w[k][n];  grid (Cd / 128, K splits, row blocks of 64)
 __global__ void __launch_bounds__(256) linear_rows_kernel(const __grid_constant__ GatherArgs a, const int M, const int kper) {
+  // weights: a ring of kLrWS chunks by cp.async, kLrWS - 1 of them in flight (with two buffers a CTA had ONE 8 KB chunk in
+  // flight: 128 CTAs x 8 KB against the ~6 MB that the HBM rate x latency asks for -- decoder_input's 33.5 MB of weights
+  // took 40 us); x (a few rows, L2-resident) stays double-buffered through registers
+  constexpr int kLrWS = 4;
   __shared__ __align__(16) float xs[2][kLrK][68];
-  __shared__ __align__(16) float ws[2][kLrK][128];
+  __shared__ __align__(16) float ws[kLrWS][kLrK][128];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int n0 = blockIdx.x * 128, m0 = blockIdx.z * 64;
   const int kbeg = blockIdx.y * kper, kend = min(a.Cs, kbeg + kper);
@@ -238,22 +242,22 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const __grid_constant_
   };
   auto store_x = [&](int b, const float4 v) { xs[b][xk][xm] = v.x; xs[b][xk + 1][xm] = v.y; xs[b][xk + 2][xm] = v.z; xs[b][xk + 3][xm] = v.w; };
   const int nch = (kend - kbeg + kLrK - 1) / kLrK;
-  if (nch > 0) {
-    store_x(0, load_x(kbeg));
-    lr_load_w(ws[0], a.wt, kbeg, kend, n0, a.Cd, tid);
+  if (nch > 0) store_x(0, load_x(kbeg));
+#pragma unroll
+  for (int s = 0; s < kLrWS - 1; ++s) {              // one commit group per chunk slot, empty past the end: uniform counts
+    if (s < nch) lr_load_w(ws[s], a.wt, kbeg + s * kLrK, kend, n0, a.Cd, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int c = 0; c < nch; ++c) {
     const int b = c & 1;
     float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c + 1 < nch) {
-      xn = load_x(kbeg + (c + 1) * kLrK);
-      lr_load_w(ws[b ^ 1], a.wt, kbeg + (c + 1) * kLrK, kend, n0, a.Cd, tid);
-    }
+    if (c + 1 < nch) xn = load_x(kbeg + (c + 1) * kLrK);
+    if (c + kLrWS - 1 < nch)                         // into the slot chunk c - 1 left (its reads ended before the last barrier)
+      lr_load_w(ws[(c + kLrWS - 1) % kLrWS], a.wt, kbeg + (c + kLrWS - 1) * kLrK, kend, n0, a.Cd, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(kLrWS - 1) : "memory");
     __syncthreads();
-    lr_fma_chunk(xs[b], ws[b], ty, tx, acc);
+    lr_fma_chunk(xs[b], ws[c % kLrWS], ty, tx, acc);
     if (c + 1 < nch) store_x(b ^ 1, xn);
     __syncthreads();
   }
