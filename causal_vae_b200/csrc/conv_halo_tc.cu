@@ -67,6 +67,8 @@ struct HaloPlan {
   int prefetch;               // 1: the loader warp requests epilogue reference rows / next halo tiles into L2
   int na;                     // A ring depth (stages of kHAStage bytes in shared memory, or 64-column stages in tensor memory)
   int xacc;                   // 1: cross terms (hi*lo' + lo*hi') in their own accumulator columns [BN, 2BN) -- see the MMA issuer
+  int ksplit;                 // Linear mode: CTAs per output tile, each taking KB / ksplit k-blocks and adding its part into the
+                              // pre-zeroed output (1: plain stores) -- see launch_conv_halo_tc
   HaloPlane plane[4];
 };
 
@@ -84,9 +86,11 @@ __device__ unsigned long long g_halo_dbg[16];
 
 __device__ __forceinline__ void hbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-struct HTile { int n, h0, w0, n0; };
+struct HTile { int n, h0, w0, n0, ks; };
 __device__ __forceinline__ HTile h_decode(const HaloPlan& p, int t) {
   HTile o;
+  o.ks = 0;
+  if (p.ksplit > 1) { o.ks = t % p.ksplit; t /= p.ksplit; }      // work item = (tile, K slice)
   o.n0 = (t % p.tiles_n) * p.BN;
   int sp = t / p.tiles_n;
   o.w0 = (sp % p.tiles_w) * kHTW; sp /= p.tiles_w;
@@ -162,13 +166,15 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       const uint32_t raw_warp = smem_u32(dsm_gen + (size_t)NB * bstage + (size_t)(tid - lane) * kPitch);
       const int crow = lane / kCh, cch = lane % kCh;   // this lane's row (within an instruction) and chunk
       const long long Mrows = (long long)a.Hs * 8;     // Linear view: ONE image of M / 8 x 8 positions, a tile = 128 consecutive rows
-      int ti = blockIdx.x, kbi = 0;                    // next (tile, k-block) to request
+      const int kbper = KB / p.ksplit;                 // k-blocks of one work item (host: KB % ksplit == 0)
+      int ti = blockIdx.x, kbi = 0, kbend = 0;         // next (tile, k-block) to request; end of the item's K slice
       const float* wbase = nullptr;                    // first row of this warp quarter in tile ti
       int nvalid = 0;                                  // rows of the quarter inside the matrix
       auto set_tile = [&](int t) {
         wbase = nullptr; nvalid = 0;
         if (t >= total) return;
         const HTile tl = h_decode(p, t);
+        kbi = tl.ks * kbper; kbend = kbi + kbper;
         const long long r0 = (long long)tl.h0 * 8 + q * 32;
         wbase = a.src + (size_t)r0 * a.Cs;
         const long long left = Mrows - r0;
@@ -188,7 +194,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
             else
               asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
           }
-          if (++kbi == KB) { kbi = 0; ti += gridDim.x; set_tile(ti); }
+          if (++kbi == kbend) { ti += gridDim.x; set_tile(ti); }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");     // always: one group per iteration keeps the count uniform
       };
@@ -200,7 +206,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         const HTile tl = h_decode(p, t);
         const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
         const bool rok = qh < a.Hs && qw < a.Ws;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
+        for (int kb = tl.ks * kbper; kb < (tl.ks + 1) * kbper; ++kb, ++it) {
           issue((int)((it + kHRawStages - 1) % kHRawStages));
           T_WAIT(1, asm volatile("cp.async.wait_group %0;" ::"n"(kHRawStages - 1) : "memory"))
           __syncwarp();                                  // the row was copied by other lanes of this warp
@@ -280,7 +286,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       return st;
     };
     int ld_t = -1;
-    HTile ld_tl{0, 0, 0, 0};
+    HTile ld_tl{0, 0, 0, 0, 0};
     auto load_stage = [&](const Stage& st, float4 (&v)[kHItems]) -> uint32_t {
       uint32_t okm = 0;
       if (st.t != ld_t) { ld_tl = h_decode(p, st.t); ld_t = st.t; }
@@ -393,7 +399,8 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         tc_fence_after();
         const uint32_t d_base = tmem + acc * acc_cols;
         uint32_t started = 0, startedx = 0;
-        for (int kb = 0; kb < KB; ++kb) {
+        const int kbper = KB / p.ksplit, kb0 = p.ksplit > 1 ? (t % p.ksplit) * kbper : 0;
+        for (int kb = kb0; kb < kb0 + kbper; ++kb) {
           const int ksteps = min(32, a.Cs - kb * 32) >> 3;
           for (int pl = 0; pl < p.nplanes; ++pl, ++ita) {
             const HaloPlane& P = p.plane[pl];
@@ -551,9 +558,10 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         __syncwarp();
       }
       if (ld_leader) {
-        const int n0 = (t % p.tiles_n) * BN;
-        const int mt = t / p.tiles_n;                  // a_pre: 128-row tile of the packed A image
-        for (int kb = 0; kb < KB; ++kb)
+        const int tt = t / p.ksplit, kbper = KB / p.ksplit, kb0 = (t % p.ksplit) * kbper;
+        const int n0 = (tt % p.tiles_n) * BN;
+        const int mt = tt / p.tiles_n;                 // a_pre: 128-row tile of the packed A image
+        for (int kb = kb0; kb < kb0 + kbper; ++kb)
           for (int pl = 0; pl < p.nplanes; ++pl) {
             if (p.a_pre) {                             // this k-block's A stage: hi and lo planes, 16 KB each
               const int aslot = ita % na;
@@ -620,13 +628,14 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
     const bool has_add = dact && a.epi_add != nullptr;
     const int ostep = a.os * a.Wd;                    // pixel distance between a thread's consecutive rows
     double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
-    struct Unit { int obase, vmask, col, t, ui; };
+    struct Unit { int obase, vmask, col, t, ui, ks; };
     HTile ctl = h_decode(p, blockIdx.x);
     int ct = blockIdx.x;
     auto unit_of = [&](int t, int ui) -> Unit {
-      Unit u{0, 0, 0, t, ui};
+      Unit u{0, 0, 0, t, ui, 0};
       if (t >= total || ui >= nunits) return u;
       if (t != ct) { ctl = h_decode(p, t); ct = t; }
+      u.ks = ctl.ks;
       const int phs = ui >> upp_sh, hf = ui - (phs << upp_sh);
       u.col = ctl.n0 + hf * 16 + cpair;
       const int qh = ctl.h0 + 4 * q, qw = ctl.w0 + rw;
@@ -689,7 +698,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 2; ++g) {                 // the thread's two channel pairs: col + 8g, col + 8g + 1
           float2 bias = make_float2(0.f, 0.f), esc = make_float2(1.f, 1.f), esh = bias, ece = bias;
-          if (a.bias != nullptr) bias = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * g));
+          if (a.bias != nullptr && cur.ks == 0) bias = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * g));   // once per tile
           if (a.e_affine) {
             esc = __ldg(reinterpret_cast<const float2*>(a.e_scale + col + 8 * g));
             esh = __ldg(reinterpret_cast<const float2*>(a.e_shift + col + 8 * g));
@@ -721,7 +730,9 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
                 f1[2 * g] += x0; f2[2 * g] = fmaf(x0, rc0, f2[2 * g]);
                 f1[2 * g + 1] += x1; f2[2 * g + 1] = fmaf(x1, rc1, f2[2 * g + 1]);
               }
-              *reinterpret_cast<float2*>(a.dst + (size_t)(cur.obase + r * ostep) * a.Cd + col + 8 * g) = make_float2(x0, x1);
+              float* op = a.dst + (size_t)(cur.obase + r * ostep) * a.Cd + col + 8 * g;
+              if (p.ksplit > 1) { atomicAdd(op, x0); atomicAdd(op + 1, x1); }       // K slices meet in the pre-zeroed output
+              else *reinterpret_cast<float2*>(op) = make_float2(x0, x1);
             }
           }
         }
@@ -980,8 +991,25 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
     static const int min_util = [] { const char* e = getenv("CVAE_HALO_MIN_UTIL"); return e ? atoi(e) : 40; }();
     if (g.wtaps >= 2 && 100ll * hp.Hq * hp.Wq < (long long)min_util * hp.tiles_h * hp.tiles_w * kHTH * kHTW) return 1;
   }
-  const long long total = (long long)g.N * hp.tiles_h * hp.tiles_w * hp.tiles_n;
+  long long total = (long long)g.N * hp.tiles_h * hp.tiles_w * hp.tiles_n;
   if (total >= (1ll << 31)) return 1;
+  // Linear launches whose tiles leave three quarters of the SMs idle and whose K loop is long (latent_translator fc2 and the
+  // input gradient of fc1: K = 1024, 34 tiles at M = 2176): two CTAs per tile, each with half of the k-blocks, adding into
+  // the pre-zeroed output.  Two addends meet a zero, so the sum does not depend on their order (bitwise reproducible).
+  // Measured (scripts/ab_small.py / ab_step.py, CVAE_LIN_KSPLIT=1 turns it off): latent_translator step 5.88 -> 5.77 ms; the
+  // vessel step's 66-tile launches (M = 4160) LOSE with it (7.58 -> 7.63 ms: the zeroing launch and the atomics cost more
+  // than the shorter K loop returns, and in backward the idle SMs were already taken by the weight-gradient stream), hence
+  // the quarter-of-the-machine threshold.
+  hp.ksplit = 1;
+  {
+    static const int ks_env = [] { const char* e = getenv("CVAE_LIN_KSPLIT"); return e ? atoi(e) : 2; }();
+    const int KBh = (g.Cs + 31) / 32;
+    if (ks_env == 2 && hp.a_tmem && g.epi == CVAE_EPI_PLAIN && 4 * total <= kNumSMs && KBh >= 16 && KBh % 2 == 0 && g.Cs % 32 == 0) {
+      if (cudaMemsetAsync(g.dst, 0, sizeof(float) * (size_t)g.Hd * 8 * g.Cd, st) != cudaSuccess) return CVAE_ERR_LAUNCH;
+      hp.ksplit = 2;
+      total *= 2;
+    }
+  }
   // A ring: tensor memory in Linear mode; else as many shared-memory stages (2 or 3) as fit beside the weight ring --
   // the producers issue a stage's global loads before they wait for its slot, so a deeper ring is more DRAM latency hidden
   static const bool pf = [] { const char* e = getenv("CVAE_HALO_PREFETCH"); return e && e[0] == '1'; }();
