@@ -139,7 +139,9 @@ def test_tc_conv_transpose2d_module(case):
              lambda P, xx: O._convT({"c.weight": P["weight"], "c.bias": P["bias"]}, "c", xx, s, p, op), x)
 
 
-@pytest.mark.parametrize("shape", [(2048, 256, 768), (1300, 512, 256)])
+@pytest.mark.parametrize("shape", [(2048, 256, 768), (1300, 512, 256),
+                                   # few tiles and a long K loop: two CTAs per tile, K halves meet in the zeroed output
+                                   (2176, 1024, 256), (1096, 512, 128)])
 def test_tc_linear_module(shape):
     from causal_vae_b200 import nn
     B, K, N = shape
