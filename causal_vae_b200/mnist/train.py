@@ -4,7 +4,7 @@ mnist_test/06_model_experiment/train.py:41-96) on the native kernels: discrimina
 import torch
 
 from .. import functional as F
-from ..graph import GraphedStep, trainer_state
+from ..graph import GraphedStep, StepScope, trainer_state
 from ..optim import FlatParams, FusedClipAdam
 from ..parallel import allreduce_gradients
 from .models import CONFIG
@@ -37,25 +37,46 @@ def disc_loss(vae, disc, x, m, t, eps=None):
 class AdversarialTrainer:
     """opt_d / opt_vae = Adam(lr=CONFIG['LR']) over flat parameter buffers (train.py:21-22)."""
 
-    def __init__(self, vae, disc, lr=None, distributed=False, process_group=None):
+    def __init__(self, vae, disc, lr=None, distributed=False, process_group=None, fused=True):
         lr = CONFIG["LR"] if lr is None else lr
         self.vae, self.disc = vae, disc
         self.distributed, self.pg = distributed, process_group
         self.graphed = None
         self.opt_vae = FusedClipAdam(FlatParams(vae), lr)
         self.opt_d = FusedClipAdam(FlatParams(disc), lr)
+        # Each half of the step has its own scope (graph.StepScope: fp64 arena, one-launch weight packing, parameter
+        # gradients written in place, weight-gradient kernels on a side stream): the discriminator's weights change
+        # between the halves, so the layouts of the second half are packed after opt_d.step().  In both halves every
+        # parameter is used once; the second half also leaves gradients in the discriminator's buffer, as the reference's
+        # loss_vae.backward() does -- opt_d.zero_grad() clears them at the start of the next step.  fused=False keeps the
+        # plain autograd accumulation (the checker of tests/test_families_gpu.py).
+        dev = self.opt_vae.flat.data.device
+        self.scope_d = StepScope(dev) if fused else None
+        self.scope_v = StepScope(dev) if fused else None
 
     def step(self, x, m, t, eps_d=None, eps=None, eps_adv=None):
         self.vae.train(); self.disc.train()
         self.opt_d.zero_grad()
-        loss_d = disc_loss(self.vae, self.disc, x, m, t, eps_d)
-        loss_d.backward()
+        if self.scope_d is not None:
+            with self.scope_d:
+                loss_d = disc_loss(self.vae, self.disc, x, m, t, eps_d)
+                with self.scope_d.backward():
+                    loss_d.backward()
+        else:
+            loss_d = disc_loss(self.vae, self.disc, x, m, t, eps_d)
+            loss_d.backward()
         if self.distributed:        # CE is batch-MEAN reduced (train.py:55): average the shard gradients
             allreduce_gradients(self.opt_d.flat.grad, group=self.pg, mean=True)
         self.opt_d.step()
         self.opt_vae.zero_grad()
-        losses = vae_loss(self.vae, self.disc, x, m, t, eps, eps_adv)
-        losses[0].backward()
+        if self.scope_v is not None:
+            with self.scope_v:
+                losses = vae_loss(self.vae, self.disc, x, m, t, eps, eps_adv)
+                with self.scope_v.backward():
+                    losses[0].backward()
+        else:
+            losses = vae_loss(self.vae, self.disc, x, m, t, eps, eps_adv)
+            losses[0].backward()
         if self.distributed:        # sum-reduced terms: SUM (the batchmean confusion term is left per shard)
             allreduce_gradients(self.opt_vae.flat.grad, group=self.pg)
         self.opt_vae.step()
