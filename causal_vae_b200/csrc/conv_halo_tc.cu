@@ -1027,8 +1027,10 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   // measured on the vessel step (B = 64): 8 everywhere 8.23 ms, 6 for every activation-derivative launch 8.38 ms, 6 everywhere
   // 8.69 ms -- the 6-warp form only pays on the HBM-shaped scatter launches with few channels (stem.3 input gradient
   // 175 -> 152 us), so that is where it is used
-  const int pw = pw_env == 6 || pw_env == 8 ? pw_env
-                 : ((g.epi == CVAE_EPI_DACT && g.nphase > 1 && g.Cd <= 32 && !hp.a_tmem && !hp.a_pre) ? 6 : 8);
+  static const int pw10 = [] { const char* e = getenv("CVAE_HALO_PW10"); return e ? atoi(e) : 0; }();   // 1: forward-type conv launches, 2: + DACT ones
+  int pw = pw_env == 6 || pw_env == 8 || pw_env == 10 ? pw_env
+           : ((g.epi == CVAE_EPI_DACT && g.nphase > 1 && g.Cd <= 32 && !hp.a_tmem && !hp.a_pre) ? 6 : 8);
+  if (pw_env == 0 && pw == 8 && !hp.a_tmem && !hp.a_pre && (pw10 == 2 || (pw10 == 1 && g.epi != CVAE_EPI_DACT))) pw = 10;
   const size_t a_bytes = hp.a_tmem ? (size_t)kHRawStages * (pw >= 8 ? 256 * 80 : 128 * 144) : (size_t)hp.na * hp.a_stage;
   while (hp.NB > 2 && a_bytes + (size_t)hp.NB * hp.bslot_bytes + stat_bytes + 1024 > kHMaxDyn) --hp.NB;   // shallower weight ring
   size_t smem = a_bytes + (size_t)hp.NB * hp.bslot_bytes;
@@ -1037,13 +1039,15 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_halo_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_halo_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess)
+        cudaFuncSetAttribute(conv_halo_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_halo_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess)
       return CVAE_ERR_LAUNCH;
     attr_set = true;
   }
   if (smem > kHMaxDyn) return 1;
   const int grid = (int)min(total, (long long)kNumSMs);
   if (pw == 6) conv_halo_tc_kernel<6><<<grid, h_threads(6), smem, st>>>(g, hp, (int)total);
+  else if (pw == 10) conv_halo_tc_kernel<10><<<grid, h_threads(10), smem, st>>>(g, hp, (int)total);
   else conv_halo_tc_kernel<8><<<grid, h_threads(8), smem, st>>>(g, hp, (int)total);
   if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); return CVAE_ERR_LAUNCH; }
   return CVAE_OK;
