@@ -447,7 +447,7 @@ def small_config_line(torch, name, world, rank, dist, barrier, steps, hbm, with_
     B = cfg["B"]
     n0 = L.launch_count
     gs, pin, loss_of, tr = _small_trainer(torch, name, dist)
-    launches = (L.launch_count - n0) // 4          # 3 eager warm-up steps + the captured one
+    launches = getattr(gs, "captured_launches", (L.launch_count - n0) // 4)     # C-ABI calls recorded in the captured step
     gs.load(**{k: v.cuda() for k, v in pin.items()})
     for _ in range(5):
         gs.replay()
@@ -553,7 +553,7 @@ def run_native(args):
     pin = [a.pin_memory() for a in (x, m, t, eps)]
     n0 = L.launch_count
     trainer.capture(B, H, W, warmup=2)
-    per_step_calls = (L.launch_count - n0) // 3     # 2 eager warm-up steps + 1 captured step
+    per_step_calls = getattr(trainer, "captured_launches", (L.launch_count - n0) // 3)     # C-ABI calls recorded in the captured step
     trainer.load_batch(*[a.cuda() for a in (x, m, t, eps)])
     torch.cuda.synchronize()
 

@@ -33,9 +33,12 @@ class GraphedStep:
             for t, v in zip(state, snap):
                 t.copy_(v)
         gc.collect()                       # stale autograd graphs remember the warm-up stream (see VesselTrainer.capture)
+        from . import _lib as L
         self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count
         with torch.cuda.graph(self.graph):
             self.outputs = fn()
+        self.captured_launches = L.launch_count - n0       # C-ABI calls recorded in the graph (bench.py: gpu_launches)
 
     def load(self, **tensors):
         for k, v in tensors.items():

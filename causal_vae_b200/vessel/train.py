@@ -230,10 +230,13 @@ class VesselTrainer:
         prio = self.side is not None and os.environ.get("CVAE_GRAPH_PRIO", "0") == "1"
         self.graph = torch.cuda.CUDAGraph(keep_graph=True) if prio else torch.cuda.CUDAGraph()
         self._prio_exec = None
+        from .. import _lib as _L
+        n0 = _L.launch_count
         with torch.cuda.graph(self.graph):
             self.static_losses = self._fwd_bwd(**self.static)
             self._allreduce()
             self.opt.step()
+        self.captured_launches = _L.launch_count - n0      # C-ABI calls recorded in the graph = kernels of ours per replay
         # the capture pass itself does not execute; nothing to undo
         if prio:
             from .. import _lib as L

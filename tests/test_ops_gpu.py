@@ -117,6 +117,8 @@ CONVT_CASES = [
     (32, 1, 4, 2, 1, 0, 14, 14, 3),   # mnist dec_conv.2 (Cout = 1)
     (32, 1, 4, 2, 1, 0, 32, 32, 70),  # causal_cascade dec_conv.6 at a training-sized batch: 4x4 tile kernels (input gradient, wgrad)
     (32, 1, 4, 2, 1, 0, 25, 22, 130), # the same with ragged tiles
+    (16, 1, 4, 2, 1, 0, 12, 12, 2),   # four-phase ConvT(C -> 1) forward kernel with 4 / 16 threads per position
+    (64, 1, 4, 2, 1, 0, 9, 7, 2),
 ]
 
 
