@@ -20,6 +20,31 @@ constexpr int kNumSMs = 148;  // B200
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// a[0..3] += x * w: as two packed fma.rn.f32x2 (FFMA2: two FMAs per instruction on 64-bit register pairs, the same
+// round-to-nearest results).  nvcc never emits FFMA2 by itself; measured on this B200 (scripts/ffma2_probe.cu) scalar FFMA
+// reaches 112 FMA/clk/SM, the packed form 127 with half the issue slots -- and these kernels spend ~40 % of their issue
+// slots on the loads, address arithmetic and moves between the FMAs.  -DCVAE_FFMA2=0 restores the scalar form.
+#ifndef CVAE_FFMA2
+#define CVAE_FFMA2 1
+#endif
+__device__ __forceinline__ void fma4(float (&a)[4], const float x, const float4& w) {
+#if CVAE_FFMA2
+  unsigned long long xx, w01, w23, a01, a23;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w01) : "f"(w.x), "f"(w.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w23) : "f"(w.z), "f"(w.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a01) : "f"(a[0]), "f"(a[1]));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a23) : "f"(a[2]), "f"(a[3]));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a01) : "l"(xx), "l"(w01));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a23) : "l"(xx), "l"(w23));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a[0]), "=f"(a[1]) : "l"(a01));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a[2]), "=f"(a[3]) : "l"(a23));
+#else
+  a[0] = fmaf(x, w.x, a[0]); a[1] = fmaf(x, w.y, a[1]); a[2] = fmaf(x, w.z, a[2]); a[3] = fmaf(x, w.w, a[3]);
+#endif
+}
+
+
 struct XformDev {
   const float* scale;
   const float* shift;

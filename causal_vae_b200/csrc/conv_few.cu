@@ -18,10 +18,6 @@ namespace cvae {
 
 constexpr int kFewThreads = 256;
 
-__device__ __forceinline__ void fma4(float (&a)[4], const float x, const float4& w) {
-  a[0] = fmaf(x, w.x, a[0]); a[1] = fmaf(x, w.y, a[1]); a[2] = fmaf(x, w.z, a[2]); a[3] = fmaf(x, w.w, a[3]);
-}
-
 struct FewEpi {    // per-thread statistics of 4 channels (fp32 within a tile, fp64 across tiles)
   float f1[4], f2[4];
   double d1[4], d2[4];

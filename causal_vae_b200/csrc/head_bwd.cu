@@ -102,13 +102,13 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, const 
       float av[4], o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 4; ++j) av[j] = z[j] > 0.f ? z[j] : z[j] * slope;
+      const float4 av4 = make_float4(av[0], av[1], av[2], av[3]);
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const float gt = gp[(2 - t / 3) * GC + (2 - t % 3)];      // G_t(q) = g[q - (kh - 1, kw - 1)] in halo-tile coordinates
         const float4 wt = sW[t * NB + c4];
-        o[0] = fmaf(gt, wt.x, o[0]); o[1] = fmaf(gt, wt.y, o[1]); o[2] = fmaf(gt, wt.z, o[2]); o[3] = fmaf(gt, wt.w, o[3]);
-        acc[t][0] = fmaf(av[0], gt, acc[t][0]); acc[t][1] = fmaf(av[1], gt, acc[t][1]);
-        acc[t][2] = fmaf(av[2], gt, acc[t][2]); acc[t][3] = fmaf(av[3], gt, acc[t][3]);
+        fma4(o, gt, wt);                                          // o[0..3] += gt * w_t[0..3]    (packed FMAs: common.cuh)
+        fma4(acc[t], gt, av4);                                    // acc[t][0..3] += a[0..3] * gt
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

@@ -183,11 +183,11 @@ __device__ __forceinline__ void lr_fma_chunk(const float (*xs)[68], const float 
     const float4 w0 = *reinterpret_cast<const float4*>(&ws[kk][4 * tx]);
     const float4 w1 = *reinterpret_cast<const float4*>(&ws[kk][64 + 4 * tx]);
     const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+    for (int i = 0; i < 4; ++i) {                     // 4 x 8 block as eight packed FMAs per row pair (common.cuh)
+      fma4(*reinterpret_cast<float(*)[4]>(&acc[i][0]), xv[i], w0);
+      fma4(*reinterpret_cast<float(*)[4]>(&acc[i][4]), xv[i], w1);
+    }
   }
 }
 

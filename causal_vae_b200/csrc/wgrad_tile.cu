@@ -178,10 +178,16 @@ wgrad_tile_kernel(const __grid_constant__ WgradArgs a, const int patches, const 
 #pragma unroll
         for (int w = 0; w < KW; ++w) {
           const VecT<VA> g = ldv<VA>(gp + w * CA);
+          if constexpr (VB == 4) {                     // four columns per row value: two packed FMAs (common.cuh)
+            const float4 d4 = make_float4(d.v[0], d.v[1], d.v[2], d.v[3]);
 #pragma unroll
-          for (int i = 0; i < VA; ++i)
+            for (int i = 0; i < VA; ++i) fma4(acc[w][i], g.v[i], d4);
+          } else {
 #pragma unroll
-            for (int j = 0; j < VB; ++j) acc[w][i][j] = fmaf(g.v[i], d.v[j], acc[w][i][j]);
+            for (int i = 0; i < VA; ++i)
+#pragma unroll
+              for (int j = 0; j < VB; ++j) acc[w][i][j] = fmaf(g.v[i], d.v[j], acc[w][i][j]);
+          }
         }
       }
     }
