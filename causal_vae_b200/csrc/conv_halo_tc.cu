@@ -985,10 +985,13 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   if (hp.bslot_bytes == 32768 && bn < 128) hp.NB = 2;
   hp.tiles_h = (hp.Hq + kHTH - 1) / kHTH; hp.tiles_w = (hp.Wq + kHTW - 1) / kHTW; hp.tiles_n = g.Cd / bn;
   {
-    // A tile is a 16 x 8 patch of ONE image: feature maps much smaller than that (4 x 4 in the causal_cascade stack:
-    // 16 of 128 MMA rows in use, its ConvTranspose2d 256->128 ran 631 us) go to the per-tap gather kernel, whose
-    // 128-row tiles run across images (CVAE_HALO_MIN_UTIL: least percentage of tile rows in use, default 40)
-    static const int min_util = [] { const char* e = getenv("CVAE_HALO_MIN_UTIL"); return e ? atoi(e) : 40; }();
+    // A tile is a 16 x 8 patch of ONE image: feature maps smaller than that (4 x 4 in the causal_cascade stack: 16 of
+    // 128 MMA rows in use, its ConvTranspose2d 256->128 ran 631 us; 8 x 8: half of the rows, and a scatter plan with
+    // cross-term accumulators then also splits 64 output channels into two n-tiles -- cascade dec_conv.2 forward 172 us
+    // for the FLOPs its 4 x 4 neighbour does in 46 us) go to the per-tap gather kernel, whose 128-row tiles run across
+    // images (CVAE_HALO_MIN_UTIL: least percentage of tile rows in use, default 60; measured 40 -> 60: cascade step
+    // 2.27 -> 2.12 ms, vessel step 7.610 -> 7.596 ms, latent_translator and mnist unchanged)
+    static const int min_util = [] { const char* e = getenv("CVAE_HALO_MIN_UTIL"); return e ? atoi(e) : 60; }();
     if (g.wtaps >= 2 && 100ll * hp.Hq * hp.Wq < (long long)min_util * hp.tiles_h * hp.tiles_w * kHTH * kHTW) return 1;
   }
   long long total = (long long)g.N * hp.tiles_h * hp.tiles_w * hp.tiles_n;
