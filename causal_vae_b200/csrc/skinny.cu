@@ -319,14 +319,10 @@ __global__ void __launch_bounds__(kThreads) conv_cs1_tile_kernel(const __grid_co
       const int r = p / TW, c = p % TW, qh = h0 + r, qw = w0 + c;
       if (qh >= P.Hq || qw >= P.Wq) continue;
       const float* gp = sG + (r * IS) * GC + c * IS;
-      float4 acc = bias;
+      float o[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const float v = gp[toff[t]];
-        acc.x = fmaf(v, w[t].x, acc.x); acc.y = fmaf(v, w[t].y, acc.y); acc.z = fmaf(v, w[t].z, acc.z); acc.w = fmaf(v, w[t].w, acc.w);
-      }
+      for (int t = 0; t < NT; ++t) fma4(o, gp[toff[t]], w[t]);          // two packed FMAs per tap (common.cuh)
       const size_t off = (((size_t)n * a.Hd + qh) * a.Wd + qw) * C + c0;
-      float o[4] = {acc.x, acc.y, acc.z, acc.w};
       if (a.epi == CVAE_EPI_STATS) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { f1[j] += o[j]; f2[j] = fmaf(o[j], o[j], f2[j]); }
