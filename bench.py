@@ -26,13 +26,13 @@ B_PER_GPU = 64
 FLOP_PER_SAMPLE = 5.057e9          # fwd+bwd matmul/conv FLOPs (2*MAC), measured on the reference
 BYTES_PER_SAMPLE = 77e6 + 8.8e6    # irreducible fp32 activation + parameter/optimizer traffic
 # dram__bytes_read.sum + dram__bytes_write.sum of the probed launch (stem.3 input gradient, B = 64) from the ncu launch
-# list of the whole step, profiles/r2_step_traffic.csv (launch id 381: 201.7 MB read + 95.8 MB written); algorithmic bytes
+# list of the whole step, profiles/r2_step_traffic.csv (launch id 346: 201.7 MB read + 94.4 MB written); algorithmic bytes
 # of that launch: 335.5e6 (part of the re-read reference tensor is served by L2)
-NCU_TRAFFIC_BYTES = 297.5e6
-NCU_TRAFFIC_SOURCE = "profiles/r2_step_traffic.csv id 381 (dram__bytes_read.sum + dram__bytes_write.sum, conv_halo_tc_kernel<6>)"
-# whole-step DRAM traffic of the same capture (389 launches, one eager step at B = 64): 7.711 GB read + 1.362 GB written
-STEP_TRAFFIC_BYTES = 9.073e9
-STEP_TRAFFIC_SOURCE = "profiles/r2_step_traffic_summary.txt (sum over the 389 launches of one step; cold-cache, serialised)"
+NCU_TRAFFIC_BYTES = 296.1e6
+NCU_TRAFFIC_SOURCE = "profiles/r2_step_traffic.csv id 346 (dram__bytes_read.sum + dram__bytes_write.sum, conv_halo_tc_kernel<6>)"
+# whole-step DRAM traffic of the same capture (354 launches, one eager step at B = 64): 7.472 GB read + 1.297 GB written
+STEP_TRAFFIC_BYTES = 8.769e9
+STEP_TRAFFIC_SOURCE = "profiles/r2_step_traffic_summary.txt (sum over the 354 launches of one step; cold-cache, serialised)"
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -670,11 +670,11 @@ def run_native(args):
                      "traffic_source": NCU_TRAFFIC_SOURCE},
         "roofline_stream": {"bound": "hbm", "achieved": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9, "peak": hbm,
                             "unit": "GB/s", "frac": probe["few_bytes"] / (probe["few_ms"] * 1e-3) / 1e9 / hbm,
-                            "traffic": 281.9e6,
+                            "traffic": 280.7e6,
                             "kernel": "convt16_up_kernel (fp32 SIMT tile kernel, csrc/conv_few.cu) on decoder.12 forward, "
                                       "ConvTranspose2d(16->16) 128^2 -> 256^2, B=64: the largest tensors of the step",
                             "bytes_per_launch": probe["few_bytes"], "ms_per_launch": probe["few_ms"],
-                            "traffic_source": "profiles/r2_step_traffic.csv (convt16_up_kernel: 67.3 MB read + 214.6 MB written)"},
+                            "traffic_source": "profiles/r2_step_traffic.csv (convt16_up_kernel: 67.3 MB read + 213.4 MB written)"},
         "roofline_tensor": {"bound": "tensor", "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s",
                             "frac": ach_tf / bf16_burst, "tf32_gemm_peak_tflops": tf32_peak,
                             "frac_of_tf32_gemm_peak": (ach_tf / tf32_peak) if tf32_peak else None,
