@@ -87,10 +87,11 @@ __device__ unsigned long long g_halo_dbg[16];
 __device__ __forceinline__ void hbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct HTile { int n, h0, w0, n0, ks; };
+template <bool KS>
 __device__ __forceinline__ HTile h_decode(const HaloPlan& p, int t) {
   HTile o;
   o.ks = 0;
-  if (p.ksplit > 1) { o.ks = t % p.ksplit; t /= p.ksplit; }      // work item = (tile, K slice)
+  if constexpr (KS) { o.ks = t % p.ksplit; t /= p.ksplit; }       // work item = (tile, K slice)
   o.n0 = (t % p.tiles_n) * p.BN;
   int sp = t / p.tiles_n;
   o.w0 = (sp % p.tiles_w) * kHTW; sp /= p.tiles_w;
@@ -99,7 +100,10 @@ __device__ __forceinline__ HTile h_decode(const HaloPlan& p, int t) {
   return o;
 }
 
-template <int PW>
+// KS: split-K instantiation (Linear launches with few tiles, see launch_conv_halo_tc).  A template parameter, not a run-time
+// branch: with `if (p.ksplit > 1) atomicAdd ... else store` in the epilogue the compiler predicated the two atomics into
+// EVERY launch (ncu on the stem.3 input gradient: 2.2 M issued, predicated-off instructions; 148 -> 158 us).
+template <int PW, bool KS = false>
 __global__ void __launch_bounds__(h_threads(PW), 1)
 conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant__ HaloPlan p, const int total) {
   extern __shared__ uint8_t dsm_raw[];
@@ -113,6 +117,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN, NB = p.NB;
   const int KB = (a.Cs + 31) >> 5;
+  const int ksplit = KS ? p.ksplit : 1;             // compile-time 1 in the ordinary instantiations
   const uint32_t bstage = (uint32_t)p.bslot_bytes;
   const uint32_t acc_cols = (uint32_t)(a.nphase * BN * (p.xacc ? 2 : 1));
   const uint32_t a_cols = p.a_tmem ? (uint32_t)(kHNAT * 64) : 0u;     // A ring in tensor memory: hi | lo, 32 columns each
@@ -166,14 +171,14 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       const uint32_t raw_warp = smem_u32(dsm_gen + (size_t)NB * bstage + (size_t)(tid - lane) * kPitch);
       const int crow = lane / kCh, cch = lane % kCh;   // this lane's row (within an instruction) and chunk
       const long long Mrows = (long long)a.Hs * 8;     // Linear view: ONE image of M / 8 x 8 positions, a tile = 128 consecutive rows
-      const int kbper = KB / p.ksplit;                 // k-blocks of one work item (host: KB % ksplit == 0)
+      const int kbper = KB / ksplit;                   // k-blocks of one work item (host: KB % ksplit == 0)
       int ti = blockIdx.x, kbi = 0, kbend = 0;         // next (tile, k-block) to request; end of the item's K slice
       const float* wbase = nullptr;                    // first row of this warp quarter in tile ti
       int nvalid = 0;                                  // rows of the quarter inside the matrix
       auto set_tile = [&](int t) {
         wbase = nullptr; nvalid = 0;
         if (t >= total) return;
-        const HTile tl = h_decode(p, t);
+        const HTile tl = h_decode<KS>(p, t);
         kbi = tl.ks * kbper; kbend = kbi + kbper;
         const long long r0 = (long long)tl.h0 * 8 + q * 32;
         wbase = a.src + (size_t)r0 * a.Cs;
@@ -203,7 +208,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       uint32_t it = 0;
       T_DECL
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const HTile tl = h_decode(p, t);
+        const HTile tl = h_decode<KS>(p, t);
         const int qh = tl.h0 + (row >> 3), qw = tl.w0 + (row & 7);
         const bool rok = qh < a.Hs && qw < a.Ws;
         for (int kb = tl.ks * kbper; kb < (tl.ks + 1) * kbper; ++kb, ++it) {
@@ -289,7 +294,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
     HTile ld_tl{0, 0, 0, 0, 0};
     auto load_stage = [&](const Stage& st, float4 (&v)[kHItems]) -> uint32_t {
       uint32_t okm = 0;
-      if (st.t != ld_t) { ld_tl = h_decode(p, st.t); ld_t = st.t; }
+      if (st.t != ld_t) { ld_tl = h_decode<KS>(p, st.t); ld_t = st.t; }
       const int c = st.kb * 32 + chunk * 4;
       const bool cok = c < a.Cs;
       const HaloPlane& P = p.plane[st.pl];
@@ -399,7 +404,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         tc_fence_after();
         const uint32_t d_base = tmem + acc * acc_cols;
         uint32_t started = 0, startedx = 0;
-        const int kbper = KB / p.ksplit, kb0 = p.ksplit > 1 ? (t % p.ksplit) * kbper : 0;
+        const int kbper = KB / ksplit, kb0 = KS ? (t % ksplit) * kbper : 0;
         for (int kb = kb0; kb < kb0 + kbper; ++kb) {
           const int ksteps = min(32, a.Cs - kb * 32) >> 3;
           for (int pl = 0; pl < p.nplanes; ++pl, ++ita) {
@@ -526,7 +531,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
       if (pf_on) {
         __syncwarp();
         if (a.epi == CVAE_EPI_DACT && t % p.tiles_n == 0) {
-          const HTile tl = h_decode(p, t);
+          const HTile tl = h_decode<KS>(p, t);
           const int oh0 = tl.h0 * a.os, ow0 = tl.w0 * a.os;
           const int npx = min(kHTW * a.os, a.Wd - ow0);
           const uint32_t bytes = (uint32_t)(npx * a.Cd) * 4u;
@@ -539,7 +544,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         }
         const int tn = t + gridDim.x;
         if (tn < total && !p.a_tmem && tn % p.tiles_n == 0) {
-          const HTile tl = h_decode(p, tn);
+          const HTile tl = h_decode<KS>(p, tn);
           // union of the planes' staged windows (plane rows / columns are `is` apart)
           int r_lo = 1 << 30, r_hi = -(1 << 30), c_lo = 1 << 30, c_hi = -(1 << 30);
           for (int pl = 0; pl < p.nplanes; ++pl) {
@@ -558,7 +563,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
         __syncwarp();
       }
       if (ld_leader) {
-        const int tt = t / p.ksplit, kbper = KB / p.ksplit, kb0 = (t % p.ksplit) * kbper;
+        const int tt = t / ksplit, kbper = KB / ksplit, kb0 = (t % ksplit) * kbper;
         const int n0 = (tt % p.tiles_n) * BN;
         const int mt = tt / p.tiles_n;                 // a_pre: 128-row tile of the packed A image
         for (int kb = kb0; kb < kb0 + kbper; ++kb)
@@ -629,12 +634,12 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
     const int ostep = a.os * a.Wd;                    // pixel distance between a thread's consecutive rows
     double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
     struct Unit { int obase, vmask, col, t, ui, ks; };
-    HTile ctl = h_decode(p, blockIdx.x);
+    HTile ctl = h_decode<KS>(p, blockIdx.x);
     int ct = blockIdx.x;
     auto unit_of = [&](int t, int ui) -> Unit {
       Unit u{0, 0, 0, t, ui, 0};
       if (t >= total || ui >= nunits) return u;
-      if (t != ct) { ctl = h_decode(p, t); ct = t; }
+      if (t != ct) { ctl = h_decode<KS>(p, t); ct = t; }
       u.ks = ctl.ks;
       const int phs = ui >> upp_sh, hf = ui - (phs << upp_sh);
       u.col = ctl.n0 + hf * 16 + cpair;
@@ -698,7 +703,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 2; ++g) {                 // the thread's two channel pairs: col + 8g, col + 8g + 1
           float2 bias = make_float2(0.f, 0.f), esc = make_float2(1.f, 1.f), esh = bias, ece = bias;
-          if (a.bias != nullptr && cur.ks == 0) bias = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * g));   // once per tile
+          if (a.bias != nullptr && (!KS || cur.ks == 0)) bias = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * g));   // once per tile
           if (a.e_affine) {
             esc = __ldg(reinterpret_cast<const float2*>(a.e_scale + col + 8 * g));
             esh = __ldg(reinterpret_cast<const float2*>(a.e_shift + col + 8 * g));
@@ -731,7 +736,7 @@ conv_halo_tc_kernel(const __grid_constant__ GatherArgs a, const __grid_constant_
                 f1[2 * g + 1] += x1; f2[2 * g + 1] = fmaf(x1, rc1, f2[2 * g + 1]);
               }
               float* op = a.dst + (size_t)(cur.obase + r * ostep) * a.Cd + col + 8 * g;
-              if (p.ksplit > 1) { atomicAdd(op, x0); atomicAdd(op + 1, x1); }       // K slices meet in the pre-zeroed output
+              if constexpr (KS) { atomicAdd(op, x0); atomicAdd(op + 1, x1); }       // K slices meet in the pre-zeroed output
               else *reinterpret_cast<float2*>(op) = make_float2(x0, x1);
             }
           }
@@ -1043,13 +1048,15 @@ int launch_conv_halo_tc(const GatherArgs& g_in, cudaStream_t st) {
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_halo_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess ||
         cudaFuncSetAttribute(conv_halo_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_halo_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess)
+        cudaFuncSetAttribute(conv_halo_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_halo_tc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHMaxDyn) != cudaSuccess)
       return CVAE_ERR_LAUNCH;
     attr_set = true;
   }
   if (smem > kHMaxDyn) return 1;
   const int grid = (int)min(total, (long long)kNumSMs);
-  if (pw == 6) conv_halo_tc_kernel<6><<<grid, h_threads(6), smem, st>>>(g, hp, (int)total);
+  if (hp.ksplit > 1) conv_halo_tc_kernel<8, true><<<grid, h_threads(8), smem, st>>>(g, hp, (int)total);     // Linear mode: pw == 8
+  else if (pw == 6) conv_halo_tc_kernel<6><<<grid, h_threads(6), smem, st>>>(g, hp, (int)total);
   else if (pw == 10) conv_halo_tc_kernel<10><<<grid, h_threads(10), smem, st>>>(g, hp, (int)total);
   else conv_halo_tc_kernel<8><<<grid, h_threads(8), smem, st>>>(g, hp, (int)total);
   if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); return CVAE_ERR_LAUNCH; }
